@@ -1,0 +1,90 @@
+"""In-tree build of libgauxc_b200.so (nvcc, sm_100a only) and of the CPU oracle.
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container; the .so
+travels to the GPU box with the repo snapshot (it is git-ignored, not gpurun-ignored).
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libgauxc_b200.so")
+
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-Wall,-Wno-unknown-pragmas",
+          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+
+SOURCES = [
+    "host/core.cxx", "host/grid.cxx", "host/load_balancer.cxx", "host/c_api.cxx",
+    "host/device_integrator.cu",
+    "cuda/collocation.cu", "cuda/contraction.cu", "cuda/ssf_weights.cu", "cuda/probe.cu",
+]
+
+
+def _deps_mtime():
+    m = 0.0
+    for d, _, fs in os.walk(CSRC):
+        for f in fs:
+            if f.endswith((".hpp", ".cuh", ".h", ".inc")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    m = max(m, os.path.getmtime(os.path.join(ROOT, "include", "gauxc_b200.h")))
+    return m
+
+
+def _compile(src, hdr_m, verbose):
+    obj = os.path.join(BUILD, src.replace("/", "_") + ".o")
+    srcp = os.path.join(CSRC, src)
+    if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), hdr_m):
+        return obj, ""
+    cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-c", srcp, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    log = r.stdout + r.stderr
+    with open(obj + ".log", "w") as f:
+        f.write(log)
+    return obj, log
+
+
+def build_library(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    if force:
+        for f in os.listdir(BUILD):
+            os.remove(os.path.join(BUILD, f))
+    hdr_m = _deps_mtime()
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        res = list(ex.map(lambda s: _compile(s, hdr_m, verbose), SOURCES))
+    objs = [o for o, _ in res]
+    if verbose:
+        for _, log in res:
+            if log:
+                print(log)
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return LIB
+
+
+def build_oracle(force=False):
+    """Compile oracle/ (CPU restatement) and, when /root/reference is present, oracle/_ref."""
+    odir = os.path.join(ROOT, "oracle")
+    r = subprocess.run(["make", "-C", odir] + (["-B"] if force else []), capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return os.path.join(odir, "liboracle.so")
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    print(build_library(force=force, verbose="-v" in sys.argv))
+    if "--no-oracle" not in sys.argv:
+        print(build_oracle(force=force))

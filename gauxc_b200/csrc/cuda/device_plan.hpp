@@ -1,0 +1,71 @@
+// Device-resident work description shared by the host integrator and the sm_100a kernels.
+//
+// Layout in HBM (all FP64 unless noted), replacing XCDeviceData / XCDeviceTask
+// (src/xc_integrator/xc_data/device/xc_device_task.hpp:16-242):
+//   * points/weights: SoA px,py,pz,w over ALL local points, ordered task by task
+//     (tasks sorted by npts*nbe descending like the reference,
+//      incore_replicated_xc_device_integrator_exc_vxc.hpp:254-257).  Resident across calls.
+//   * a task is cut into TILES of <= TP consecutive points that share the task's shell list.
+//   * per batch of tiles a workspace holds, per tile, NMAT matrices [nbe][TP]
+//     (point index fastest): B, (dBx,dBy,dBz for GGA), Z; and per point rho, drho(3).
+#pragma once
+#include <cstdint>
+
+namespace gxb {
+
+constexpr int TP = 128;  // points per tile
+
+struct DevShell {
+  double x, y, z;
+  int l, pure, nprim, prim_off;  // prim_off: offset into the alpha/coeff arrays
+  int ao_off, nfunc;             // first global AO, functions in this shell
+  int pad0, pad1;
+};
+
+struct DevTask {
+  int shell_off, nshells;  // into task_shells / task_shell_bf
+  int ao_off, nbe;         // into task_ao (local mu -> global AO)
+  int pt_off, npts;        // into the point arrays
+  int iParent, pad;
+};
+
+struct DevTile {
+  int task;
+  int pt_off;  // global point offset of the tile's first point
+  int npts;    // <= TP
+  int pad;
+  int64_t ws_off;  // offset (in doubles) of the tile's matrices inside the batch workspace
+};
+
+// one unit of the VXC rank update: output block (mblk,nblk) of task `task`, accumulated
+// over tiles [tile_begin, tile_end) of the current batch
+struct VxcItem {
+  int task, mblk, nblk, tile_begin, tile_end, pad0, pad1, pad2;
+};
+
+struct PlanView {
+  // static
+  const DevShell* shells;
+  const double* prim_alpha;
+  const double* prim_coeff;
+  const DevTask* tasks;
+  const int* task_shells;    // global shell index
+  const int* task_shell_bf;  // local AO offset of each listed shell
+  const int* task_ao;        // local mu -> global AO index
+  const double *px, *py, *pz;
+  double* w;
+  int nbf;
+};
+
+enum XcKind : int { XC_LDA = 0, XC_GGA = 1 };
+
+// functional = sum_k coeff_k * kernel_k  (ExchCXX XCFunctional semantics)
+enum KernelId : int { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5 };
+struct FunctionalDesc {
+  int nkern;
+  int is_gga;
+  int kern[4];
+  double coeff[4];
+};
+
+}  // namespace gxb

@@ -1,0 +1,785 @@
+// Device execution space: runtime, device-resident task plan, SSF weights driver,
+// EXC/VXC integrator, NCCL reduction driver.  Host orchestration only -- every numerical
+// stage is one of the kernels in ../cuda.  There is deliberately no CPU fallback: without a
+// CUDA device every entry point here throws.
+#include "xc_integrator.hpp"
+#include "../cuda/kernels.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <nccl.h>
+#include <numeric>
+
+namespace GauXC {
+
+#define CUDA_CHECK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      GAUXC_GENERIC_EXCEPTION(std::string("CUDA Failed: ") + cudaGetErrorString(_e) + \
+                              " in " #expr);                                          \
+  } while (0)
+
+static void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    GAUXC_GENERIC_EXCEPTION(
+        "No CUDA device: the Device execution space has no CPU fallback in this build");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// runtime
+// ------------------------------------------------------------------------------------
+DeviceRuntimeEnvironment::DeviceRuntimeEnvironment(double fill_fraction)
+    : fill_fraction_(fill_fraction) {
+  if (fill_fraction <= 0. || fill_fraction > 1.) GAUXC_GENERIC_EXCEPTION("Invalid Fill Fraction");
+}
+DeviceRuntimeEnvironment::DeviceRuntimeEnvironment(void* mem, size_t sz)
+    : fill_fraction_(0.), user_mem_(mem), user_mem_sz_(sz) {}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t cnt) {
+    release();
+    n = cnt;
+    if (cnt) CUDA_CHECK(cudaMalloc((void**)&p, cnt * sizeof(T)));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s = 0) {
+    alloc(v.size());
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// device plan: everything about the local tasks that does not change between calls
+// ------------------------------------------------------------------------------------
+struct Schedule {
+  // per xc-kind batching of the tiles into workspace-sized groups
+  std::vector<gxb::DevTile> tiles;  // with ws_off
+  struct Batch {
+    int tile_begin, tile_end, item_begin, item_end;
+  };
+  std::vector<Batch> batches;
+  std::vector<gxb::VxcItem> items;
+  DevBuf<gxb::DevTile> d_tiles;
+  DevBuf<gxb::VxcItem> d_items;
+  size_t ws_doubles = 0;
+  int max_batch_tiles = 0;
+};
+
+struct DevicePlan {
+  int nbf = 0, natoms = 0;
+  size_t npts = 0;
+  std::vector<gxb::DevTask> tasks;
+  std::vector<gxb::DevTile> tiles;  // ws_off unset; used by the weights kernel
+  DevBuf<gxb::DevShell> d_shells;
+  DevBuf<double> d_alpha, d_coeff;
+  DevBuf<gxb::DevTask> d_tasks;
+  DevBuf<gxb::DevTile> d_tiles;
+  DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
+  DevBuf<double> d_px, d_py, d_pz, d_w;
+  DevBuf<double> d_atoms, d_rab, d_dist_nearest;
+  double f_dense = 0., sum_nbe_npts = 0.;
+  std::map<int, std::shared_ptr<Schedule>> schedules;  // key: nmat
+  size_t schedule_ws_bytes = 0;
+
+  gxb::PlanView view() const {
+    gxb::PlanView v{};
+    v.shells = d_shells.p;
+    v.prim_alpha = d_alpha.p;
+    v.prim_coeff = d_coeff.p;
+    v.tasks = d_tasks.p;
+    v.task_shells = d_task_shells.p;
+    v.task_shell_bf = d_task_shell_bf.p;
+    v.task_ao = d_task_ao.p;
+    v.px = d_px.p;
+    v.py = d_py.p;
+    v.pz = d_pz.p;
+    v.w = d_w.p;
+    v.nbf = nbf;
+    return v;
+  }
+};
+
+static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
+  require_device();
+  auto plan = std::make_shared<DevicePlan>();
+  auto& tasks = lb.get_tasks();
+  const auto& basis = lb.basis();
+  const auto& bmap = lb.basis_map();
+  const auto& mol = lb.molecule();
+  const auto& meta = lb.molmeta();
+
+  if (basis.max_l() > 4) GAUXC_GENERIC_EXCEPTION("L > 4 Not Supported on Device");
+
+  // same ordering as the reference device driver (…exc_vxc.hpp:254-257, weights :41-44)
+  std::stable_sort(tasks.begin(), tasks.end(), [](const XCTask& a, const XCTask& b) {
+    return (a.points.size() * a.bfn_screening.nbe) > (b.points.size() * b.bfn_screening.nbe);
+  });
+
+  plan->nbf = bmap.nbf;
+  plan->natoms = (int)mol.size();
+
+  // shells
+  std::vector<gxb::DevShell> shells(basis.size());
+  std::vector<double> alpha, coeff;
+  for (size_t s = 0; s < basis.size(); ++s) {
+    auto& sh = basis[s];
+    gxb::DevShell d{};
+    d.x = sh.O[0]; d.y = sh.O[1]; d.z = sh.O[2];
+    d.l = sh.l; d.pure = sh.pure; d.nprim = sh.nprim;
+    d.prim_off = (int)alpha.size();
+    d.ao_off = bmap.shell_to_ao_range[s].first;
+    d.nfunc = sh.size();
+    for (int k = 0; k < sh.nprim; ++k) {
+      alpha.push_back(sh.alpha[k]);
+      coeff.push_back(sh.coeff[k]);
+    }
+    shells[s] = d;
+  }
+
+  size_t npts = 0;
+  for (auto& t : tasks) npts += t.points.size();
+  if (npts > (size_t)std::numeric_limits<int>::max()) GAUXC_GENERIC_EXCEPTION("Too Many Local Points");
+  plan->npts = npts;
+  std::vector<double> px(npts), py(npts), pz(npts), w(npts);
+  std::vector<int> task_shells, task_shell_bf, task_ao;
+  size_t off = 0;
+  for (size_t it = 0; it < tasks.size(); ++it) {
+    auto& t = tasks[it];
+    gxb::DevTask d{};
+    d.shell_off = (int)task_shells.size();
+    d.nshells = (int)t.bfn_screening.shell_list.size();
+    d.ao_off = (int)task_ao.size();
+    d.nbe = t.bfn_screening.nbe;
+    d.pt_off = (int)off;
+    d.npts = (int)t.points.size();
+    d.iParent = t.iParent;
+    int bf = 0;
+    for (int s : t.bfn_screening.shell_list) {
+      task_shells.push_back(s);
+      task_shell_bf.push_back(bf);
+      const auto r = bmap.shell_to_ao_range[s];
+      for (int a = r.first; a < r.second; ++a) task_ao.push_back(a);
+      bf += r.second - r.first;
+    }
+    if (bf != d.nbe) GAUXC_GENERIC_EXCEPTION("Inconsistent NBE in Task");
+    for (size_t i = 0; i < t.points.size(); ++i) {
+      px[off + i] = t.points[i][0];
+      py[off + i] = t.points[i][1];
+      pz[off + i] = t.points[i][2];
+      w[off + i] = t.weights[i];
+    }
+    for (int p0 = 0; p0 < d.npts; p0 += gxb::TP) {
+      gxb::DevTile tl{};
+      tl.task = (int)it;
+      tl.pt_off = d.pt_off + p0;
+      tl.npts = std::min(gxb::TP, d.npts - p0);
+      plan->tiles.push_back(tl);
+    }
+    plan->f_dense += 4. * double(d.nbe) * double(d.nbe) * double(d.npts);
+    plan->sum_nbe_npts += double(d.nbe) * double(d.npts);
+    off += t.points.size();
+    plan->tasks.push_back(d);
+  }
+
+  std::vector<double> atoms(3 * mol.size());
+  for (size_t a = 0; a < mol.size(); ++a) {
+    atoms[3 * a] = mol[a].x; atoms[3 * a + 1] = mol[a].y; atoms[3 * a + 2] = mol[a].z;
+  }
+
+  plan->d_shells.upload(shells);
+  plan->d_alpha.upload(alpha);
+  plan->d_coeff.upload(coeff);
+  plan->d_tasks.upload(plan->tasks);
+  plan->d_tiles.upload(plan->tiles);
+  plan->d_task_shells.upload(task_shells);
+  plan->d_task_shell_bf.upload(task_shell_bf);
+  plan->d_task_ao.upload(task_ao);
+  plan->d_px.upload(px);
+  plan->d_py.upload(py);
+  plan->d_pz.upload(pz);
+  plan->d_w.upload(w);
+  plan->d_atoms.upload(atoms);
+  plan->d_rab.upload(meta.rab);
+  plan->d_dist_nearest.upload(meta.dist_nearest);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  return plan;
+}
+
+std::shared_ptr<DevicePlan> get_device_plan(LoadBalancer& lb) {
+  lb.get_tasks();
+  if (!lb.device_cache || lb.device_cache_version != lb.version()) {
+    lb.device_cache = build_plan(lb);
+    lb.device_cache_version = lb.version();
+  }
+  return std::static_pointer_cast<DevicePlan>(lb.device_cache);
+}
+
+static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size_t ws_doubles,
+                                                int tiles_per_item) {
+  auto sc = std::make_shared<Schedule>();
+  sc->tiles = plan.tiles;
+  size_t cur = 0, ws_max = 0;
+  Schedule::Batch b{0, 0, 0, 0};
+  auto close_batch = [&](int tile_end) {
+    b.tile_end = tile_end;
+    // VXC items: runs of tiles of one task, cut into chunks, times the output blocks
+    b.item_begin = (int)sc->items.size();
+    int q = b.tile_begin;
+    while (q < b.tile_end) {
+      int e = q;
+      while (e < b.tile_end && sc->tiles[e].task == sc->tiles[q].task) ++e;
+      const int nbe = plan.tasks[sc->tiles[q].task].nbe;
+      const int mb = (nbe + 127) / 128, nb = (nbe + 63) / 64;
+      for (int c = q; c < e; c += tiles_per_item)
+        for (int im = 0; im < mb; ++im)
+          for (int in = 0; in < nb; ++in) {
+            gxb::VxcItem it{};
+            it.task = sc->tiles[q].task;
+            it.mblk = im;
+            it.nblk = in;
+            it.tile_begin = c - b.tile_begin;
+            it.tile_end = std::min(e, c + tiles_per_item) - b.tile_begin;
+            sc->items.push_back(it);
+          }
+      q = e;
+    }
+    b.item_end = (int)sc->items.size();
+    sc->batches.push_back(b);
+    sc->max_batch_tiles = std::max(sc->max_batch_tiles, b.tile_end - b.tile_begin);
+    ws_max = std::max(ws_max, cur);
+  };
+  for (int i = 0; i < (int)sc->tiles.size(); ++i) {
+    const size_t need = (size_t)nmat * plan.tasks[sc->tiles[i].task].nbe * gxb::TP;
+    if (need > ws_doubles) GAUXC_GENERIC_EXCEPTION("Device Workspace Too Small For One Tile");
+    if (cur + need > ws_doubles) {
+      close_batch(i);
+      b.tile_begin = i;
+      cur = 0;
+    }
+    sc->tiles[i].ws_off = (int64_t)cur;
+    cur += need;
+  }
+  if (!sc->tiles.empty()) close_batch((int)sc->tiles.size());
+  sc->ws_doubles = ws_max;
+  sc->d_tiles.upload(sc->tiles);
+  sc->d_items.upload(sc->items);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  return sc;
+}
+
+// ------------------------------------------------------------------------------------
+// functional names (tests/standalone_driver.cxx:428-433 uses ExchCXX functional_map)
+// ------------------------------------------------------------------------------------
+XCFunctional functional_from_string(const std::string& spec_in, bool polarized) {
+  std::string spec = spec_in;
+  std::transform(spec.begin(), spec.end(), spec.begin(), ::toupper);
+  XCFunctional f;
+  f.name = spec;
+  f.polarized = polarized;
+  auto set = [&](bool gga, std::initializer_list<std::pair<int, double>> ks) {
+    f.desc.is_gga = gga;
+    f.desc.nkern = 0;
+    for (auto& k : ks) {
+      f.desc.kern[f.desc.nkern] = k.first;
+      f.desc.coeff[f.desc.nkern] = k.second;
+      ++f.desc.nkern;
+    }
+  };
+  using namespace gxb;
+  if (spec == "SVWN5") set(false, {{K_SLATER_X, 1.}, {K_VWN5_C, 1.}});
+  else if (spec == "LDA" || spec == "SLATER") set(false, {{K_SLATER_X, 1.}});
+  else if (spec == "VWN5") set(false, {{K_VWN5_C, 1.}});
+  else if (spec == "SPW92") set(false, {{K_SLATER_X, 1.}, {K_PW92_C, 1.}});
+  else if (spec == "PBE") set(true, {{K_PBE_X, 1.}, {K_PBE_C, 1.}});
+  else if (spec == "PBE0") { set(true, {{K_PBE_X, 0.75}, {K_PBE_C, 1.}}); f.hyb_exx = 0.25; }
+  else GAUXC_GENERIC_EXCEPTION("Functional NYI in B200 path: " + spec_in);
+  if (polarized) GAUXC_GENERIC_EXCEPTION("Polarized (UKS/GKS) functionals NYI in B200 path");
+  return f;
+}
+
+// ------------------------------------------------------------------------------------
+// NCCL reduction driver (dlopen: the library must load on boxes without NCCL)
+// ------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  void load() {
+    if (h) return;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) GAUXC_GENERIC_EXCEPTION("NCCL FAILED: cannot load libnccl.so.2");
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy)
+      GAUXC_GENERIC_EXCEPTION("NCCL FAILED: missing symbols");
+  }
+};
+NcclApi g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_comm_rank = 0, g_comm_size = 1;
+
+struct NoopReductionDriver : ReductionDriver {
+  bool takes_host_memory() const override { return true; }
+  bool takes_device_memory() const override { return true; }
+  void allreduce_inplace(double*, size_t, ReductionOp, void*) override {}
+  int comm_size() const override { return 1; }
+};
+struct NCCLReductionDriver : ReductionDriver {
+  bool takes_host_memory() const override { return false; }
+  bool takes_device_memory() const override { return true; }
+  int comm_size() const override { return g_comm_size; }
+  void allreduce_inplace(double* data, size_t n, ReductionOp, void* stream) override {
+    if (!g_comm) GAUXC_GENERIC_EXCEPTION("NCCL FAILED: communicator not initialised");
+    auto r = g_nccl.AllReduce(data, data, n, ncclDouble, ncclSum, g_comm, (cudaStream_t)stream);
+    if (r != ncclSuccess) GAUXC_GENERIC_EXCEPTION("NCCL FAILED");
+  }
+};
+}  // namespace
+
+void nccl_get_unique_id(char out[128]) {
+  g_nccl.load();
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) GAUXC_GENERIC_EXCEPTION("NCCL FAILED");
+  std::memcpy(out, &id, 128);
+}
+void nccl_init_global(const char idb[128], int rank, int size) {
+  require_device();
+  g_nccl.load();
+  if (g_comm) nccl_finalize_global();
+  ncclUniqueId id;
+  std::memcpy(&id, idb, 128);
+  if (g_nccl.CommInitRank(&g_comm, size, id, rank) != ncclSuccess)
+    GAUXC_GENERIC_EXCEPTION("NCCL FAILED");
+  g_comm_rank = rank;
+  g_comm_size = size;
+}
+void nccl_finalize_global() {
+  if (g_comm) g_nccl.CommDestroy(g_comm);
+  g_comm = nullptr;
+  g_comm_size = 1;
+}
+
+std::shared_ptr<ReductionDriver> make_reduction_driver(const RuntimeEnvironment& rt,
+                                                       const std::string& name_in) {
+  std::string name = name_in;
+  std::transform(name.begin(), name.end(), name.begin(), ::toupper);
+  if (name == "BASICMPI")
+    GAUXC_GENERIC_EXCEPTION("BasicMPI ReductionDriver unavailable: no MPI in this build (use NCCL)");
+  if (name != "DEFAULT" && name != "NCCL")
+    GAUXC_GENERIC_EXCEPTION("ReductionDriver Not Recognized: " + name_in);
+  if (rt.comm_size() == 1) return std::make_shared<NoopReductionDriver>();
+  if (!g_comm || g_comm_size != rt.comm_size())
+    GAUXC_GENERIC_EXCEPTION("NCCL FAILED: call gauxc_b200_nccl_init before creating the integrator");
+  return std::make_shared<NCCLReductionDriver>();
+}
+
+// ------------------------------------------------------------------------------------
+// molecular weights
+// ------------------------------------------------------------------------------------
+MolecularWeights::MolecularWeights(ExecutionSpace ex, const std::string&, MolecularWeightsSettings s)
+    : ex_(ex), settings_(s) {
+  if (ex != ExecutionSpace::Device)
+    GAUXC_GENERIC_EXCEPTION("Host MolecularWeights are not part of the B200 build (Device only)");
+}
+
+void MolecularWeights::modify_weights(LoadBalancer& lb) {
+  // src/molecular_weights/device/device_molecular_weights.cxx:18-88
+  if (lb.state().modified_weights_are_stored)
+    GAUXC_GENERIC_EXCEPTION("Attempting to Overwrite Modified Weights");
+  if (settings_.weight_alg != XCWeightAlg::SSF)
+    GAUXC_GENERIC_EXCEPTION("Non-SSF Weights NYI for Device Integration");
+
+  auto plan = get_device_plan(lb);  // sorts tasks, uploads raw quadrature weights
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, 0));
+  gxb::launch_ssf_weights(plan->view(), plan->d_tiles.p, (int)plan->tiles.size(), plan->d_atoms.p,
+                          plan->d_rab.p, plan->d_dist_nearest.p, plan->natoms, 0);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(e1, 0));
+  // copy_weights_to_tasks: the host XCTask list stays the source of truth for other consumers
+  std::vector<double> w(plan->npts);
+  if (plan->npts)
+    CUDA_CHECK(cudaMemcpy(w.data(), plan->d_w.p, plan->npts * sizeof(double), cudaMemcpyDeviceToHost));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  timer_.add("MolecularWeights", ms);
+  auto& tasks = lb.get_tasks();
+  size_t off = 0;
+  for (auto& t : tasks) {
+    std::copy(w.begin() + off, w.begin() + off + t.weights.size(), t.weights.begin());
+    off += t.weights.size();
+    t.max_weight = t.weights.empty() ? 0. : *std::max_element(t.weights.begin(), t.weights.end());
+  }
+  lb.state().modified_weights_are_stored = true;
+  lb.state().weight_alg = XCWeightAlg::SSF;
+  // device copy is already current: no version bump
+}
+
+// ------------------------------------------------------------------------------------
+// integrator
+// ------------------------------------------------------------------------------------
+struct XCIntegrator::Impl {
+  cudaStream_t stream = nullptr;
+  DevBuf<double> dP, dVXC, d_ws, d_den, d_exc_part, d_nel_part, d_out2;
+  std::shared_ptr<DevicePlan> plan;
+  std::shared_ptr<Schedule> sched;
+  int sched_nmat = 0;
+  bool profile = false;
+  cudaEvent_t ev[6]{};
+  cudaEvent_t e_begin{}, e_lw0{}, e_lw1{}, e_end{};
+  double* h_out2 = nullptr;  // pinned
+  double* h_pin = nullptr;   // pinned staging for P / VXC
+  size_t h_pin_n = 0;
+  ~Impl() {
+    if (stream) cudaStreamDestroy(stream);
+    if (h_out2) cudaFreeHost(h_out2);
+    if (h_pin) cudaFreeHost(h_pin);
+  }
+};
+
+XCIntegrator::XCIntegrator(ExecutionSpace ex, const std::string& input_type,
+                           const std::string& integrator_kernel, const std::string& lwd_kernel,
+                           const std::string& reduction_kernel, std::shared_ptr<XCFunctional> func,
+                           std::shared_ptr<LoadBalancer> lb)
+    : func_(std::move(func)), lb_(std::move(lb)) {
+  auto up = [](std::string s) {
+    std::transform(s.begin(), s.end(), s.begin(), ::toupper);
+    return s;
+  };
+  if (ex != ExecutionSpace::Device)
+    GAUXC_GENERIC_EXCEPTION("Host XCIntegrator is not part of the B200 build (Device only)");
+  if (up(input_type) != "REPLICATED") GAUXC_GENERIC_EXCEPTION("INTEGRATOR TYPE NOT RECOGNIZED");
+  const auto ik = up(integrator_kernel);
+  if (ik != "DEFAULT" && ik != "INCORE")
+    GAUXC_GENERIC_EXCEPTION("Integrator Kernel Not Recognized: " + integrator_kernel);
+  const auto lk = up(lwd_kernel);
+  if (lk != "DEFAULT" && lk != "SCHEME1" && lk != "B200")
+    GAUXC_GENERIC_EXCEPTION("LWD Not Recognized: " + lwd_kernel);
+  if (!func_ || !lb_) GAUXC_GENERIC_EXCEPTION("Null Functional / LoadBalancer");
+  red_ = make_reduction_driver(lb_->runtime(), reduction_kernel);
+  require_device();
+  impl_ = std::make_shared<Impl>();
+  CUDA_CHECK(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
+  for (auto& e : impl_->ev) CUDA_CHECK(cudaEventCreate(&e));
+  CUDA_CHECK(cudaEventCreate(&impl_->e_begin));
+  CUDA_CHECK(cudaEventCreate(&impl_->e_lw0));
+  CUDA_CHECK(cudaEventCreate(&impl_->e_lw1));
+  CUDA_CHECK(cudaEventCreate(&impl_->e_end));
+  CUDA_CHECK(cudaMallocHost((void**)&impl_->h_out2, 2 * sizeof(double)));
+}
+
+XCIntegrator::~XCIntegrator() = default;
+void XCIntegrator::set_profile(bool on) { impl_->profile = on; }
+void* XCIntegrator::stream() const { return impl_->stream; }
+
+static size_t workspace_bytes(const LoadBalancer& lb) {
+  if (const char* e = std::getenv("GAUXC_B200_WORKSPACE_MB")) return (size_t)std::atoll(e) << 20;
+  size_t free_b = 0, tot_b = 0;
+  cudaMemGetInfo(&free_b, &tot_b);
+  double frac = 0.9;
+  if (auto* d = dynamic_cast<const DeviceRuntimeEnvironment*>(&lb.runtime()))
+    if (d->fill_fraction() > 0.) frac = d->fill_fraction();
+  size_t cap = (size_t)4 << 30;  // default: 4 GiB of B/Z workspace per batch
+  if (const char* e = std::getenv("GAUXC_DEVICE_MEMORY_CAP")) cap = (size_t)std::atoll(e);
+  return std::min<size_t>(cap, (size_t)(frac * free_b * 0.8));
+}
+
+void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d_out2, bool do_vxc) {
+  auto& I = *impl_;
+  if (!lb_->state().modified_weights_are_stored)
+    GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
+  {
+    auto np = get_device_plan(*lb_);
+    if (np != I.plan) {
+      I.plan = np;
+      I.sched.reset();
+    }
+  }
+  auto& plan = *I.plan;
+  const bool gga = func_->is_gga();
+  const int nmat = gga ? 5 : 2;
+  cudaStream_t s = I.stream;
+
+  if (!I.sched || I.sched_nmat != nmat) {
+    auto it = plan.schedules.find(nmat);
+    if (it == plan.schedules.end()) {
+      const size_t wsb = workspace_bytes(*lb_);
+      int tpi = 8;
+      if (const char* e = std::getenv("GAUXC_B200_TILES_PER_ITEM")) tpi = std::max(1, std::atoi(e));
+      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), tpi);
+      plan.schedule_ws_bytes = wsb;
+      it = plan.schedules.find(nmat);
+    }
+    I.sched = it->second;
+    I.sched_nmat = nmat;
+    I.d_ws.alloc(I.sched->ws_doubles);
+    I.d_den.alloc((size_t)4 * I.sched->max_batch_tiles * gxb::TP);
+    I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
+    I.d_nel_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
+  }
+  auto& sc = *I.sched;
+  const gxb::PlanView pv = plan.view();
+  const int nbf = plan.nbf;
+
+  if (do_vxc) CUDA_CHECK(cudaMemsetAsync(dVXC, 0, sizeof(double) * (size_t)nbf * nbf, s));
+  CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
+  double kms[4] = {0, 0, 0, 0};
+  long long launches = 0;
+  for (auto& b : sc.batches) {
+    const int nt = b.tile_end - b.tile_begin;
+    const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
+    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[0], s));
+    gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
+    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[1], s));
+    gxb::launch_xmat_density(pv, tl, nt, I.d_ws.p, dP, nbf, I.d_den.p, gga, s);
+    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[2], s));
+    gxb::launch_func_zmat(pv, tl, nt, I.d_ws.p, I.d_den.p, func_->desc, I.d_exc_part.p,
+                          I.d_nel_part.p, b.tile_begin, s);
+    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[3], s));
+    launches += 3;
+    if (do_vxc) {
+      gxb::launch_vxc(pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin, I.d_ws.p,
+                      gga, dVXC, nbf, s);
+      ++launches;
+    }
+    if (I.profile) {
+      CUDA_CHECK(cudaEventRecord(I.ev[4], s));
+      CUDA_CHECK(cudaEventSynchronize(I.ev[4]));
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, I.ev[k], I.ev[k + 1]);
+        kms[k] += ms;
+      }
+    }
+  }
+  gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), d_out2, s);
+  ++launches;
+  if (do_vxc) {
+    gxb::launch_symmetrize(dVXC, nbf, nbf, s);
+    ++launches;
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(I.e_lw1, s));
+
+  // replicated-data reduction over the ranks (…exc_vxc.hpp:158-162)
+  if (red_->comm_size() > 1) {
+    if (do_vxc) red_->allreduce_inplace(dVXC, (size_t)nbf * nbf, ReductionOp::Sum, s);
+    red_->allreduce_inplace(d_out2, 2, ReductionOp::Sum, s);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, I.e_lw0, I.e_lw1);
+  stats_.last_local_work_ms = ms;
+  timer_.add("XCIntegrator.LocalWork_EXC_VXC", ms);
+  for (int k = 0; k < 4; ++k) stats_.kernel_ms[k] = kms[k];
+  stats_.kernel_launches = launches;
+  stats_.f_dense = plan.f_dense;
+  stats_.sum_nbe_npts = plan.sum_nbe_npts;
+  stats_.npts = (long long)plan.npts;
+  stats_.ntiles = (long long)sc.tiles.size();
+  stats_.nbatches = (long long)sc.batches.size();
+  stats_.nitems = (long long)sc.items.size();
+}
+
+static void check_dims(const LoadBalancer& lb, int64_t m, int64_t n, int64_t ldp, int64_t ldv,
+                       bool vxc) {
+  // incore_replicated_xc_device_integrator_exc_vxc.hpp:66-92
+  const int64_t nbf = lb.basis_map().nbf;
+  if (m != n) GAUXC_GENERIC_EXCEPTION("P/VXC Must Be Square");
+  if (m != nbf) GAUXC_GENERIC_EXCEPTION("P/VXC Must Have Same Dimension as Basis");
+  if (ldp < nbf) GAUXC_GENERIC_EXCEPTION("Invalid LDP");
+  if (vxc && ldv < nbf) GAUXC_GENERIC_EXCEPTION("Invalid LDVXC");
+}
+
+void XCIntegrator::eval_exc_vxc(int64_t m, int64_t n, const double* P, int64_t ldp, double* VXC,
+                                int64_t ldvxc, double* EXC) {
+  check_dims(*lb_, m, n, ldp, ldvxc, true);
+  if (!lb_->state().modified_weights_are_stored)
+    GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
+  auto& I = *impl_;
+  const size_t nbf = (size_t)m;
+  cudaStream_t s = I.stream;
+  if (I.dP.n != nbf * nbf) {
+    I.dP.alloc(nbf * nbf);
+    I.dVXC.alloc(nbf * nbf);
+    I.d_out2.alloc(2);
+  }
+  CUDA_CHECK(cudaEventRecord(I.e_begin, s));
+  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), P, ldp * sizeof(double),
+                               nbf * sizeof(double), nbf, cudaMemcpyHostToDevice, s));
+  eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, true);
+  CUDA_CHECK(cudaMemcpy2DAsync(VXC, ldvxc * sizeof(double), I.dVXC.p, nbf * sizeof(double),
+                               nbf * sizeof(double), nbf, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaEventRecord(I.e_end, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, I.e_begin, I.e_end);
+  stats_.last_total_ms = ms;
+  *EXC = I.h_out2[0];
+  stats_.n_el = I.h_out2[1];
+}
+
+void XCIntegrator::eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC) {
+  check_dims(*lb_, m, n, ldp, 0, false);
+  auto& I = *impl_;
+  const size_t nbf = (size_t)m;
+  cudaStream_t s = I.stream;
+  if (I.dP.n != nbf * nbf) {
+    I.dP.alloc(nbf * nbf);
+    I.dVXC.alloc(nbf * nbf);
+    I.d_out2.alloc(2);
+  }
+  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), P, ldp * sizeof(double),
+                               nbf * sizeof(double), nbf, cudaMemcpyHostToDevice, s));
+  eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, false);
+  CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  *EXC = I.h_out2[0];
+  stats_.n_el = I.h_out2[1];
+}
+
+void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL) {
+  // the reference integrates with X = 1.0 * P * B (…integrate_den.hpp); N_EL of the EXC path
+  // carries the RKS factor 2, so halve it (integrate_den(P) == N_el / 2)
+  double exc;
+  eval_exc(m, n, P, ldp, &exc);
+  *N_EL = 0.5 * stats_.n_el;
+}
+
+}  // namespace GauXC
+
+// ------------------------------------------------------------------------------------
+// helpers behind the C ABI extensions
+// ------------------------------------------------------------------------------------
+namespace GauXC {
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+double device_probe_peak(int which) {
+  require_device();
+  switch (which) {
+    case 0: return gxb::probe_dmma_tflops(20000);
+    case 1: return gxb::probe_dfma_tflops(20000);
+    case 2: return gxb::probe_copy_gbs((size_t)1 << 30, 10);
+    default: GAUXC_GENERIC_EXCEPTION("Unknown probe");
+  }
+}
+
+void device_allreduce(double* dptr, size_t n) {
+  if (g_comm_size <= 1) return;
+  NCCLReductionDriver d;
+  d.allreduce_inplace(dptr, n, ReductionOp::Sum, nullptr);
+  CUDA_CHECK(cudaStreamSynchronize(0));
+}
+
+// Collocation of one ad-hoc task on the device (unit tests against the golden collocation
+// fixture, tests/collocation.cxx:45-91 in the reference).  Output in the host layout
+// eval[ipt*nbe + mu] of gau2grid_collocation.cxx.
+void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& shell_list,
+                             int64_t npts, const double* points, double* eval, double* dx,
+                             double* dy, double* dz) {
+  require_device();
+  const bool grad = dx != nullptr;
+  Molecule mol;  // centres are irrelevant here
+  BasisSetMap bmap(basis, mol);
+  std::vector<gxb::DevShell> shells(basis.size());
+  std::vector<double> alpha, coeff;
+  for (size_t s = 0; s < basis.size(); ++s) {
+    auto& sh = basis[s];
+    gxb::DevShell d{};
+    d.x = sh.O[0]; d.y = sh.O[1]; d.z = sh.O[2];
+    d.l = sh.l; d.pure = sh.pure; d.nprim = sh.nprim;
+    d.prim_off = (int)alpha.size();
+    d.ao_off = bmap.shell_to_ao_range[s].first;
+    d.nfunc = sh.size();
+    for (int k = 0; k < sh.nprim; ++k) { alpha.push_back(sh.alpha[k]); coeff.push_back(sh.coeff[k]); }
+    shells[s] = d;
+  }
+  gxb::DevTask task{};
+  std::vector<int> tsh, tbf;
+  int nbe = 0;
+  for (int s : shell_list) {
+    tsh.push_back(s);
+    tbf.push_back(nbe);
+    nbe += basis.at(s).size();
+  }
+  task.nshells = (int)shell_list.size();
+  task.nbe = nbe;
+  task.npts = (int)npts;
+  std::vector<gxb::DevTile> tiles;
+  const int nmat = grad ? 4 : 1;
+  for (int p0 = 0; p0 < npts; p0 += gxb::TP) {
+    gxb::DevTile t{};
+    t.task = 0; t.pt_off = p0; t.npts = (int)std::min<int64_t>(gxb::TP, npts - p0);
+    t.ws_off = (int64_t)tiles.size() * nmat * nbe * gxb::TP;
+    tiles.push_back(t);
+  }
+  std::vector<double> px(npts), py(npts), pz(npts);
+  for (int64_t i = 0; i < npts; ++i) { px[i] = points[3 * i]; py[i] = points[3 * i + 1]; pz[i] = points[3 * i + 2]; }
+  DevBuf<gxb::DevShell> d_sh; DevBuf<double> d_a, d_c, d_px, d_py, d_pz, d_ws;
+  DevBuf<gxb::DevTask> d_task; DevBuf<gxb::DevTile> d_tiles; DevBuf<int> d_tsh, d_tbf;
+  d_sh.upload(shells); d_a.upload(alpha); d_c.upload(coeff);
+  d_px.upload(px); d_py.upload(py); d_pz.upload(pz);
+  d_task.upload(std::vector<gxb::DevTask>{task}); d_tiles.upload(tiles);
+  d_tsh.upload(tsh); d_tbf.upload(tbf);
+  const size_t wsn = tiles.size() * (size_t)nmat * nbe * gxb::TP;
+  d_ws.alloc(wsn);
+  gxb::PlanView pv{};
+  pv.shells = d_sh.p; pv.prim_alpha = d_a.p; pv.prim_coeff = d_c.p; pv.tasks = d_task.p;
+  pv.task_shells = d_tsh.p; pv.task_shell_bf = d_tbf.p; pv.px = d_px.p; pv.py = d_py.p; pv.pz = d_pz.p;
+  gxb::launch_collocation(pv, d_tiles.p, (int)tiles.size(), d_ws.p, grad, 0);
+  CUDA_CHECK(cudaGetLastError());
+  std::vector<double> h(wsn);
+  CUDA_CHECK(cudaMemcpy(h.data(), d_ws.p, wsn * sizeof(double), cudaMemcpyDeviceToHost));
+  const size_t ms = (size_t)nbe * gxb::TP;
+  for (size_t t = 0; t < tiles.size(); ++t)
+    for (int i = 0; i < tiles[t].npts; ++i)
+      for (int mu = 0; mu < nbe; ++mu) {
+        const size_t src = (size_t)tiles[t].ws_off + (size_t)mu * gxb::TP + i;
+        const size_t dst = (size_t)(tiles[t].pt_off + i) * nbe + mu;
+        eval[dst] = h[src];
+        if (grad) { dx[dst] = h[src + ms]; dy[dst] = h[src + 2 * ms]; dz[dst] = h[src + 3 * ms]; }
+      }
+}
+
+}  // namespace GauXC

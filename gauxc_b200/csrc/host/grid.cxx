@@ -1,0 +1,301 @@
+// Lebedev expansion, radial rules, pruning specs, atomic grid generation + octree batcher.
+#include "grid.hpp"
+#include <algorithm>
+#include <mutex>
+
+namespace GauXC {
+
+// ---------------------------------------------------------------------------
+// Lebedev
+// ---------------------------------------------------------------------------
+namespace {
+struct OrbitRow {
+  int npts, degree, type;
+  double a, b, w;
+};
+const OrbitRow lebedev_orbits[] = {
+#include "lebedev_orbits.inc"
+};
+
+void push_signs(LebedevRule& R, double x, double y, double z, double w) {
+  // all sign combinations of the non-zero coordinates
+  for (int sx = 0; sx < (x != 0. ? 2 : 1); ++sx)
+    for (int sy = 0; sy < (y != 0. ? 2 : 1); ++sy)
+      for (int sz = 0; sz < (z != 0. ? 2 : 1); ++sz) {
+        R.pts.push_back({sx ? -x : x, sy ? -y : y, sz ? -z : z});
+        R.wts.push_back(w);
+      }
+}
+
+LebedevRule expand(int npts) {
+  LebedevRule R;
+  const double four_pi = 4. * M_PI;
+  for (auto& o : lebedev_orbits) {
+    if (o.npts != npts) continue;
+    const double w = o.w * four_pi;
+    switch (o.type) {
+      case 1:
+        push_signs(R, 1, 0, 0, w);
+        push_signs(R, 0, 1, 0, w);
+        push_signs(R, 0, 0, 1, w);
+        break;
+      case 2: {
+        const double a = std::sqrt(0.5);
+        push_signs(R, 0, a, a, w);
+        push_signs(R, a, 0, a, w);
+        push_signs(R, a, a, 0, w);
+      } break;
+      case 3: {
+        const double a = std::sqrt(1. / 3.);
+        push_signs(R, a, a, a, w);
+      } break;
+      case 4: {  // (a,a,b)
+        const double a = o.a, b = std::sqrt(1. - 2. * a * a);
+        push_signs(R, a, a, b, w);
+        push_signs(R, a, b, a, w);
+        push_signs(R, b, a, a, w);
+      } break;
+      case 5: {  // (a,b,0)
+        const double a = o.a, b = std::sqrt(1. - a * a);
+        push_signs(R, a, b, 0, w);
+        push_signs(R, b, a, 0, w);
+        push_signs(R, a, 0, b, w);
+        push_signs(R, b, 0, a, w);
+        push_signs(R, 0, a, b, w);
+        push_signs(R, 0, b, a, w);
+      } break;
+      case 6: {  // (a,b,c)
+        const double a = o.a, b = o.b, c = std::sqrt(1. - a * a - b * b);
+        push_signs(R, a, b, c, w);
+        push_signs(R, a, c, b, w);
+        push_signs(R, b, a, c, w);
+        push_signs(R, b, c, a, w);
+        push_signs(R, c, a, b, w);
+        push_signs(R, c, b, a, w);
+      } break;
+    }
+  }
+  if ((int)R.pts.size() != npts) GAUXC_GENERIC_EXCEPTION("Unsupported Lebedev Grid Size");
+  return R;
+}
+}  // namespace
+
+const LebedevRule& lebedev_rule(int npts) {
+  static std::map<int, LebedevRule> cache;
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lk(mtx);
+  auto it = cache.find(npts);
+  if (it == cache.end()) it = cache.emplace(npts, expand(npts)).first;
+  return it->second;
+}
+
+int lebedev_algebraic_order_by_npts(int npts) {
+  for (auto& o : lebedev_orbits)
+    if (o.npts == npts) return o.degree;
+  return -1;
+}
+int lebedev_npts_by_algebraic_order(int order) {
+  for (auto& o : lebedev_orbits)
+    if (o.degree == order) return o.npts;
+  return -1;
+}
+int lebedev_next_algebraic_order(int order) {
+  int best = -1;
+  for (auto& o : lebedev_orbits)
+    if (o.degree >= order && (best < 0 || o.degree < best)) best = o.degree;
+  return best;
+}
+
+// ---------------------------------------------------------------------------
+// Defaults (src/molgrid_defaults.cxx:52-71, 145-199)
+// ---------------------------------------------------------------------------
+double default_radial_scaling_factor(RadialQuad rq, int64_t Z) {
+  if (rq != RadialQuad::MuraKnowles && rq != RadialQuad::MurrayHandyLaming)
+    GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path (MuraKnowles only)");
+  switch (Z) {
+    case 3: case 4: case 11: case 12: case 19: case 20:
+    case 37: case 38: case 55: case 56: case 87: case 88:
+      return 7.0;
+    default:
+      return 5.0;
+  }
+}
+
+static int pyscf_radial_size(int64_t Z, int level) {
+  // src/molgrid_defaults.cxx:24-50
+  if (level < 0 || level > 8) GAUXC_GENERIC_EXCEPTION("Invalid PySCF grid level");
+  if (Z <= 2) return level == 0 ? 10 : 20 + 10 * level;
+  if (Z <= 10) return level == 0 ? 15 : (level == 1 ? 40 : 30 + 15 * level);
+  if (Z <= 18) return level == 0 ? 20 : 35 + 15 * level;
+  if (Z <= 36) return level == 0 ? 30 : 45 + 15 * level;
+  if (Z <= 54) return level == 0 ? 35 : 50 + 15 * level;
+  if (Z <= 86) return level == 0 ? 40 : 55 + 15 * level;
+  if (Z <= 118) return level == 0 ? 50 : 60 + 15 * level;
+  GAUXC_GENERIC_EXCEPTION("Z > 118 Not Supported for PySCF Grid Defaults");
+}
+
+std::pair<int, int> default_grid_size(int64_t Z, RadialQuad, AtomicGridSizeDefault s) {
+  using G = AtomicGridSizeDefault;
+  switch (s) {
+    case G::GM3: return {35, 110};
+    case G::GM5: return {50, 302};
+    case G::PySCF0: return {pyscf_radial_size(Z, 0), Z <= 2 ? 50 : (Z <= 10 ? 86 : 110)};
+    case G::PySCF1: return {pyscf_radial_size(Z, 1), Z <= 2 ? 110 : 194};
+    case G::PySCF2: return {pyscf_radial_size(Z, 2), Z <= 2 ? 194 : 302};
+    case G::PySCF3: return {pyscf_radial_size(Z, 3), Z <= 10 ? 302 : 434};
+    case G::PySCF4: return {pyscf_radial_size(Z, 4), Z <= 2 ? 434 : 590};
+    case G::PySCF5: return {pyscf_radial_size(Z, 5), Z <= 2 ? 590 : 770};
+    case G::PySCF6: return {pyscf_radial_size(Z, 6), Z <= 2 ? 770 : 974};
+    case G::PySCF7: return {pyscf_radial_size(Z, 7), Z <= 2 ? 974 : 1202};
+    case G::PySCF8: return {pyscf_radial_size(Z, 8), 1202};
+    case G::PySCF9: return {200, 1454};
+    case G::FineGrid: return {75, 302};
+    case G::UltraFineGrid: return {99, 590};
+    case G::SuperFineGrid: return {Z <= 2 ? 175 : 250, 974};
+  }
+  GAUXC_GENERIC_EXCEPTION("Not A Recognized Standard Grid");
+}
+
+// src/grid_factory.cxx:158-247
+PrunedAtomicGridSpecification create_pruned_spec(PruningScheme scheme,
+                                                 UnprunedAtomicGridSpecification unp) {
+  const size_t rsz = unp.radial_size;
+  std::vector<PruningRegion> regions;
+  if (scheme == PruningScheme::Robust) {
+    const int base_order = lebedev_algebraic_order_by_npts(unp.angular_size);
+    if (base_order < 0) GAUXC_GENERIC_EXCEPTION("Invalid Base Grid");
+    const int med_order = lebedev_next_algebraic_order(base_order > 6 ? base_order - 6 : base_order);
+    const int med_sz = lebedev_npts_by_algebraic_order(med_order);
+    const int low_sz = lebedev_npts_by_algebraic_order(7);
+    const size_t r4 = rsz / 4ul + 1ul, r2 = rsz / 2ul + 1ul;
+    regions = {{0ul, r4, low_sz}, {r4, r2, med_sz}, {r2, rsz, unp.angular_size}};
+  } else if (scheme == PruningScheme::Treutler) {
+    const int med_sz = lebedev_npts_by_algebraic_order(11);
+    const int low_sz = lebedev_npts_by_algebraic_order(7);
+    const size_t r3 = rsz / 3ul + 1ul, r2 = rsz / 2ul + 1ul;
+    regions = {{0ul, r3, low_sz}, {r3, r2, med_sz}, {r2, rsz, unp.angular_size}};
+  } else {
+    regions = {{0ul, rsz, unp.angular_size}};
+  }
+  return {unp.radial_quad, unp.radial_size, unp.radial_scale, regions};
+}
+
+// ---------------------------------------------------------------------------
+// Radial rules.  MuraKnowles as produced by IntegratorXX (verified
+// against the raw points of tests/ref_data/benzene_weights_ssf.hdf5):
+//   x_i = i/(n+1), r_i = -R ln(1-x_i^3), w_i = 3 R x_i^2/(1-x_i^3)/(n+1) * r_i^2
+// ---------------------------------------------------------------------------
+void radial_quadrature(RadialQuad rq, int n, double R, std::vector<double>& r,
+                       std::vector<double>& w) {
+  r.resize(n);
+  w.resize(n);
+  for (int i = 1; i <= n; ++i) {
+    const double x = double(i) / double(n + 1);
+    double ri, dr;
+    if (rq == RadialQuad::MuraKnowles) {
+      const double x3 = x * x * x;
+      ri = -R * std::log(1. - x3);
+      dr = 3. * R * x * x / (1. - x3);
+    } else if (rq == RadialQuad::MurrayHandyLaming) {
+      const double omx = 1. - x;
+      ri = R * x * x / (omx * omx);
+      dr = 2. * R * x / (omx * omx * omx);
+    } else {
+      GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path");
+    }
+    r[i - 1] = ri;
+    w[i - 1] = dr / double(n + 1) * ri * ri;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Atomic grid + octree micro-batcher (plays the role of IntegratorXX's
+// SphericalMicroBatcher: boxes of <= max_batch_sz points with a bounding box that
+// the load balancer screens shells against).
+// ---------------------------------------------------------------------------
+namespace {
+struct Pt {
+  std::array<double, 3> p;
+  double w;
+};
+
+void split(std::vector<Pt>& pts, size_t b, size_t e, std::array<double, 3> lo,
+           std::array<double, 3> up, size_t max_sz, int depth, std::vector<GridBatch>& out) {
+  if (e == b) return;
+  if (e - b <= max_sz || depth > 40) {
+    GridBatch g;
+    // tight bounding box of the points actually in the leaf
+    g.lo = {1e300, 1e300, 1e300};
+    g.up = {-1e300, -1e300, -1e300};
+    g.points.reserve(e - b);
+    g.weights.reserve(e - b);
+    for (size_t i = b; i < e; ++i) {
+      for (int d = 0; d < 3; ++d) {
+        g.lo[d] = std::min(g.lo[d], pts[i].p[d]);
+        g.up[d] = std::max(g.up[d], pts[i].p[d]);
+      }
+      g.points.push_back(pts[i].p);
+      g.weights.push_back(pts[i].w);
+    }
+    out.push_back(std::move(g));
+    return;
+  }
+  const std::array<double, 3> mid = {0.5 * (lo[0] + up[0]), 0.5 * (lo[1] + up[1]),
+                                     0.5 * (lo[2] + up[2])};
+  auto oct = [&](const Pt& q) {
+    return (q.p[0] >= mid[0] ? 1 : 0) | (q.p[1] >= mid[1] ? 2 : 0) | (q.p[2] >= mid[2] ? 4 : 0);
+  };
+  // stable counting sort into 8 octants keeps generation order inside a leaf
+  std::array<size_t, 9> cnt{};
+  for (size_t i = b; i < e; ++i) cnt[oct(pts[i]) + 1]++;
+  for (int k = 0; k < 8; ++k) cnt[k + 1] += cnt[k];
+  std::vector<Pt> tmp(e - b);
+  std::array<size_t, 8> pos;
+  for (int k = 0; k < 8; ++k) pos[k] = cnt[k];
+  for (size_t i = b; i < e; ++i) tmp[pos[oct(pts[i])]++] = pts[i];
+  std::copy(tmp.begin(), tmp.end(), pts.begin() + b);
+  for (int k = 0; k < 8; ++k) {
+    std::array<double, 3> l = lo, u = up;
+    for (int d = 0; d < 3; ++d) {
+      if (k & (1 << d)) l[d] = mid[d];
+      else u[d] = mid[d];
+    }
+    split(pts, b + cnt[k], b + cnt[k + 1], l, u, max_sz, depth + 1, out);
+  }
+}
+}  // namespace
+
+Grid::Grid(const PrunedAtomicGridSpecification& spec, int64_t max_batch_sz)
+    : max_batch_sz_(max_batch_sz) {
+  std::vector<double> r, w;
+  radial_quadrature(spec.radial_quad, spec.radial_size, spec.radial_scale, r, w);
+  std::vector<Pt> pts;
+  double rmax = 0;
+  for (auto& reg : spec.pruning_regions) {
+    const auto& L = lebedev_rule(reg.angular_size);
+    for (size_t i = reg.idx_st; i < reg.idx_en; ++i)
+      for (size_t j = 0; j < L.pts.size(); ++j) {
+        pts.push_back({{r[i] * L.pts[j][0], r[i] * L.pts[j][1], r[i] * L.pts[j][2]},
+                       w[i] * L.wts[j]});
+        rmax = std::max(rmax, r[i]);
+      }
+  }
+  npts_ = pts.size();
+  const double h = rmax * (1. + 1e-12) + 1e-12;
+  split(pts, 0, pts.size(), {-h, -h, -h}, {h, h, h}, (size_t)std::max<int64_t>(1, max_batch_sz),
+        0, batches_);
+}
+
+MolGrid create_default_molgrid(const Molecule& mol, PruningScheme scheme, int64_t batch_size,
+                               RadialQuad rq, AtomicGridSizeDefault size) {
+  std::map<int64_t, std::shared_ptr<Grid>> grids;
+  for (auto& at : mol) {
+    if (grids.count(at.Z)) continue;
+    auto [rsz, asz] = default_grid_size(at.Z, rq, size);
+    UnprunedAtomicGridSpecification unp{rq, rsz, default_radial_scaling_factor(rq, at.Z), asz};
+    grids[at.Z] = std::make_shared<Grid>(create_pruned_spec(scheme, unp), batch_size);
+  }
+  return MolGrid(std::move(grids));
+}
+
+}  // namespace GauXC
