@@ -41,7 +41,9 @@ GXB_HD XcOut slater_x(double rho) {
 GXB_HD XcOut vwn5_c(double rho) {
   XcOut o{0., 0., 0.};
   if (rho <= 1e-24) return o;
-  const double A = 0.0310907, b = 3.72744, c = 12.9352, x0 = -0.10498;
+  // ExchCXX maps Kernel::VWN5 onto libxc's XC_LDA_C_VWN_RPA parameter set (pinned by the
+  // golden benzene SVWN5 EXC/VXC): paramagnetic RPA fit
+  const double A = 0.0310907, b = 13.0720, c = 42.7198, x0 = -0.409286;
   const double Q = sqrt(4. * c - b * b);
   const double X0 = x0 * x0 + b * x0 + c;
   const double rs = cbrt(0.75 / (M_PI * rho));

@@ -1,0 +1,597 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Nothing under gauxc_b200/ may include, link or call
+// this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs use it, and only as the checker / CPU baseline.
+//
+// CPU restatement (C++/OpenMP, plain C interface) of the reference's HOST execution space
+// for the EXC/VXC hot path.  Each function cites the reference file:line it follows:
+//   driver         src/xc_integrator/replicated/host/reference_replicated_xc_host_integrator_exc_vxc.hpp:107-601
+//   primitives     src/xc_integrator/local_work_driver/host/reference_local_host_work_driver.cxx
+//                  eval_xmat :123-146, eval_uvvar_lda_rks :150-163, eval_uvvar_gga_rks :242-268,
+//                  eval_zmat_lda_vxc_rks :586-604, eval_zmat_gga_vxc_rks :678-713, inc_vxc :1678-1692
+//   gather/scatter src/xc_integrator/local_work_driver/host/util.hpp:21-168
+//   cut map        src/xc_integrator/integrator_util/integrator_common.cxx:22-146
+//   collocation    src/xc_integrator/local_work_driver/host/reference/gau2grid_collocation.cxx:25-116
+//                  over gau2grid (external/gau2grid, CCA orderings); restated here and checked
+//                  against gau2grid itself compiled into oracle/_ref (tests/test_oracle_golden.py)
+//   SSF weights    src/xc_integrator/local_work_driver/host/reference/weights.cxx:117-237
+//   functionals    ExchCXX (un-vendored, pinned 67be5c6e, cmake/gauxc-dep-versions.cmake:10-11):
+//                  published Slater / VWN5 / PW92(mod) / PBE closed forms, written independently of
+//                  the product's xc_functionals.cuh
+// Parity is PINNED: golden vectors of the reference's own tests (tests/golden/*.npz converted
+// from tests/ref_data/*.hdf5) are reproduced by tests/test_oracle_golden.py.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ----------------------------------------------------------------------------------
+// BLAS: OpenBLAS found at run time (the reference Host path calls a vendor BLAS), else
+// straightforward loops.
+// ----------------------------------------------------------------------------------
+typedef void (*dgemm_t)(const char*, const char*, const int*, const int*, const int*, const double*,
+                        const double*, const int*, const double*, const int*, const double*, double*,
+                        const int*);
+typedef void (*dsyr2k_t)(const char*, const char*, const int*, const int*, const double*, const double*,
+                         const int*, const double*, const int*, const double*, double*, const int*);
+dgemm_t f_dgemm = nullptr;
+dsyr2k_t f_dsyr2k = nullptr;
+char blas_name[512] = "builtin-loops";
+
+void naive_gemm_nn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+                   double* C, int ldc) {
+  // C(m x n) = alpha * A(m x k) B(k x n), column major
+  for (int j = 0; j < n; ++j) {
+    double* c = C + (size_t)j * ldc;
+    for (int i = 0; i < m; ++i) c[i] = 0.;
+    for (int p = 0; p < k; ++p) {
+      const double b = alpha * B[p + (size_t)j * ldb];
+      const double* a = A + (size_t)p * lda;
+      for (int i = 0; i < m; ++i) c[i] += a[i] * b;
+    }
+  }
+}
+void naive_syr2k_ln(int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+  // lower(C) = A B^T + B A^T, A,B n x k
+  for (int j = 0; j < n; ++j)
+    for (int i = j; i < n; ++i) C[i + (size_t)j * ldc] = 0.;
+  for (int p = 0; p < k; ++p) {
+    const double* a = A + (size_t)p * lda;
+    const double* b = B + (size_t)p * ldb;
+    for (int j = 0; j < n; ++j) {
+      const double aj = a[j], bj = b[j];
+      double* c = C + (size_t)j * ldc;
+      for (int i = j; i < n; ++i) c[i] += a[i] * bj + b[i] * aj;
+    }
+  }
+}
+
+void gemm_nn(int m, int n, int k, double alpha, const double* A, int lda, const double* B, int ldb,
+             double* C, int ldc) {
+  if (f_dgemm) {
+    const double beta = 0.;
+    f_dgemm("N", "N", &m, &n, &k, &alpha, A, &lda, B, &ldb, &beta, C, &ldc);
+  } else naive_gemm_nn(m, n, k, alpha, A, lda, B, ldb, C, ldc);
+}
+void syr2k_ln(int n, int k, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+  if (f_dsyr2k) {
+    const double one = 1., zero = 0.;
+    f_dsyr2k("L", "N", &n, &k, &one, A, &lda, B, &ldb, &zero, C, &ldc);
+  } else naive_syr2k_ln(n, k, A, lda, B, ldb, C, ldc);
+}
+
+// ----------------------------------------------------------------------------------
+// functionals (independent derivation; unpolarised)
+// ----------------------------------------------------------------------------------
+const double PI = 3.14159265358979323846;
+
+void f_slater(double rho, double& e, double& v) {
+  if (rho <= 1e-24) { e = v = 0; return; }
+  // eps_x = -3/4 (3/pi)^(1/3) rho^(1/3)
+  e = -0.75 * std::cbrt(3. / PI) * std::cbrt(rho);
+  v = 4. * e / 3.;
+}
+
+// VWN5: eps_c(x), x = sqrt(rs); v = eps - rs/3 d eps/d rs
+void f_vwn5(double rho, double& e, double& v) {
+  if (rho <= 1e-24) { e = v = 0; return; }
+  // ExchCXX maps Kernel::VWN5 onto libxc's XC_LDA_C_VWN_RPA parameter set (pinned by the
+  // golden benzene SVWN5 EXC/VXC): paramagnetic RPA fit
+  const double A = 0.0310907, b = 13.0720, c = 42.7198, x0 = -0.409286;
+  const double rs = std::cbrt(3. / (4. * PI * rho));
+  const double x = std::sqrt(rs);
+  auto Xf = [&](double y) { return y * y + b * y + c; };
+  const double Q = std::sqrt(4. * c - b * b);
+  auto eps = [&](double xx) {
+    const double X = Xf(xx);
+    const double at = std::atan(Q / (2. * xx + b));
+    return A * (std::log(xx * xx / X) + 2. * b / Q * at -
+                b * x0 / Xf(x0) * (std::log((xx - x0) * (xx - x0) / X) + 2. * (b + 2. * x0) / Q * at));
+  };
+  e = eps(x);
+  // analytic derivative: d eps/dx = A [ c (x - x0) - b x x0 ] / [ x X(x) (x - x0) ] * ... (closed form below)
+  // d/dx of each term
+  const double X = Xf(x), Xp = 2. * x + b;
+  const double dat = -2. * Q / (Xp * Xp + Q * Q);
+  const double de = A * ((2. / x - Xp / X) + 2. * b / Q * dat -
+                         b * x0 / Xf(x0) * ((2. / (x - x0) - Xp / X) + 2. * (b + 2. * x0) / Q * dat));
+  v = e - rs / 3. * de / (2. * x);
+}
+
+void pw92mod(double rs, double& e, double& de) {
+  const double A = 0.0310907, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+  const double q0 = -2. * A * (1. + a1 * rs);
+  const double rs12 = std::sqrt(rs), rs32 = rs * rs12;
+  const double q1 = 2. * A * (b1 * rs12 + b2 * rs + b3 * rs32 + b4 * rs * rs);
+  const double q1p = A * (b1 / rs12 + 2. * b2 + 3. * b3 * rs12 + 4. * b4 * rs);
+  const double lg = std::log(1. + 1. / q1);
+  e = q0 * lg;
+  de = -2. * A * a1 * lg - q0 * q1p / (q1 * q1 + q1);
+}
+void f_pw92(double rho, double& e, double& v) {
+  if (rho <= 1e-24) { e = v = 0; return; }
+  const double rs = std::cbrt(3. / (4. * PI * rho));
+  double de;
+  pw92mod(rs, e, de);
+  v = e - rs / 3. * de;
+}
+
+void f_pbe_x(double rho, double sigma, double& e, double& v, double& vs) {
+  if (rho <= 1e-32) { e = v = vs = 0; return; }
+  sigma = std::max(sigma, 1e-40);
+  const double kappa = 0.8040, mu = 0.2195149727645171;
+  const double kf = std::cbrt(3. * PI * PI * rho);
+  const double s = std::sqrt(sigma) / (2. * kf * rho);
+  const double s2 = s * s;
+  const double Fx = 1. + kappa - kappa / (1. + mu * s2 / kappa);
+  const double dF_ds2 = mu / ((1. + mu * s2 / kappa) * (1. + mu * s2 / kappa));
+  const double ex_lda = -0.75 * std::cbrt(3. / PI) * std::cbrt(rho);
+  e = ex_lda * Fx;
+  // E = rho ex_lda Fx ; s2 ~ sigma rho^(-8/3)
+  v = (4. / 3.) * ex_lda * Fx + rho * ex_lda * dF_ds2 * (-8. / 3.) * s2 / rho;
+  vs = rho * ex_lda * dF_ds2 * s2 / sigma;
+}
+
+void f_pbe_c(double rho, double sigma, double& e, double& v, double& vs) {
+  if (rho <= 1e-12) { e = v = vs = 0; return; }
+  sigma = std::max(sigma, 1e-32);
+  const double beta = 0.06672455060314922, gamma = (1. - std::log(2.)) / (PI * PI);
+  const double rs = std::cbrt(3. / (4. * PI * rho));
+  double ec, dec;
+  pw92mod(rs, ec, dec);
+  const double kf = std::cbrt(3. * PI * PI * rho);
+  const double ks = std::sqrt(4. * kf / PI);
+  const double t = std::sqrt(sigma) / (2. * ks * rho);
+  const double t2 = t * t, t4 = t2 * t2;
+  const double ex = std::exp(-ec / gamma);
+  const double Ac = beta / gamma / (ex - 1.);
+  const double num = 1. + Ac * t2;
+  const double den = 1. + Ac * t2 + Ac * Ac * t4;
+  const double arg = 1. + beta / gamma * t2 * num / den;
+  const double H = gamma * std::log(arg);
+  e = ec + H;
+  // partial derivatives of H wrt t2 and Ac
+  const double dq_dt2 = (num / den) + t2 * (Ac * den - num * (Ac + 2. * Ac * Ac * t2)) / (den * den);
+  const double dq_dA = t2 * (t2 * den - num * (t2 + 2. * Ac * t4)) / (den * den);
+  const double dH_dt2 = beta * dq_dt2 / arg;
+  const double dH_dA = beta * dq_dA / arg;
+  const double dA_dec = beta / gamma * ex / (gamma * (ex - 1.) * (ex - 1.));
+  const double drs_drho = -rs / (3. * rho);
+  const double dec_drho = dec * drs_drho;
+  const double dt2_drho = -7. / 3. * t2 / rho;
+  const double dH_drho = dH_dt2 * dt2_drho + dH_dA * dA_dec * dec_drho;
+  v = e + rho * (dec_drho + dH_drho);
+  vs = rho * dH_dt2 * t2 / sigma;
+}
+
+enum { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5 };
+
+struct Func {
+  int nkern, is_gga;
+  int kern[4];
+  double coeff[4];
+};
+
+void eval_func(const Func& f, int npts, const double* rho, const double* sigma, double* eps, double* vrho,
+               double* vsigma) {
+  for (int i = 0; i < npts; ++i) {
+    double E = 0, V = 0, S = 0;
+    for (int k = 0; k < f.nkern; ++k) {
+      double e = 0, v = 0, s = 0;
+      switch (f.kern[k]) {
+        case K_SLATER_X: f_slater(rho[i], e, v); break;
+        case K_VWN5_C: f_vwn5(rho[i], e, v); break;
+        case K_PW92_C: f_pw92(rho[i], e, v); break;
+        case K_PBE_X: f_pbe_x(rho[i], sigma[i], e, v, s); break;
+        case K_PBE_C: f_pbe_c(rho[i], sigma[i], e, v, s); break;
+      }
+      E += f.coeff[k] * e; V += f.coeff[k] * v; S += f.coeff[k] * s;
+    }
+    eps[i] = E; vrho[i] = V;
+    if (vsigma) vsigma[i] = S;
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// collocation: gau2grid semantics (gg_collocation / gg_collocation_deriv1), host layout
+// basis_eval[mu + ipt*nbe]
+// ----------------------------------------------------------------------------------
+struct Basis {
+  int nshells;
+  const int32_t *l, *pure, *nprim;
+  const double *alpha, *coeff, *origin;  // [nshells][32], [nshells][32], [nshells][3]
+  int size(int s) const { return pure[s] ? 2 * l[s] + 1 : (l[s] + 1) * (l[s] + 2) / 2; }
+};
+
+// real solid harmonics of order l in CCA order m=-l..l as combinations of cartesian monomials
+// (gau2grid "spherical CCA"; (l,0,0)-normalised cartesians)
+struct SphTerm { int a, b, c; double f; };
+const std::vector<std::vector<SphTerm>>& sph_table(int l) {
+  static std::vector<std::vector<std::vector<SphTerm>>> T;
+  if (T.empty()) {
+    T.resize(5);
+    const double s3 = std::sqrt(3.);
+    T[0] = {{{0, 0, 0, 1.}}};
+    T[1] = {{{0, 1, 0, 1.}}, {{0, 0, 1, 1.}}, {{1, 0, 0, 1.}}};
+    T[2] = {{{1, 1, 0, s3}},
+            {{0, 1, 1, s3}},
+            {{0, 0, 2, 1.}, {2, 0, 0, -0.5}, {0, 2, 0, -0.5}},
+            {{1, 0, 1, s3}},
+            {{2, 0, 0, 0.5 * s3}, {0, 2, 0, -0.5 * s3}}};
+    const double c58 = std::sqrt(5. / 8.), c15 = std::sqrt(15.), c38 = std::sqrt(3. / 8.);
+    T[3] = {{{2, 1, 0, 3 * c58}, {0, 3, 0, -c58}},
+            {{1, 1, 1, c15}},
+            {{0, 1, 2, 4 * c38}, {2, 1, 0, -c38}, {0, 3, 0, -c38}},
+            {{0, 0, 3, 1.}, {2, 0, 1, -1.5}, {0, 2, 1, -1.5}},
+            {{1, 0, 2, 4 * c38}, {3, 0, 0, -c38}, {1, 2, 0, -c38}},
+            {{2, 0, 1, 0.5 * c15}, {0, 2, 1, -0.5 * c15}},
+            {{3, 0, 0, c58}, {1, 2, 0, -3 * c58}}};
+    const double c35 = std::sqrt(35.), c70 = std::sqrt(70.), c5 = std::sqrt(5.), c10 = std::sqrt(10.);
+    T[4] = {{{3, 1, 0, c35 / 2}, {1, 3, 0, -c35 / 2}},
+            {{2, 1, 1, 3 * c70 / 4}, {0, 3, 1, -c70 / 4}},
+            {{1, 1, 2, 6 * c5 / 2}, {3, 1, 0, -c5 / 2}, {1, 3, 0, -c5 / 2}},
+            {{0, 1, 3, 4 * c10 / 4}, {2, 1, 1, -3 * c10 / 4}, {0, 3, 1, -3 * c10 / 4}},
+            {{0, 0, 4, 1.}, {2, 0, 2, -3.}, {0, 2, 2, -3.}, {4, 0, 0, 0.375}, {2, 2, 0, 0.75}, {0, 4, 0, 0.375}},
+            {{1, 0, 3, 4 * c10 / 4}, {3, 0, 1, -3 * c10 / 4}, {1, 2, 1, -3 * c10 / 4}},
+            {{2, 0, 2, 6 * c5 / 4}, {0, 2, 2, -6 * c5 / 4}, {4, 0, 0, -c5 / 4}, {0, 4, 0, c5 / 4}},
+            {{3, 0, 1, c70 / 4}, {1, 2, 1, -3 * c70 / 4}},
+            {{4, 0, 0, c35 / 8}, {2, 2, 0, -6 * c35 / 8}, {0, 4, 0, c35 / 8}}};
+  }
+  return T[l];
+}
+
+double ipow(double x, int n) {
+  double r = 1.;
+  for (int i = 0; i < n; ++i) r *= x;
+  return r;
+}
+
+// values (+ gradient) of one shell at one point, written with stride 1 at out[0..size)
+void shell_at_point(const Basis& B, int s, const double* p, bool grad, double* v, double* gx, double* gy,
+                    double* gz) {
+  const double x = p[0] - B.origin[3 * s], y = p[1] - B.origin[3 * s + 1], z = p[2] - B.origin[3 * s + 2];
+  const double r2 = x * x + y * y + z * z;
+  double S0 = 0, S1 = 0;
+  for (int k = 0; k < B.nprim[s]; ++k) {
+    const double a = B.alpha[32 * s + k];
+    const double e = B.coeff[32 * s + k] * std::exp(-a * r2);
+    S0 += e;
+    S1 += -2. * a * e;
+  }
+  const int l = B.l[s];
+  auto mono = [&](int a, int b, int c, double& vv, double& dx, double& dy, double& dz) {
+    const double f = ipow(x, a) * ipow(y, b) * ipow(z, c);
+    vv = f * S0;
+    if (grad) {
+      dx = (a ? a * ipow(x, a - 1) * ipow(y, b) * ipow(z, c) * S0 : 0.) + f * x * S1;
+      dy = (b ? b * ipow(x, a) * ipow(y, b - 1) * ipow(z, c) * S0 : 0.) + f * y * S1;
+      dz = (c ? c * ipow(x, a) * ipow(y, b) * ipow(z, c - 1) * S0 : 0.) + f * z * S1;
+    }
+  };
+  if (!B.pure[s]) {
+    int c = 0;
+    for (int a = l; a >= 0; --a)
+      for (int b = l - a; b >= 0; --b, ++c) {
+        double vv, dx = 0, dy = 0, dz = 0;
+        mono(a, b, l - a - b, vv, dx, dy, dz);
+        v[c] = vv;
+        if (grad) { gx[c] = dx; gy[c] = dy; gz[c] = dz; }
+      }
+  } else {
+    if (l > 4) { std::fprintf(stderr, "oracle: pure l>4 unsupported\n"); std::abort(); }
+    const auto& T = sph_table(l);
+    for (int m = 0; m < 2 * l + 1; ++m) {
+      double vv = 0, dx = 0, dy = 0, dz = 0;
+      for (auto& t : T[m]) {
+        double v1, d1 = 0, d2 = 0, d3 = 0;
+        mono(t.a, t.b, t.c, v1, d1, d2, d3);
+        vv += t.f * v1; dx += t.f * d1; dy += t.f * d2; dz += t.f * d3;
+      }
+      v[m] = vv;
+      if (grad) { gx[m] = dx; gy[m] = dy; gz[m] = dz; }
+    }
+  }
+}
+
+void collocation(const Basis& B, int nsh, const int32_t* shell_list, int npts, const double* pts, int nbe,
+                 bool grad, double* ev, double* dx, double* dy, double* dz) {
+  for (int i = 0; i < npts; ++i) {
+    int off = 0;
+    for (int q = 0; q < nsh; ++q) {
+      const int s = shell_list[q];
+      const size_t o = (size_t)i * nbe + off;
+      shell_at_point(B, s, pts + 3 * i, grad, ev + o, grad ? dx + o : nullptr, grad ? dy + o : nullptr,
+                     grad ? dz + o : nullptr);
+      off += B.size(s);
+    }
+  }
+}
+
+// Neumaier sum
+struct Acc {
+  double s = 0, c = 0;
+  void add(double x) {
+    const double t = s + x;
+    if (std::fabs(s) >= std::fabs(x)) c += (s - t) + x;
+    else c += (x - t) + s;
+    s = t;
+  }
+  double value() const { return s + c; }
+};
+
+}  // namespace
+
+extern "C" {
+
+// returns the BLAS in use
+const char* oracle_init_blas(const char* path_hint) {
+  if (f_dgemm) return blas_name;
+  std::vector<std::string> cands;
+  if (path_hint && *path_hint) cands.push_back(path_hint);
+  if (const char* e = std::getenv("ORACLE_BLAS")) cands.push_back(e);
+  for (auto& c : cands) {
+    void* h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) continue;
+    const char* names[][2] = {{"dgemm_", "dsyr2k_"}, {"scipy_dgemm_", "scipy_dsyr2k_"}};
+    for (auto& n : names) {
+      auto g = (dgemm_t)dlsym(h, n[0]);
+      auto s = (dsyr2k_t)dlsym(h, n[1]);
+      if (g && s) {
+        f_dgemm = g;
+        f_dsyr2k = s;
+        std::snprintf(blas_name, sizeof(blas_name), "%s", c.c_str());
+        // single-threaded BLAS inside the OpenMP task loop
+        typedef void (*setnt_t)(int);
+        for (const char* sn : {"openblas_set_num_threads", "scipy_openblas_set_num_threads"}) {
+          if (auto f = (setnt_t)dlsym(h, sn)) { f(1); break; }
+        }
+        return blas_name;
+      }
+    }
+  }
+  return blas_name;
+}
+
+int oracle_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#endif
+}
+
+void oracle_functional(int nkern, const int* kern, const double* coeff, int is_gga, int npts,
+                       const double* rho, const double* sigma, double* eps, double* vrho, double* vsigma) {
+  Func f{};
+  f.nkern = nkern; f.is_gga = is_gga;
+  for (int k = 0; k < nkern; ++k) { f.kern[k] = kern[k]; f.coeff[k] = coeff[k]; }
+  std::vector<double> zero;
+  if (!sigma) { zero.assign(npts, 0.); sigma = zero.data(); }
+  eval_func(f, npts, rho, sigma, eps, vrho, vsigma);
+}
+
+void oracle_collocation(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                        const double* alpha, const double* coeff, const double* origin, int nsh,
+                        const int32_t* shell_list, int npts, const double* points, int want_grad,
+                        double* eval, double* dx, double* dy, double* dz) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  int nbe = 0;
+  for (int q = 0; q < nsh; ++q) nbe += B.size(shell_list[q]);
+  collocation(B, nsh, shell_list, npts, points, nbe, want_grad != 0, eval, dx, dy, dz);
+}
+
+// weights.cxx:117-237 (reference_ssf_weights_host), RAB from src/molmeta.cxx:28-58
+void oracle_ssf_weights(int natoms, const double* coords, int ntasks, const int32_t* task_npts,
+                        const int32_t* task_iparent, const double* task_dist_nearest,
+                        const double* points, double* weights) {
+  const double magic = 0.64, tol = 1e-13;
+  std::vector<double> RAB((size_t)natoms * natoms, 0.);
+  for (int i = 0; i < natoms; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double dx = coords[3 * i] - coords[3 * j], dy = coords[3 * i + 1] - coords[3 * j + 1],
+                   dz = coords[3 * i + 2] - coords[3 * j + 2];
+      RAB[i + (size_t)j * natoms] = std::sqrt(dx * dx + dy * dy + dz * dz);
+      RAB[j + (size_t)i * natoms] = RAB[i + (size_t)j * natoms];
+    }
+  auto gFrisch = [&](double x) {
+    const double s_x = x / magic;
+    const double s_x2 = s_x * s_x, s_x3 = s_x * s_x2, s_x5 = s_x3 * s_x2, s_x7 = s_x5 * s_x2;
+    return (35. * (s_x - s_x3) + 21. * s_x5 - 5. * s_x7) / 16.;
+  };
+  std::vector<size_t> off(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) off[t + 1] = off[t] + task_npts[t];
+#pragma omp parallel
+  {
+    std::vector<double> part(natoms), dist(natoms);
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; ++iT)
+      for (int i = 0; i < task_npts[iT]; ++i) {
+        const int par = task_iparent[iT];
+        double& weight = weights[off[iT] + i];
+        const double* point = points + 3 * (off[iT] + i);
+        const double dist_cutoff = 0.5 * (1 - magic) * task_dist_nearest[iT];
+        {
+          const double dx = point[0] - coords[3 * par], dy = point[1] - coords[3 * par + 1],
+                       dz = point[2] - coords[3 * par + 2];
+          dist[par] = std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        if (dist[par] < dist_cutoff) continue;
+        for (int iA = 0; iA < natoms; ++iA) {
+          if (iA == par) continue;
+          const double dx = point[0] - coords[3 * iA], dy = point[1] - coords[3 * iA + 1],
+                       dz = point[2] - coords[3 * iA + 2];
+          dist[iA] = std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        std::fill(part.begin(), part.end(), 1.);
+        for (int iA = 0; iA < natoms; ++iA)
+          for (int jA = 0; jA < iA; ++jA)
+            if (part[iA] > tol || part[jA] > tol) {
+              const double mu = (dist[iA] - dist[jA]) / RAB[jA + (size_t)iA * natoms];
+              if (mu <= -magic) part[jA] = 0.;
+              else if (mu >= magic) part[iA] = 0.;
+              else {
+                const double g = 0.5 * (1. - gFrisch(mu));
+                part[iA] *= g;
+                part[jA] *= 1. - g;
+              }
+            }
+        double sum = 0.;
+        for (int iA = 0; iA < natoms; ++iA) sum += part[iA];
+        weight *= part[par] / sum;
+      }
+  }
+}
+
+// The EXC/VXC host driver (…host_integrator_exc_vxc.hpp:107-601) for RKS LDA/GGA.
+// P: nbf x nbf (ld = ldp), the alpha density (X = 2 P B).  VXC: nbf x nbf (ld = nbf), fully
+// overwritten and symmetric.  out3 = {EXC, N_EL, F_dense flops}.  task_stride > 1 evaluates
+// only every task_stride-th task (bounded CPU-baseline sample in bench.py).
+void oracle_exc_vxc(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                    const double* alpha, const double* coeff, const double* origin, int nbf,
+                    const double* P, int ldp, int ntasks, const int32_t* task_npts,
+                    const int32_t* task_nshells, const int32_t* shell_lists, const double* points,
+                    const double* weights, int nkern, const int* kern, const double* kcoeff, int is_gga,
+                    int task_stride, double* VXC, double* out3) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  Func func{};
+  func.nkern = nkern; func.is_gga = is_gga;
+  for (int k = 0; k < nkern; ++k) { func.kern[k] = kern[k]; func.coeff[k] = kcoeff[k]; }
+  std::vector<int> first_ao(nshells_total + 1, 0);
+  for (int s = 0; s < nshells_total; ++s) first_ao[s + 1] = first_ao[s] + B.size(s);
+  std::vector<size_t> poff(ntasks + 1, 0), soff(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) {
+    poff[t + 1] = poff[t] + task_npts[t];
+    soff[t + 1] = soff[t] + task_nshells[t];
+  }
+  std::fill(VXC, VXC + (size_t)nbf * nbf, 0.);
+  std::vector<double> exc_t(ntasks, 0.), nel_t(ntasks, 0.), flops_t(ntasks, 0.);
+  if (task_stride < 1) task_stride = 1;
+
+#pragma omp parallel
+  {
+    std::vector<double> ev, dxv, dyv, dzv, X, Z, scr, Psub, den, ddx, ddy, ddz, gam, eps, vrho, vgam;
+    std::vector<int> ao;
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; iT += task_stride) {
+      const int npts = task_npts[iT];
+      const int nsh = task_nshells[iT];
+      const int32_t* sl = shell_lists + soff[iT];
+      const double* pts = points + 3 * poff[iT];
+      const double* w = weights + poff[iT];
+      // local AO list == the cut map of gen_compressed_submat_map (contiguous shell ranges)
+      ao.clear();
+      for (int q = 0; q < nsh; ++q)
+        for (int a = first_ao[sl[q]]; a < first_ao[sl[q] + 1]; ++a) ao.push_back(a);
+      const int nbe = (int)ao.size();
+      const size_t nn = (size_t)nbe * npts;
+      ev.resize(nn); X.resize(nn); Z.resize(nn);
+      if (is_gga) { dxv.resize(nn); dyv.resize(nn); dzv.resize(nn); }
+      scr.resize((size_t)nbe * nbe); Psub.resize((size_t)nbe * nbe);
+      den.resize(npts); eps.resize(npts); vrho.resize(npts); gam.assign(npts, 0.);
+      if (is_gga) { ddx.resize(npts); ddy.resize(npts); ddz.resize(npts); vgam.resize(npts); }
+
+      collocation(B, nsh, sl, npts, pts, nbe, is_gga != 0, ev.data(), dxv.data(), dyv.data(), dzv.data());
+
+      // eval_xmat: submat_set + dgemm('N','N', nbe, npts, nbe, 2.0, P_sub, B)
+      for (int j = 0; j < nbe; ++j)
+        for (int i = 0; i < nbe; ++i) Psub[i + (size_t)j * nbe] = P[ao[i] + (size_t)ao[j] * ldp];
+      gemm_nn(nbe, npts, nbe, 2.0, Psub.data(), nbe, ev.data(), nbe, X.data(), nbe);
+
+      // eval_uvvar_{lda,gga}_rks
+      for (int i = 0; i < npts; ++i) {
+        const double* xi = X.data() + (size_t)i * nbe;
+        const double* bi = ev.data() + (size_t)i * nbe;
+        double d = 0;
+        for (int m = 0; m < nbe; ++m) d += bi[m] * xi[m];
+        den[i] = d;
+        if (is_gga) {
+          double a = 0, b = 0, c = 0;
+          const double *bx = dxv.data() + (size_t)i * nbe, *by = dyv.data() + (size_t)i * nbe,
+                       *bz = dzv.data() + (size_t)i * nbe;
+          for (int m = 0; m < nbe; ++m) { a += bx[m] * xi[m]; b += by[m] * xi[m]; c += bz[m] * xi[m]; }
+          ddx[i] = 2. * a; ddy[i] = 2. * b; ddz[i] = 2. * c;
+          gam[i] = ddx[i] * ddx[i] + ddy[i] * ddy[i] + ddz[i] * ddz[i];
+        }
+      }
+      eval_func(func, npts, den.data(), gam.data(), eps.data(), vrho.data(), is_gga ? vgam.data() : nullptr);
+      // factor weights (:453-466) and scalar integrals (:490-497)
+      Acc e_acc, n_acc;
+      for (int i = 0; i < npts; ++i) {
+        eps[i] *= w[i];
+        vrho[i] *= w[i];
+        if (is_gga) vgam[i] *= w[i];
+        n_acc.add(w[i] * den[i]);
+        e_acc.add(eps[i] * den[i]);
+      }
+      exc_t[iT] = e_acc.value();
+      nel_t[iT] = n_acc.value();
+      // eval_zmat_{lda,gga}_vxc_rks
+      for (int i = 0; i < npts; ++i) {
+        double* zi = Z.data() + (size_t)i * nbe;
+        const double* bi = ev.data() + (size_t)i * nbe;
+        const double lda_fact = 0.5 * vrho[i];
+        for (int m = 0; m < nbe; ++m) zi[m] = lda_fact * bi[m];
+        if (is_gga) {
+          const double gf = 2. * vgam[i];
+          const double xf = gf * ddx[i], yf = gf * ddy[i], zf = gf * ddz[i];
+          const double *bx = dxv.data() + (size_t)i * nbe, *by = dyv.data() + (size_t)i * nbe,
+                       *bz = dzv.data() + (size_t)i * nbe;
+          for (int m = 0; m < nbe; ++m) zi[m] += xf * bx[m];
+          for (int m = 0; m < nbe; ++m) zi[m] += yf * by[m];
+          for (int m = 0; m < nbe; ++m) zi[m] += zf * bz[m];
+        }
+      }
+      // inc_vxc: syr2k('L','N') + inc_by_submat_atomic (lower triangle is what matters)
+      syr2k_ln(nbe, npts, ev.data(), nbe, Z.data(), nbe, scr.data(), nbe);
+      for (int j = 0; j < nbe; ++j)
+        for (int i = j; i < nbe; ++i) {
+#pragma omp atomic
+          VXC[ao[i] + (size_t)ao[j] * nbf] += scr[i + (size_t)j * nbe];
+        }
+      flops_t[iT] = 4. * double(nbe) * double(nbe) * double(npts);
+    }
+  }
+  // symmetrise (:577-583): upper <- lower
+  for (int j = 0; j < nbf; ++j)
+    for (int i = j + 1; i < nbf; ++i) VXC[j + (size_t)i * nbf] = VXC[i + (size_t)j * nbf];
+  Acc E, N, F;
+  for (int t = 0; t < ntasks; ++t) { E.add(exc_t[t]); N.add(nel_t[t]); F.add(flops_t[t]); }
+  out3[0] = E.value(); out3[1] = N.value(); out3[2] = F.value();
+}
+
+}  // extern "C"
