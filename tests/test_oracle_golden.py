@@ -1,0 +1,135 @@
+"""CPU: the oracle (oracle/oracle.cxx) against every golden vector the reference's own tests
+hold for this path, plus the pieces of the product's host layer the goldens pin (grid
+generation, batching/screening through the full EXC/VXC integrals)."""
+import numpy as np
+import pytest
+
+from conftest import make_lb
+from gauxc_b200 import capi, systems
+
+
+def test_collocation_golden_and_gau2grid(orc):
+    # reference: tests/collocation.cxx:45-91 over water_cc-pVDZ_collocation.hdf5 (tol 1e-6 there)
+    import gauxc_b200 as gx
+    atoms = systems.geometry("water")
+    basis = gx.BasisSet(systems.make_basis_shells(atoms, "cc-pvdz", spherical=True), normalize=True)
+    fb = basis.flat()
+    col = systems.golden("water_collocation")
+    for e in range(int(col["nentries"][0])):
+        mask, pts = col[f"e{e}_mask"], col[f"e{e}_pts"]
+        res = orc.collocation(fb, mask, pts, gradient=True)
+        for a, k in zip(res, ("eval", "deval_x", "deval_y", "deval_z")):
+            assert np.abs(a - col[f"e{e}_{k}"].reshape(a.shape)).max() < 1e-14
+        if orc.gau2grid() is not None:  # oracle/_ref: the reference's own gau2grid
+            ref = orc.gau2grid_collocation(fb, mask, pts, gradient=True)
+            for a, b in zip(res, ref):
+                assert np.abs(a - b).max() < 1e-14
+
+
+def test_collocation_high_l_vs_gau2grid(orc):
+    import gauxc_b200 as gx
+    if orc.gau2grid() is None:
+        pytest.skip("oracle/_ref/libgau2grid.so not built (reference tree absent)")
+    shells = [dict(l=l, pure=p, exps=[1.3, 0.4], coefs=[0.6, 0.5], origin=(0.1, -0.2, 0.3))
+              for l in range(5) for p in (False, True)]
+    basis = gx.BasisSet(shells, normalize=True)
+    fb = basis.flat()
+    pts = np.random.default_rng(1).standard_normal((64, 3))
+    sl = np.arange(len(shells), dtype=np.int32)
+    for a, b in zip(orc.collocation(fb, sl, pts, True), orc.gau2grid_collocation(fb, sl, pts, True)):
+        assert np.abs(a - b).max() < 2e-15
+
+
+def test_ssf_weights_golden(orc):
+    # reference: tests/weights.cxx:58-77 over benzene_weights_ssf.hdf5 (Approx there)
+    g = systems.golden("benzene_weights_ssf")
+    nt = int(g["ntasks"][0])
+    npts = [len(g[f"t{i}_weights"]) for i in range(nt)]
+    ip = [int(g[f"t{i}_iParent"][0]) for i in range(nt)]
+    dn = [float(g[f"t{i}_dist_nearest"][0]) for i in range(nt)]
+    pts = np.concatenate([g[f"t{i}_points"].reshape(-1, 3) for i in range(nt)])
+    w = np.concatenate([g[f"t{i}_weights"] for i in range(nt)])
+    wm = np.concatenate([g[f"t{i}_weights_mod"] for i in range(nt)])
+    w2 = orc.ssf_weights(g["mol_xyz"], npts, ip, dn, pts, w)
+    assert np.abs(w2 - wm).max() <= 1e-16  # bit-level restatement
+
+
+def test_grid_against_golden_points():
+    # the raw FineGrid points of the weights fixture pin MuraKnowles(75, R=5) x Lebedev-302
+    g = systems.golden("benzene_weights_ssf")
+    r, w = capi.radial("MuraKnowles", 75, 5.0)
+    xyz, lw = capi.lebedev(302)
+    centre = g["mol_xyz"][int(g["t0_iParent"][0])]
+    p = g["t0_points"].reshape(-1, 3) - centre
+    rad = np.linalg.norm(p, axis=1)
+    # every golden radius is a MuraKnowles node, every golden weight a node x Lebedev product
+    k = np.abs(rad[:, None] - r[None, :]).argmin(1)
+    assert np.abs(rad - r[k]).max() < 1e-9
+    wang = g["t0_weights"] / w[k]  # must be one of the Lebedev-302 weights
+    ulw = np.unique(np.round(lw, 15))
+    rel = np.abs(wang[:, None] - ulw[None, :]).min(1) / wang
+    assert rel.max() < 1e-9
+
+
+@pytest.mark.parametrize("name,func,pruning", [
+    ("benzene_svwn5_cc-pvdz_ufg_ssf", "SVWN5", "Unpruned"),
+    ("benzene_pbe0_cc-pvdz_ufg_ssf", "PBE0", "Unpruned"),
+    ("benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "SVWN5", "Robust"),
+    ("benzene_svwn5_cc-pvdz_ufg_ssf_treutler_prune", "SVWN5", "Treutler"),
+])
+def test_exc_vxc_golden(orc, benzene_golden, name, func, pruning):
+    # reference: tests/xc_integrator.cxx:185-216, 405-426 (|VXC-ref|_F/nbf < 1e-10, EXC Approx)
+    atoms, shells, P, VXC, EXC = benzene_golden(name, pruning)
+    mol, basis, lb = make_lb(atoms, shells, "UltraFineGrid", pruning, normalize=False)
+    tasks = lb.export_tasks()
+    assert lb.total_npts() == {"Unpruned": 700920, "Robust": 484920, "Treutler": 367128}[pruning]
+    coords = np.array([a[1:] for a in atoms])
+    tasks["weights"] = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"],
+                                       tasks["points"], tasks["weights"])
+    r = orc.exc_vxc(basis.flat(), basis.nbf(), P, tasks, func)
+    assert abs(r["exc"] - EXC) < 1e-10
+    assert np.abs(r["vxc"] - VXC).max() < 1e-10
+    assert np.linalg.norm(r["vxc"] - VXC) / basis.nbf() < 1e-10
+    assert abs(r["nel"] - 42.0) < 1e-5
+
+
+def test_functionals_product_vs_oracle_and_fd(orc):
+    """The product's functional code (host hook over the same __host__ __device__ source) against
+    the oracle's independent derivation, and both against finite differences."""
+    import gauxc_b200 as gx
+    rng = np.random.default_rng(7)
+    rho = 10 ** rng.uniform(-9, 2, 4000)
+    s = 10 ** rng.uniform(-2, 1.5, 4000)  # reduced gradient
+    sigma = (s * 2 * (3 * np.pi ** 2) ** (1 / 3) * rho ** (4 / 3)) ** 2
+    for fn in ("SVWN5", "SPW92", "LDA", "PBE", "PBE0"):
+        f = gx.Functional(fn)
+        e1, v1, s1 = f.eval_host(rho, sigma)
+        e2, v2, s2 = orc.functional(fn, rho, sigma)
+        for a, b in ((e1, e2), (v1, v2), (s1, s2)):
+            err = np.abs(a - b) / (np.abs(b) + 1e-13)
+            assert err.max() < 1e-8, (fn, err.max())
+        # finite differences of E = rho*eps on a well-conditioned range
+        m = (rho > 1e-4) & (rho < 10) & (s > 0.1) & (s < 3)
+        r_, g_ = rho[m], sigma[m]
+        _, vr, vs = orc.functional(fn, r_, g_)
+        h = 1e-5 * r_
+        ep, _, _ = orc.functional(fn, r_ + h, g_)
+        em, _, _ = orc.functional(fn, r_ - h, g_)
+        fd = ((r_ + h) * ep - (r_ - h) * em) / (2 * h)
+        assert (np.abs(fd - vr) / np.abs(vr)).max() < 1e-6, fn
+        if fn in ("PBE", "PBE0"):
+            hs = 1e-4 * g_
+            ep, _, _ = orc.functional(fn, r_, g_ + hs)
+            em, _, _ = orc.functional(fn, r_, g_ - hs)
+            fd = r_ * (ep - em) / (2 * hs)
+            assert (np.abs(fd - vs) / np.abs(vs)).max() < 1e-5, fn
+
+
+def test_functional_thresholds(orc):
+    import gauxc_b200 as gx
+    rho = np.array([0.0, 1e-40, 1e-26, -1e-3])
+    for fn in ("SVWN5", "PBE"):
+        for ev in (gx.Functional(fn).eval_host(rho, np.zeros(4)), orc.functional(fn, rho, np.zeros(4))):
+            for a in ev:
+                assert np.all(np.isfinite(a))
+            assert ev[0][0] == 0 and ev[1][0] == 0 and ev[0][3] == 0
