@@ -128,6 +128,8 @@ def lib():
         "gauxc_b200_functional_eval_host": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_probe_peak": (C.c_double, [S, C.c_int]),
         "gauxc_b200_device_count": (C.c_int, []),
+        "gauxc_b200_set_device": (None, [S, C.c_int]),
+        "gauxc_b200_integrator_stream": (C.c_void_p, [S, _Handle]),
         "gauxc_b200_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -443,6 +445,10 @@ class XCIntegrator(_Obj):
                 "launches", "f_dense", "sum_nbe_npts", "npts", "ntiles", "nbatches", "nitems", "n_el"]
         return dict(zip(keys, o[:14]))
 
+    def stream(self):
+        """cudaStream_t (int) the integrator launches on."""
+        return _call("gauxc_b200_integrator_stream", self.h)
+
     def set_profile(self, on):
         _call("gauxc_b200_integrator_set_profile", self.h, int(on))
 
@@ -466,6 +472,10 @@ class XCIntegratorFactory:
 # ---- misc extension entry points -----------------------------------------------------------
 def device_count():
     return lib().gauxc_b200_device_count()
+
+
+def set_device(dev):
+    _call("gauxc_b200_set_device", int(dev))
 
 
 def probe_peak(which):

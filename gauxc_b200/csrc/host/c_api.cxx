@@ -15,6 +15,7 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
                              double* dy, double* dz);
 double device_probe_peak(int which);
 int device_count();
+void device_set(int dev);
 void device_allreduce(double* dptr, size_t n);
 }  // namespace GauXC
 
@@ -603,6 +604,17 @@ double gauxc_b200_probe_peak(GauXCStatus* status, int which) {
   return v;
 }
 int gauxc_b200_device_count(void) { return device_count(); }
+void gauxc_b200_set_device(GauXCStatus* status, int device) {
+  C_TRY(status)
+  device_set(device);
+  C_CATCH(status)
+}
+void* gauxc_b200_integrator_stream(GauXCStatus* status, const GauXCIntegrator integrator) {
+  C_TRY(status)
+  return INTG(integrator)->stream();
+  C_CATCH(status)
+  return nullptr;
+}
 const char* gauxc_b200_version(void) { return "gauxc_b200 0.1 (sm_100a)"; }
 
 }  // extern "C"

@@ -457,12 +457,13 @@ struct XCIntegrator::Impl {
   std::shared_ptr<Schedule> sched;
   int sched_nmat = 0;
   bool profile = false;
-  cudaEvent_t ev[6]{};
+  std::vector<cudaEvent_t> ev;  // profile mode: 5 events per batch, read after the final sync
   cudaEvent_t e_begin{}, e_lw0{}, e_lw1{}, e_end{};
   double* h_out2 = nullptr;  // pinned
   double* h_pin = nullptr;   // pinned staging for P / VXC
   size_t h_pin_n = 0;
   ~Impl() {
+    for (auto e : ev) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (h_out2) cudaFreeHost(h_out2);
     if (h_pin) cudaFreeHost(h_pin);
@@ -492,7 +493,6 @@ XCIntegrator::XCIntegrator(ExecutionSpace ex, const std::string& input_type,
   require_device();
   impl_ = std::make_shared<Impl>();
   CUDA_CHECK(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking));
-  for (auto& e : impl_->ev) CUDA_CHECK(cudaEventCreate(&e));
   CUDA_CHECK(cudaEventCreate(&impl_->e_begin));
   CUDA_CHECK(cudaEventCreate(&impl_->e_lw0));
   CUDA_CHECK(cudaEventCreate(&impl_->e_lw1));
@@ -557,32 +557,35 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
   double kms[4] = {0, 0, 0, 0};
   long long launches = 0;
+  // profile mode brackets every kernel with events on the launching stream; they are read
+  // after the final synchronise, so the pipeline is not stalled by the measurement
+  if (I.profile)
+    while (I.ev.size() < 5 * sc.batches.size()) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      I.ev.push_back(e);
+    }
+  size_t ib = 0;
   for (auto& b : sc.batches) {
     const int nt = b.tile_end - b.tile_begin;
     const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
-    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[0], s));
+    cudaEvent_t* ev = I.profile ? &I.ev[5 * ib] : nullptr;
+    if (ev) CUDA_CHECK(cudaEventRecord(ev[0], s));
     gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
-    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[1], s));
+    if (ev) CUDA_CHECK(cudaEventRecord(ev[1], s));
     gxb::launch_xmat_density(pv, tl, nt, I.d_ws.p, dP, nbf, I.d_den.p, gga, s);
-    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[2], s));
+    if (ev) CUDA_CHECK(cudaEventRecord(ev[2], s));
     gxb::launch_func_zmat(pv, tl, nt, I.d_ws.p, I.d_den.p, func_->desc, I.d_exc_part.p,
                           I.d_nel_part.p, b.tile_begin, s);
-    if (I.profile) CUDA_CHECK(cudaEventRecord(I.ev[3], s));
+    if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
     launches += 3;
     if (do_vxc) {
       gxb::launch_vxc(pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin, I.d_ws.p,
                       gga, dVXC, nbf, s);
       ++launches;
     }
-    if (I.profile) {
-      CUDA_CHECK(cudaEventRecord(I.ev[4], s));
-      CUDA_CHECK(cudaEventSynchronize(I.ev[4]));
-      for (int k = 0; k < 4; ++k) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, I.ev[k], I.ev[k + 1]);
-        kms[k] += ms;
-      }
-    }
+    if (ev) CUDA_CHECK(cudaEventRecord(ev[4], s));
+    ++ib;
   }
   gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), d_out2, s);
   ++launches;
@@ -599,6 +602,13 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     red_->allreduce_inplace(d_out2, 2, ReductionOp::Sum, s);
   }
   CUDA_CHECK(cudaStreamSynchronize(s));
+  if (I.profile)
+    for (size_t q = 0; q < sc.batches.size(); ++q)
+      for (int k = 0; k < 4; ++k) {
+        float ems = 0;
+        cudaEventElapsedTime(&ems, I.ev[5 * q + k], I.ev[5 * q + k + 1]);
+        kms[k] += ems;
+      }
   float ms = 0;
   cudaEventElapsedTime(&ms, I.e_lw0, I.e_lw1);
   stats_.last_local_work_ms = ms;
@@ -685,6 +695,11 @@ void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t 
 // helpers behind the C ABI extensions
 // ------------------------------------------------------------------------------------
 namespace GauXC {
+
+void device_set(int dev) {
+  require_device();
+  CUDA_CHECK(cudaSetDevice(dev));
+}
 
 int device_count() {
   int n = 0;

@@ -296,6 +296,10 @@ void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional 
 /* FP64 machine-peak probes (roofline denominators): which = 0 DMMA TF/s, 1 DFMA TF/s, 2 HBM copy GB/s */
 double gauxc_b200_probe_peak(GauXCStatus* status, int which);
 int gauxc_b200_device_count(void);
+/* select the CUDA device of the calling thread (one process per GPU: LOCAL_RANK) */
+void gauxc_b200_set_device(GauXCStatus* status, int device);
+/* the cudaStream_t every kernel of this integrator is launched on (for CUDA-event timing) */
+void* gauxc_b200_integrator_stream(GauXCStatus* status, const GauXCIntegrator integrator);
 const char* gauxc_b200_version(void);
 
 #ifdef __cplusplus

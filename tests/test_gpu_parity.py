@@ -1,0 +1,301 @@
+"""GPU parity tests (B200): the CUDA Device path, called through the C ABI, against the CPU oracle
+on the same seeded inputs and against the reference's own golden vectors.
+
+Tolerances are the ones BASELINE.json's north_star states: |dEXC| <= 1e-10 Eh,
+max|dVXC| <= 1e-10, |dN_el| <= 1e-10 (all FP64)."""
+import numpy as np
+import pytest
+
+from conftest import make_lb
+from gauxc_b200 import capi, systems
+import gauxc_b200 as gx
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device visible: the -m gpu tests must run on a B200 (no CPU fallback exists)")
+
+
+def raw_weights_in_device_order(raw, tasks):
+    """Unmodified quadrature weights reordered to the (sorted) device task order; tasks are
+    identified by (iParent, first point)."""
+    key, off = {}, 0
+    for t in range(len(raw["npts"])):
+        n = int(raw["npts"][t])
+        key[(int(raw["iParent"][t]), tuple(raw["points"][off]))] = (off, n)
+        off += n
+    out = np.zeros_like(tasks["weights"])
+    off = 0
+    for t in range(len(tasks["npts"])):
+        n = int(tasks["npts"][t])
+        o, m = key[(int(tasks["iParent"][t]), tuple(tasks["points"][off]))]
+        assert m == n
+        out[off:off + n] = raw["weights"][o:o + n]
+        off += n
+    return out
+
+
+def device_run(lb, func, P, orc=None, atoms=None, check_ssf=True):
+    """modify_weights(Device) + eval_exc_vxc(Device); returns results + the oracle's on the same tasks."""
+    raw = lb.export_tasks()
+    gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(lb)
+    tasks = lb.export_tasks()
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func), lb)
+    exc, vxc = integ.eval_exc_vxc(P)
+    out = dict(exc=exc, vxc=vxc, nel=integ.stats()["n_el"], tasks=tasks, integ=integ)
+    if orc is not None:
+        coords = np.array([a[1:] for a in atoms])
+        if check_ssf:
+            w = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"], tasks["points"],
+                                raw_weights_in_device_order(raw, tasks))
+            out["ssf_err"] = np.abs(w - tasks["weights"]).max()
+    return out
+
+
+def check_against_oracle(orc, basis, P, res, func):
+    ref = orc.exc_vxc(basis.flat(), basis.nbf(), P, res["tasks"], func)
+    assert abs(res["exc"] - ref["exc"]) <= TOL
+    assert np.abs(res["vxc"] - ref["vxc"]).max() <= TOL
+    assert abs(res["nel"] - ref["nel"]) <= TOL
+    assert np.array_equal(res["vxc"], res["vxc"].T)
+    return ref
+
+
+# --------------------------------------------------------------------------------------------------
+def test_collocation_golden(orc):
+    # reference: tests/collocation.cxx:45-91 (water_cc-pVDZ_collocation.hdf5)
+    atoms = systems.geometry("water")
+    basis = gx.BasisSet(systems.make_basis_shells(atoms, "cc-pvdz", spherical=True), normalize=True)
+    col = systems.golden("water_collocation")
+    for e in range(int(col["nentries"][0])):
+        mask, pts = col[f"e{e}_mask"], col[f"e{e}_pts"]
+        res = capi.eval_collocation(basis, mask, pts, gradient=True)
+        for a, k in zip(res, ("eval", "deval_x", "deval_y", "deval_z")):
+            assert np.abs(a - col[f"e{e}_{k}"].reshape(a.shape)).max() < 1e-13
+        ev = capi.eval_collocation(basis, mask, pts, gradient=False)
+        assert np.array_equal(ev, res[0])
+
+
+def test_collocation_all_l_vs_oracle(orc):
+    shells = [dict(l=l, pure=p, exps=[2.3, 0.7, 0.2], coefs=[0.3, 0.6, 0.5], origin=(0.1 * l, -0.2, 0.3))
+              for l in range(5) for p in (False, True)]
+    basis = gx.BasisSet(shells, normalize=True)
+    fb = basis.flat()
+    pts = np.random.default_rng(3).standard_normal((301, 3)) * 1.5  # ragged: 2 tiles + 45 points
+    sl = np.arange(len(shells), dtype=np.int32)
+    dev = capi.eval_collocation(basis, sl, pts, gradient=True)
+    ref = orc.collocation(fb, sl, pts, gradient=True)
+    for a, b in zip(dev, ref):
+        assert np.abs(a - b).max() < 1e-13 * max(1.0, np.abs(b).max())
+
+
+def test_ssf_weights_golden(orc):
+    # reference: tests/weights.cxx:58-77 over benzene_weights_ssf.hdf5
+    g = systems.golden("benzene_weights_ssf")
+    nt = int(g["ntasks"][0])
+    atoms = [(6 if i < 6 else 1, *xyz) for i, xyz in enumerate(g["mol_xyz"])]
+    shells = systems.make_basis_shells(atoms, "cc-pvdz")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", device=True)
+    npts = [len(g[f"t{i}_weights"]) for i in range(nt)]
+    ip = [int(g[f"t{i}_iParent"][0]) for i in range(nt)]
+    dn = [float(g[f"t{i}_dist_nearest"][0]) for i in range(nt)]
+    pts = np.concatenate([g[f"t{i}_points"].reshape(-1, 3) for i in range(nt)])
+    w = np.concatenate([g[f"t{i}_weights"] for i in range(nt)])
+    wm = np.concatenate([g[f"t{i}_weights_mod"] for i in range(nt)])
+    lb.set_tasks(npts, ip, dn, pts, w, [1] * nt, [0] * nt, False)
+    gx.MolecularWeightsFactory("Device").get_instance().modify_weights(lb)
+    out = lb.export_tasks()
+    # device sorts tasks by npts*nbe: map back through (iParent, first point)
+    key = {}
+    off = 0
+    for t in range(nt):
+        key[(ip[t], tuple(pts[off]))] = (off, npts[t])
+        off += npts[t]
+    off = 0
+    err = 0.0
+    for t in range(nt):
+        n = int(out["npts"][t])
+        o, m = key[(int(out["iParent"][t]), tuple(out["points"][off]))]
+        assert m == n
+        err = max(err, np.abs(out["weights"][off:off + n] - wm[o:o + n]).max())
+        off += n
+    assert err < 1e-13 * np.abs(wm).max()
+    with pytest.raises(gx.GauXCError, match="Overwrite Modified Weights"):
+        gx.MolecularWeightsFactory("Device").get_instance().modify_weights(lb)
+
+
+@pytest.mark.parametrize("name,func,pruning", [
+    ("benzene_svwn5_cc-pvdz_ufg_ssf", "SVWN5", "Unpruned"),
+    ("benzene_pbe0_cc-pvdz_ufg_ssf", "PBE0", "Unpruned"),
+    ("benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "SVWN5", "Robust"),
+    ("benzene_svwn5_cc-pvdz_ufg_ssf_treutler_prune", "SVWN5", "Treutler"),
+])
+def test_exc_vxc_golden_and_oracle(orc, benzene_golden, name, func, pruning):
+    # reference: tests/xc_integrator.cxx:185-216, 405-426
+    atoms, shells, P, VXC, EXC = benzene_golden(name, pruning)
+    _, basis, lb = make_lb(atoms, shells, "UltraFineGrid", pruning, normalize=False, device=True)
+    res = device_run(lb, func, P, orc, atoms)
+    assert res["ssf_err"] < 1e-11
+    assert abs(res["exc"] - EXC) <= TOL
+    assert np.abs(res["vxc"] - VXC).max() <= TOL
+    assert np.linalg.norm(res["vxc"] - VXC) / basis.nbf() <= TOL
+    check_against_oracle(orc, basis, P, res, func)
+    # second call on the same integrator: resident data reused, same answer
+    exc2, vxc2 = res["integ"].eval_exc_vxc(P)
+    assert abs(exc2 - res["exc"]) < 1e-12 and np.abs(vxc2 - res["vxc"]).max() < 1e-12
+    # EXC-only and integrate_den entry points
+    assert abs(res["integ"].eval_exc(P) - res["exc"]) < 1e-12
+    assert abs(res["integ"].integrate_den(P) - 0.5 * res["nel"]) < 1e-12
+
+
+@pytest.mark.parametrize("workload,func,grid", [
+    ("water", "SVWN5", "UltraFineGrid"),      # BASELINE config 0
+    ("benzene", "PBE", "UltraFineGrid"),      # BASELINE config 1
+    ("water", "PBE", "FineGrid"),
+    ("water", "SPW92", "FineGrid"),
+])
+def test_exc_vxc_configs_vs_oracle(orc, workload, func, grid):
+    from gauxc_b200.driver import System
+    s = System(workload, device=True, func=func, grid=grid)
+    res = device_run(s.lb, func, s.P, orc, s.atoms)
+    assert res["ssf_err"] < 1e-11
+    ref = check_against_oracle(orc, s.basis, s.P, res, func)
+    nel = sum(a[0] for a in s.atoms)
+    if workload == "benzene":
+        assert abs(ref["nel"] - nel) < 1e-4
+
+
+@pytest.mark.parametrize("workload,stride", [("taxol", 300), ("ubiquitin", 2500)])
+def test_large_config_task_sample_vs_oracle(orc, workload, stride):
+    """BASELINE configs 2/3 at their full task shapes (nbe up to ~1600, merged tasks of 1e4+ points):
+    every `stride`-th task of the real task list, device vs oracle on identical inputs."""
+    from gauxc_b200.driver import System
+    s = System(workload, device=True)
+    full = s.lb.export_tasks()
+    nt = len(full["npts"])
+    pick = np.arange(0, nt, stride)
+    # always include the largest-nbe and the largest-npts task
+    pick = np.unique(np.r_[pick, full["nbe"].argmax(), full["npts"].argmax()])
+    poff = np.r_[0, np.cumsum(full["npts"])]
+    soff = np.r_[0, np.cumsum(full["nshells"])]
+    pts = np.concatenate([full["points"][poff[t]:poff[t + 1]] for t in pick])
+    w = np.concatenate([full["weights"][poff[t]:poff[t + 1]] for t in pick])
+    sl = np.concatenate([full["shell_lists"][soff[t]:soff[t + 1]] for t in pick])
+    s.lb.set_tasks(full["npts"][pick], full["iParent"][pick], full["dist_nearest"][pick], pts, w,
+                   full["nshells"][pick], sl, False)
+    res = device_run(s.lb, s.func_name, s.P, orc, s.atoms, check_ssf=(workload == "taxol"))
+    if "ssf_err" in res:
+        assert res["ssf_err"] < 1e-11
+    check_against_oracle(orc, s.basis, s.P, res, s.func_name)
+
+
+def test_edge_cases_ragged_tasks_and_leading_dimensions(orc):
+    """npts = 1, npts just above/below a 128-point tile, a single-shell task, ldp/ldvxc > nbf."""
+    atoms = systems.geometry("water")
+    shells = systems.make_basis_shells(atoms, "cc-pvdz")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", device=True)
+    rng = np.random.default_rng(5)
+    nbf = basis.nbf()
+    nsh = basis.nshells()
+    npts = [1, 127, 128, 129, 5, 300]
+    lists = [list(range(nsh)), list(range(nsh)), [0], [1, 4, 7], list(range(0, nsh, 2)), list(range(nsh))]
+    pts = rng.standard_normal((sum(npts), 3)) * 1.2
+    w = rng.uniform(0.01, 0.1, sum(npts))
+    lb.set_tasks(npts, [0, 1, 2, 0, 1, 2], [1.8] * 6, pts, w, [len(l) for l in lists],
+                 [x for l in lists for x in l], True)
+    P = systems.synthetic_density(atoms, shells)
+    for func in ("SVWN5", "PBE"):
+        integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func), lb)
+        tasks = lb.export_tasks()
+        ldp, ldv = nbf + 3, nbf + 5
+        Pbig = np.zeros((ldp, nbf), order="F")
+        Pbig[:nbf] = P
+        Vbig = np.full((ldv, nbf), 7.0, order="F")
+        exc = integ.eval_exc_vxc_raw(nbf, nbf, Pbig, ldp, Vbig, ldv)
+        ref = orc.exc_vxc(basis.flat(), nbf, P, tasks, func)
+        assert abs(exc - ref["exc"]) <= TOL
+        assert np.abs(Vbig[:nbf] - ref["vxc"]).max() <= TOL
+        assert np.all(Vbig[nbf:] == 7.0)  # padding rows untouched
+
+
+def test_empty_task_list_gives_zero():
+    atoms = systems.geometry("water")
+    shells = systems.make_basis_shells(atoms, "cc-pvdz")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", device=True)
+    lb.set_tasks([], [], [], np.zeros((0, 3)), [], [], [], True)
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional("PBE"), lb)
+    exc, vxc = integ.eval_exc_vxc(systems.synthetic_density(atoms, shells))
+    assert exc == 0.0 and not vxc.any()
+
+
+def test_error_behaviour_matches_reference():
+    atoms = systems.geometry("water")
+    shells = systems.make_basis_shells(atoms, "cc-pvdz")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", device=True)
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional("SVWN5"), lb)
+    nbf = basis.nbf()
+    P = systems.synthetic_density(atoms, shells)
+    with pytest.raises(gx.GauXCError, match="Weights Have Not Been Modified"):
+        integ.eval_exc_vxc(P)
+    gx.MolecularWeightsFactory("Device").get_instance().modify_weights(lb)
+    V = np.zeros((nbf, nbf), order="F")
+    with pytest.raises(gx.GauXCError, match="Must Be Square"):
+        integ.eval_exc_vxc_raw(nbf, nbf - 1, P, nbf, V, nbf)
+    with pytest.raises(gx.GauXCError, match="Same Dimension as Basis"):
+        integ.eval_exc_vxc_raw(nbf - 1, nbf - 1, P, nbf, V, nbf)
+    with pytest.raises(gx.GauXCError, match="Invalid LDP"):
+        integ.eval_exc_vxc_raw(nbf, nbf, P, nbf - 1, V, nbf)
+    with pytest.raises(gx.GauXCError, match="Invalid LDVXC"):
+        integ.eval_exc_vxc_raw(nbf, nbf, P, nbf, V, nbf - 1)
+    with pytest.raises(gx.GauXCError, match="Not Recognized"):
+        gx.XCIntegratorFactory("Device", "Replicated", "Default", "Bogus").get_instance(gx.Functional("SVWN5"), lb)
+    with pytest.raises(gx.GauXCError, match="BasicMPI"):
+        gx.XCIntegratorFactory("Device", "Replicated", "Default", "Default", "BasicMPI") \
+            .get_instance(gx.Functional("SVWN5"), lb)
+
+
+def test_rank_partition_sums_to_whole(orc):
+    """The 2-rank deal of grid batches (replicated_host_load_balancer.cxx:106-115): the two partial
+    VXC/EXC, each computed on the GPU, add up to the single-rank result (what the NCCL allreduce
+    produces; the NCCL call itself is exercised by bench.py --gpus N)."""
+    atoms, shells, P, _, _ = systems.golden_system("benzene_pbe0_cc-pvdz_ufg_ssf")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", normalize=False, device=True)
+    whole = device_run(lb, "PBE", P)
+    exc, nel, vxc = 0.0, 0.0, 0.0
+    for r in range(2):
+        _, _, lbr = make_lb(atoms, shells, "FineGrid", normalize=False, device=False, rank=r, size=2)
+        t = lbr.export_tasks()
+        _, _, lb1 = make_lb(atoms, shells, "FineGrid", normalize=False, device=True)
+        lb1.set_tasks(t["npts"], t["iParent"], t["dist_nearest"], t["points"], t["weights"], t["nshells"],
+                      t["shell_lists"], False)
+        part = device_run(lb1, "PBE", P)
+        exc += part["exc"]; nel += part["nel"]; vxc = vxc + part["vxc"]
+    assert abs(exc - whole["exc"]) <= TOL and abs(nel - whole["nel"]) <= TOL
+    assert np.abs(vxc - whole["vxc"]).max() <= TOL
+
+
+def test_device_resident_entry_point_and_small_workspace(orc, monkeypatch):
+    """eval through device pointers (no H2D/D2H) and with a workspace so small that the tile list
+    is cut into many batches: same numbers."""
+    import torch
+    atoms, shells, P, _, _ = systems.golden_system("benzene_pbe0_cc-pvdz_ufg_ssf")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", normalize=False, device=True)
+    res = device_run(lb, "PBE", P)
+    nbf = basis.nbf()
+    dP = torch.from_numpy(np.ascontiguousarray(P)).cuda()
+    dV = torch.zeros((nbf, nbf), dtype=torch.float64, device="cuda")
+    d2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+    res["integ"].eval_exc_vxc_device(dP.data_ptr(), dV.data_ptr(), d2.data_ptr())
+    torch.cuda.synchronize()
+    assert abs(float(d2[0]) - res["exc"]) < 1e-12
+    assert np.abs(dV.cpu().numpy() - res["vxc"]).max() < 1e-12
+    monkeypatch.setenv("GAUXC_B200_WORKSPACE_MB", "8")
+    _, _, lb2 = make_lb(atoms, shells, "FineGrid", normalize=False, device=True)
+    res2 = device_run(lb2, "PBE", P)
+    assert res2["integ"].stats()["nbatches"] > 4
+    assert abs(res2["exc"] - res["exc"]) < 1e-11
+    assert np.abs(res2["vxc"] - res["vxc"]).max() < 1e-11
