@@ -121,14 +121,17 @@ def oracle_sample(sys_, tasks, seconds, threads=None):
     fb = sys_.basis.flat()
     nt = len(tasks["npts"])
     cost = tasks["nbe"].astype(float) ** 2 * tasks["npts"] * 4
-    # calibrate on a small sample first (about 1/400 of the flops)
+    # calibrate the stride on growing samples until one takes >= 1 s (first calls pay thread start-up)
     stride = max(1, nt // 64)
-    t0 = time.time()
-    r = orc.exc_vxc(fb, sys_.nbf, sys_.P, tasks, sys_.func_name, task_stride=stride)
-    dt = max(time.time() - t0, 1e-3)
+    while True:
+        t0 = time.time()
+        r = orc.exc_vxc(fb, sys_.nbf, sys_.P, tasks, sys_.func_name, task_stride=stride)
+        dt = max(time.time() - t0, 1e-3)
+        if dt >= 1.0 or stride == 1:
+            break
+        stride = max(1, stride // 4)
     rate = r["flops"] / dt  # dense flops/s seen by the calibration run
-    want = rate * seconds
-    stride = int(max(1, np.ceil(cost.sum() / max(want, 1.0))))
+    stride = int(max(1, np.ceil(cost.sum() / max(rate * seconds, 1.0))))
     t0 = time.time()
     r = orc.exc_vxc(fb, sys_.nbf, sys_.P, tasks, sys_.func_name, task_stride=stride)
     dt = time.time() - t0

@@ -8,8 +8,9 @@
 // cartesian xx,xy,xz,yy,yz,zz; spherical m=-l..l (p pure: y,z,x).
 //
 // One CTA = one tile of TP points, thread = point; the tile's shells are staged in shared
-// memory once and broadcast.  Output matrices are [mu][TP], point index fastest, so every
-// store is a fully coalesced 1 KB row.  Bound: FP64 exp/ALU; HBM traffic = the write of
+// memory once and broadcast.  Output matrices are [mu][TP], point index fastest (XOR-swizzled
+// inside 128-byte lines, rows padded to a multiple of 16), so every store is a fully coalesced
+// 1 KB row.  Bound: FP64 exp/ALU; HBM traffic = the write of
 // 8*k*nbe bytes per point (k = 1 LDA, 4 GGA).
 #include "kernels.cuh"
 
@@ -19,10 +20,11 @@ namespace {
 
 constexpr int MAX_STAGED_PRIMS = 512;
 
+// element (row, i) of a tile matrix lives at column i ^ ((row & 3) << 2) (device_plan.hpp)
 template <bool GRAD>
 __device__ __forceinline__ void store(double* __restrict__ B, size_t ms, int row, int i, bool ok,
                                       double v, double gx, double gy, double gz) {
-  const size_t o = (size_t)row * TP + i;
+  const size_t o = (size_t)row * TP + swz(row, i);
   B[o] = ok ? v : 0.;
   if (GRAD) {
     B[o + ms] = ok ? gx : 0.;
@@ -42,7 +44,10 @@ __global__ void __launch_bounds__(TP) collocation_kernel(PlanView pv,
   const int ip = tile.pt_off + (ok ? i : 0);
   const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];
   double* __restrict__ B = ws + tile.ws_off;
-  const size_t ms = (size_t)task.nbe * TP;
+  const int nbp = pad16(task.nbe);
+  const size_t ms = (size_t)nbp * TP;
+  // zero pad rows: they are K rows of the X = B P contraction
+  for (int r = task.nbe; r < nbp; ++r) store<GRAD>(B, ms, r, i, false, 0., 0., 0., 0.);
 
   const double sqrt3 = 1.7320508075688772935;
 

@@ -6,14 +6,28 @@
 //     (tasks sorted by npts*nbe descending like the reference,
 //      incore_replicated_xc_device_integrator_exc_vxc.hpp:254-257).  Resident across calls.
 //   * a task is cut into TILES of <= TP consecutive points that share the task's shell list.
-//   * per batch of tiles a workspace holds, per tile, NMAT matrices [nbe][TP]
-//     (point index fastest): B, (dBx,dBy,dBz for GGA), Z; and per point rho, drho(3).
+//   * per batch of tiles a workspace holds, per tile, NMAT matrices [nbp][TP] (nbp = nbe
+//     rounded up to 16 rows, pad rows are zero): B, (dBx,dBy,dBz for GGA), Z.  Rows are 1 KB
+//     (point index fastest) and XOR-swizzled: element (row, i) lives at column
+//     i ^ ((row & 3) << 2).  With that one permutation a TMA box of 16 rows x 128 points (the
+//     A operand of X = B P) and a TMA box of 128 rows x 16 points (both operands of B^T Z)
+//     land in shared memory dense AND conflict-free for the m8n8k4 DMMA fragment loads,
+//     while every global row access stays fully coalesced.
 #pragma once
 #include <cstdint>
+
+#if defined(__CUDACC__)
+#define GXB_HOST_DEVICE __host__ __device__
+#else
+#define GXB_HOST_DEVICE
+#endif
 
 namespace gxb {
 
 constexpr int TP = 128;  // points per tile
+
+GXB_HOST_DEVICE inline int pad16(int nbe) { return (nbe + 15) & ~15; }
+GXB_HOST_DEVICE inline int swz(int row, int i) { return i ^ ((row & 3) << 2); }
 
 struct DevShell {
   double x, y, z;
@@ -42,6 +56,7 @@ struct DevTile {
 struct VxcItem {
   int task, mblk, nblk, tile_begin, tile_end, pad0, pad1, pad2;
 };
+constexpr int VXC_BLK = 128;  // output block edge of the VXC rank update
 
 struct PlanView {
   // static

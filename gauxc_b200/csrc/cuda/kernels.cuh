@@ -1,6 +1,7 @@
 // Launch wrappers of the sm_100a kernels (definitions in *.cu next to this file).
 #pragma once
 #include "device_plan.hpp"
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace gxb {
@@ -9,18 +10,18 @@ namespace gxb {
 void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws,
                         bool gradient, cudaStream_t s);
 
-// K_B  X = P_sub * B on the FP64 tensor pipe fused with rho / grad rho
-void launch_xmat_density(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws,
-                         const double* P, int ldp, double* den, bool gga, cudaStream_t s);
+// K_F  fused persistent kernel: X = B P_sub (DMMA) -> rho / grad rho -> functional, weights,
+//      EXC / N_EL tile partials -> Z.  tmapA: box of 16 rows x 128 points over the workspace;
+//      order / cta_begin: host-balanced tile lists per CTA.
+void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, const int* order,
+                  const int* cta_begin, int ncta, double* ws, const double* P, int ldp,
+                  FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
+                  cudaStream_t s);
 
-// K_C  functional evaluation, weight scaling, EXC/N_EL partials, Z formation
-void launch_func_zmat(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws,
-                      const double* den, FunctionalDesc func, double* exc_part,
-                      double* nel_part, int part_off, cudaStream_t s);
-
-// K_D  VXC_sub += B^T Z on the FP64 tensor pipe, scatter-added (lower triangle) into VXC
-void launch_vxc(const PlanView& pv, const DevTile* tiles, const VxcItem* items, int nitems,
-                const double* ws, bool gga, double* VXC, int ldv, cudaStream_t s);
+// K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe, scatter-added (lower triangle) into VXC.
+//      tmapV: box of 128 rows x 16 points over the workspace.
+void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
+                int nitems, bool gga, double* VXC, int ldv, cudaStream_t s);
 
 // finalisation
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

@@ -1,0 +1,232 @@
+// K_D: VXC_sub = B^T Z + Z^T B on the FP64 DMMA pipe with a scatter-add into the full matrix,
+// plus the finalisation kernels (partials reduction, symmetrise).
+//
+// Host semantics matched: inc_vxc (reference_local_host_work_driver.cxx:1678-1692: dsyr2k lower +
+// inc_by_submat_atomic, host/util.hpp:130-168) and the symmetrise loop of the host driver
+// (reference_replicated_xc_host_integrator_exc_vxc.hpp:577-583).  Replaces the reference device
+// path's per-task cuBLAS dsyr2k + sym_task_inc_potential (scheme1_base.cxx:1711-1766,
+// cuda_inc_potential.cu) by one grouped launch per batch.
+//
+// An item = one 128 x 128 output block (mblk, nblk) of M = B^T Z of one task, accumulated over a
+// run of that task's tiles (K = points).  Both operands arrive as TMA boxes of 128 basis rows x
+// 16 points straight from the swizzled workspace (dense + conflict-free, device_plan.hpp) through
+// a 5-stage mbarrier ring fed by one producer thread; 16 MMA warps (4 x 4, warp tile 32 x 32).
+// M + M^T is folded into the LOWER triangle of VXC with FP64 reductions (RED.ADD.F64).  For LDA
+// Z = diag(1/2 w vrho) B makes M symmetric: only blocks mblk >= nblk are scheduled (`sym`).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace gxb {
+
+namespace {
+
+constexpr int VK = 16;  // points (K) per stage
+constexpr int VSTAGES = 5;
+constexpr int V_MMA_WARPS = 16;
+constexpr int V_MMA_THREADS = V_MMA_WARPS * 32;
+constexpr int V_THREADS = V_MMA_THREADS + 32;
+
+struct VxcSmem {
+  double A[VSTAGES][VXC_BLK][VK];
+  double Z[VSTAGES][VXC_BLK][VK];
+  uint64_t full[VSTAGES], empty[VSTAGES];
+};
+constexpr size_t VXC_SMEM_BYTES = sizeof(VxcSmem) + 1024;
+
+__global__ void __launch_bounds__(V_THREADS, 1)
+vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile* __restrict__ tiles,
+           const VxcItem* __restrict__ items, int zmat, int sym, double* __restrict__ VXC, int ldv) {
+  extern __shared__ uint8_t smem_raw[];
+  VxcSmem& S = *reinterpret_cast<VxcSmem*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const VxcItem item = items[blockIdx.x];
+  const DevTask task = pv.tasks[item.task];
+  const int nbe = task.nbe;
+  const int nbp = pad16(nbe);
+  const int m0 = item.mblk * VXC_BLK, n0 = item.nblk * VXC_BLK;
+
+  if (tid == 0) {
+    for (int s = 0; s < VSTAGES; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], V_MMA_THREADS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == V_MMA_WARPS) {
+    // ---------------------------------------------------------------- producer (one thread)
+    if (lane == 0) {
+      tma_prefetch_desc(&tmapV);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int q = item.tile_begin; q < item.tile_end; ++q) {
+        const DevTile tl = tiles[q];
+        const int rowB = (int)(tl.ws_off / TP);
+        const int rowZ = rowB + zmat * nbp;
+        const int nks = (tl.npts + VK - 1) / VK;
+        for (int ks = 0; ks < nks; ++ks) {
+          mbar_wait(&S.empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&S.full[s], 2 * VXC_BLK * VK * sizeof(double));
+          tma_load_2d(&S.A[s][0][0], &tmapV, &S.full[s], ks * VK, rowB + m0);
+          tma_load_2d(&S.Z[s][0][0], &tmapV, &S.full[s], ks * VK, rowZ + n0);
+          if (++s == VSTAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ MMA warps
+  const int g = lane >> 2, t = lane & 3;
+  // sub-partition = warp & 3 = (wm + wn) & 3: idle row / column blocks of ragged output blocks are
+  // spread over all four DMMA pipes
+  const int wm = warp >> 2;
+  const int wn = ((warp & 3) - wm) & 3;
+  const int mi_cnt = min(4, max(0, (nbe - m0 - wm * 32 + 7) / 8));
+  const int ni_cnt = min(4, max(0, (nbe - n0 - wn * 32 + 7) / 8));
+  const bool diag = sym && item.mblk == item.nblk;
+  const bool active = mi_cnt > 0 && ni_cnt > 0 && !(diag && wn > wm);
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+
+  {
+    int s = 0;
+    uint32_t ph = 0;
+    const int sw = (g & 3) << 2;
+    for (int q = item.tile_begin; q < item.tile_end; ++q) {
+      const int nks = (tiles[q].npts + VK - 1) / VK;
+      for (int ks = 0; ks < nks; ++ks) {
+        mbar_wait(&S.full[s], ph);
+        if (active) {
+          const double* as = &S.A[s][wm * 32 + g][0];
+          const double* zs = &S.Z[s][wn * 32 + g][0];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int col = (kk * 4 + t) ^ sw;
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * VK + col];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = zs[ni * 8 * VK + col];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni)
+                if (mi < mi_cnt && ni < ni_cnt) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          }
+        }
+        mbar_arrive(&S.empty[s]);
+        if (++s == VSTAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+  if (!active) return;
+
+  // scatter: VXC_sub = M + M^T, only the lower triangle of the full matrix is accumulated
+  const int* __restrict__ ao = pv.task_ao + task.ao_off;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      if (mi >= mi_cnt || ni >= ni_cnt) continue;
+      const int mu = m0 + wm * 32 + mi * 8 + g;
+      if (mu >= nbe) continue;
+      const int gm = __ldg(ao + mu);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int nu = n0 + wn * 32 + ni * 8 + 2 * t + j;
+        if (nu >= nbe) continue;
+        double v = acc[mi][ni][j];
+        if (sym) {
+          if (diag && nu > mu) continue;  // M symmetric: the mirror entry carries it
+          v *= 2.;
+        } else if (mu == nu) {
+          v *= 2.;
+        }
+        const int gn = __ldg(ao + nu);
+        const int hi = max(gm, gn), lo = min(gm, gn);
+        atomicAdd(VXC + (size_t)lo * ldv + hi, v);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalisation kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void two_sum(double& s, double& c, double x) {
+  // Neumaier compensated accumulation
+  const double tsum = s + x;
+  if (fabs(s) >= fabs(x)) c += (s - tsum) + x;
+  else c += (x - tsum) + s;
+  s = tsum;
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ e,
+                                                               const double* __restrict__ n,
+                                                               int cnt, double* __restrict__ out2) {
+  __shared__ double sh[4][256];
+  double es = 0, ec = 0, ns = 0, nc = 0;
+  for (int i = threadIdx.x; i < cnt; i += 256) {
+    two_sum(es, ec, e[i]);
+    two_sum(ns, nc, n[i]);
+  }
+  sh[0][threadIdx.x] = es; sh[1][threadIdx.x] = ec;
+  sh[2][threadIdx.x] = ns; sh[3][threadIdx.x] = nc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double Es = 0, Ec = 0, Ns = 0, Nc = 0;
+    for (int i = 0; i < 256; ++i) {
+      two_sum(Es, Ec, sh[0][i]); Ec += sh[1][i];
+      two_sum(Ns, Nc, sh[2][i]); Nc += sh[3][i];
+    }
+    out2[0] = Es + Ec;
+    out2[1] = Ns + Nc;
+  }
+}
+
+// upper <- lower (host driver :577-583; device K12 symmetrize_mat.cu)
+__global__ void symmetrize_kernel(double* __restrict__ A, int n, int ld) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bj > bi) return;  // only blocks on/below the diagonal are sources
+  const int i = bi * 32 + threadIdx.x, j = bj * 32 + threadIdx.y;
+  // A(i,j) col-major, i>=j in the lower triangle
+  if (i < n && j < n) tile[threadIdx.y][threadIdx.x] = A[(size_t)j * ld + i];
+  __syncthreads();
+  const int ti = bj * 32 + threadIdx.x;  // row index in the upper block
+  const int tj = bi * 32 + threadIdx.y;  // col index in the upper block
+  if (ti < n && tj < n && tj > ti) A[(size_t)tj * ld + ti] = tile[threadIdx.x][threadIdx.y];
+}
+
+}  // namespace
+
+void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
+                int nitems, bool gga, double* VXC, int ldv, cudaStream_t s) {
+  if (nitems <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(vxc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VXC_SMEM_BYTES);
+    attr_set = true;
+  }
+  vxc_kernel<<<nitems, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapV, pv, tiles, items, gga ? 4 : 1, gga ? 0 : 1,
+                                                       VXC, ldv);
+}
+
+void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,
+                            cudaStream_t s) {
+  reduce_partials_kernel<<<1, 256, 0, s>>>(exc_part, nel_part, n, out2);
+}
+
+void launch_symmetrize(double* VXC, int nbf, int ldv, cudaStream_t s) {
+  const int nb = (nbf + 31) / 32;
+  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 32), 0, s>>>(VXC, nbf, ldv);
+}
+
+}  // namespace gxb

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <nccl.h>
 #include <numeric>
+#include <queue>
 
 namespace GauXC {
 
@@ -77,8 +78,13 @@ struct Schedule {
   };
   std::vector<Batch> batches;
   std::vector<gxb::VxcItem> items;
+  // fused kernel: per batch a permutation of the batch's tiles grouped per CTA (longest
+  // processing time first over `ncta` persistent CTAs) and the ncta+1 group offsets
+  std::vector<int> order, cta_begin;
+  int ncta = 0;
   DevBuf<gxb::DevTile> d_tiles;
   DevBuf<gxb::VxcItem> d_items;
+  DevBuf<int> d_order, d_cta_begin;
   size_t ws_doubles = 0;
   int max_batch_tiles = 0;
 };
@@ -233,24 +239,27 @@ std::shared_ptr<DevicePlan> get_device_plan(LoadBalancer& lb) {
 }
 
 static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size_t ws_doubles,
-                                                int tiles_per_item) {
+                                                int tiles_per_item, int ncta, bool sym) {
   auto sc = std::make_shared<Schedule>();
   sc->tiles = plan.tiles;
+  sc->ncta = ncta;
+  sc->order.resize(sc->tiles.size());
   size_t cur = 0, ws_max = 0;
   Schedule::Batch b{0, 0, 0, 0};
   auto close_batch = [&](int tile_end) {
     b.tile_end = tile_end;
-    // VXC items: runs of tiles of one task, cut into chunks, times the output blocks
+    // VXC items: runs of tiles of one task, cut into chunks, times the 128 x 128 output blocks
+    // (lower block triangle only when M = B^T Z is symmetric, i.e. LDA)
     b.item_begin = (int)sc->items.size();
     int q = b.tile_begin;
     while (q < b.tile_end) {
       int e = q;
       while (e < b.tile_end && sc->tiles[e].task == sc->tiles[q].task) ++e;
       const int nbe = plan.tasks[sc->tiles[q].task].nbe;
-      const int mb = (nbe + 127) / 128, nb = (nbe + 63) / 64;
+      const int nb = (nbe + gxb::VXC_BLK - 1) / gxb::VXC_BLK;
       for (int c = q; c < e; c += tiles_per_item)
-        for (int im = 0; im < mb; ++im)
-          for (int in = 0; in < nb; ++in) {
+        for (int im = 0; im < nb; ++im)
+          for (int in = 0; in < (sym ? im + 1 : nb); ++in) {
             gxb::VxcItem it{};
             it.task = sc->tiles[q].task;
             it.mblk = im;
@@ -262,12 +271,39 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
       q = e;
     }
     b.item_end = (int)sc->items.size();
+    // fused kernel tile lists: LPT over ncta persistent CTAs, cost ~ DMMA time + streamed bytes
+    {
+      const int nt = b.tile_end - b.tile_begin;
+      std::vector<int> idx(nt);
+      std::iota(idx.begin(), idx.end(), 0);
+      auto cost = [&](int i) {
+        const double n = plan.tasks[sc->tiles[b.tile_begin + i].task].nbe;
+        return n * (n + 256.);
+      };
+      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return cost(x) > cost(y); });
+      std::vector<std::vector<int>> lists(ncta);
+      using QE = std::pair<double, int>;
+      std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+      for (int c = 0; c < ncta; ++c) pq.push({0., c});
+      for (int i : idx) {
+        auto [load, c] = pq.top();
+        pq.pop();
+        lists[c].push_back(i);
+        pq.push({load + cost(i), c});
+      }
+      int o = 0;
+      for (int c = 0; c < ncta; ++c) {
+        sc->cta_begin.push_back(o);
+        for (int i : lists[c]) sc->order[b.tile_begin + o++] = i;
+      }
+      sc->cta_begin.push_back(o);
+    }
     sc->batches.push_back(b);
     sc->max_batch_tiles = std::max(sc->max_batch_tiles, b.tile_end - b.tile_begin);
     ws_max = std::max(ws_max, cur);
   };
   for (int i = 0; i < (int)sc->tiles.size(); ++i) {
-    const size_t need = (size_t)nmat * plan.tasks[sc->tiles[i].task].nbe * gxb::TP;
+    const size_t need = (size_t)nmat * gxb::pad16(plan.tasks[sc->tiles[i].task].nbe) * gxb::TP;
     if (need > ws_doubles) GAUXC_GENERIC_EXCEPTION("Device Workspace Too Small For One Tile");
     if (cur + need > ws_doubles) {
       close_batch(i);
@@ -281,8 +317,42 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
+  sc->d_order.upload(sc->order);
+  sc->d_cta_begin.upload(sc->cta_begin);
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
+}
+
+// ------------------------------------------------------------------------------------
+// TMA descriptors over the batch workspace viewed as [rows][128 points] FP64
+// ------------------------------------------------------------------------------------
+static CUtensorMap make_ws_tensor_map(double* base, size_t ndoubles, int box_cols, int box_rows) {
+  using encode_t = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                CUtensorMapFloatOOBfill);
+  static encode_t encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      GAUXC_GENERIC_EXCEPTION("CUDA Failed: cuTensorMapEncodeTiled unavailable");
+    encode = (encode_t)fn;
+  }
+  CUtensorMap m;
+  std::memset(&m, 0, sizeof(m));
+  const cuuint64_t rows = std::max<size_t>(1, ndoubles / gxb::TP);
+  const cuuint64_t gdim[2] = {(cuuint64_t)gxb::TP, rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)gxb::TP * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    GAUXC_GENERIC_EXCEPTION("CUDA Failed: cuTensorMapEncodeTiled returned " + std::to_string((int)r));
+  return m;
 }
 
 // ------------------------------------------------------------------------------------
@@ -452,7 +522,9 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
 // ------------------------------------------------------------------------------------
 struct XCIntegrator::Impl {
   cudaStream_t stream = nullptr;
-  DevBuf<double> dP, dVXC, d_ws, d_den, d_exc_part, d_nel_part, d_out2;
+  DevBuf<double> dP, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
+  CUtensorMap tmapA{}, tmapV{};  // TMA views of d_ws: 16 rows x 128 points / 128 rows x 16 points
+  int ncta = 0;
   std::shared_ptr<DevicePlan> plan;
   std::shared_ptr<Schedule> sched;
   int sched_nmat = 0;
@@ -531,21 +603,33 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   const bool gga = func_->is_gga();
   const int nmat = gga ? 5 : 2;
   cudaStream_t s = I.stream;
+  if (plan.nbf && (size_t)plan.nbf * plan.nbf > (size_t)std::numeric_limits<int>::max() * 64)
+    GAUXC_GENERIC_EXCEPTION("Basis Too Large");
 
   if (!I.sched || I.sched_nmat != nmat) {
     auto it = plan.schedules.find(nmat);
     if (it == plan.schedules.end()) {
       const size_t wsb = workspace_bytes(*lb_);
-      int tpi = 8;
+      int tpi = 16;
       if (const char* e = std::getenv("GAUXC_B200_TILES_PER_ITEM")) tpi = std::max(1, std::atoi(e));
-      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), tpi);
+      if (!I.ncta) {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&I.ncta, cudaDevAttrMultiProcessorCount, dev));
+      }
+      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), tpi, I.ncta, !gga);
       plan.schedule_ws_bytes = wsb;
       it = plan.schedules.find(nmat);
     }
     I.sched = it->second;
     I.sched_nmat = nmat;
     I.d_ws.alloc(I.sched->ws_doubles);
-    I.d_den.alloc((size_t)4 * I.sched->max_batch_tiles * gxb::TP);
+    if (I.sched->ws_doubles) {
+      // TMA may read (never use) rows of a neighbouring matrix: keep every byte finite
+      CUDA_CHECK(cudaMemsetAsync(I.d_ws.p, 0, I.sched->ws_doubles * sizeof(double), s));
+      I.tmapA = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, gxb::TP, 16);
+      I.tmapV = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 16, gxb::VXC_BLK);
+    }
     I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
     I.d_nel_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
   }
@@ -573,15 +657,15 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     if (ev) CUDA_CHECK(cudaEventRecord(ev[0], s));
     gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[1], s));
-    gxb::launch_xmat_density(pv, tl, nt, I.d_ws.p, dP, nbf, I.d_den.p, gga, s);
+    gxb::launch_fused(I.tmapA, pv, tl, sc.d_order.p + b.tile_begin,
+                      sc.d_cta_begin.p + ib * (size_t)(sc.ncta + 1), sc.ncta, I.d_ws.p, dP, nbf,
+                      func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[2], s));
-    gxb::launch_func_zmat(pv, tl, nt, I.d_ws.p, I.d_den.p, func_->desc, I.d_exc_part.p,
-                          I.d_nel_part.p, b.tile_begin, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
-    launches += 3;
+    launches += 2;
     if (do_vxc) {
-      gxb::launch_vxc(pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin, I.d_ws.p,
-                      gga, dVXC, nbf, s);
+      gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin, gga,
+                      dVXC, nbf, s);
       ++launches;
     }
     if (ev) CUDA_CHECK(cudaEventRecord(ev[4], s));
@@ -766,7 +850,7 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   for (int p0 = 0; p0 < npts; p0 += gxb::TP) {
     gxb::DevTile t{};
     t.task = 0; t.pt_off = p0; t.npts = (int)std::min<int64_t>(gxb::TP, npts - p0);
-    t.ws_off = (int64_t)tiles.size() * nmat * nbe * gxb::TP;
+    t.ws_off = (int64_t)tiles.size() * nmat * gxb::pad16(nbe) * gxb::TP;
     tiles.push_back(t);
   }
   std::vector<double> px(npts), py(npts), pz(npts);
@@ -777,7 +861,7 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   d_px.upload(px); d_py.upload(py); d_pz.upload(pz);
   d_task.upload(std::vector<gxb::DevTask>{task}); d_tiles.upload(tiles);
   d_tsh.upload(tsh); d_tbf.upload(tbf);
-  const size_t wsn = tiles.size() * (size_t)nmat * nbe * gxb::TP;
+  const size_t wsn = tiles.size() * (size_t)nmat * gxb::pad16(nbe) * gxb::TP;
   d_ws.alloc(wsn);
   gxb::PlanView pv{};
   pv.shells = d_sh.p; pv.prim_alpha = d_a.p; pv.prim_coeff = d_c.p; pv.tasks = d_task.p;
@@ -786,11 +870,11 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   CUDA_CHECK(cudaGetLastError());
   std::vector<double> h(wsn);
   CUDA_CHECK(cudaMemcpy(h.data(), d_ws.p, wsn * sizeof(double), cudaMemcpyDeviceToHost));
-  const size_t ms = (size_t)nbe * gxb::TP;
+  const size_t ms = (size_t)gxb::pad16(nbe) * gxb::TP;
   for (size_t t = 0; t < tiles.size(); ++t)
     for (int i = 0; i < tiles[t].npts; ++i)
       for (int mu = 0; mu < nbe; ++mu) {
-        const size_t src = (size_t)tiles[t].ws_off + (size_t)mu * gxb::TP + i;
+        const size_t src = (size_t)tiles[t].ws_off + (size_t)mu * gxb::TP + gxb::swz(mu, i);
         const size_t dst = (size_t)(tiles[t].pt_off + i) * nbe + mu;
         eval[dst] = h[src];
         if (grad) { dx[dst] = h[src + ms]; dy[dst] = h[src + 2 * ms]; dz[dst] = h[src + 3 * ms]; }

@@ -77,7 +77,7 @@ def test_collocation_golden(orc):
         for a, k in zip(res, ("eval", "deval_x", "deval_y", "deval_z")):
             assert np.abs(a - col[f"e{e}_{k}"].reshape(a.shape)).max() < 1e-13
         ev = capi.eval_collocation(basis, mask, pts, gradient=False)
-        assert np.array_equal(ev, res[0])
+        assert np.abs(ev - res[0]).max() < 1e-15  # GRAD/no-GRAD instantiations differ by fma contraction only
 
 
 def test_collocation_all_l_vs_oracle(orc):
