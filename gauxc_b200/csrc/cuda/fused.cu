@@ -10,12 +10,16 @@
 //
 // One CTA per SM walks a host-balanced list of tiles.  Five roles, 17 warps:
 //   producer (1 warp) : TMA box loads of B^T (16 basis rows x 128 points) + LDGSTS gather of the
-//                       matching 16 x 64 block of P through the task's AO map, 4-stage mbarrier ring
-//   MMA      (8 warps): 128 x 64 chunk of X on the DMMA pipe (m8n8k4), hands each finished chunk
+//                       matching 16 x 64 block of P through the task's AO map, 5-stage mbarrier ring
+//   MMA      (8 warps): 128 x 64 chunk of X on the DMMA pipe (m8n8k4); warp tile 64 x 16 with the two
+//                       row halves of a column strip on the SAME SM sub-partition, so ragged tiles
+//                       (npts < 128) load the four DMMA pipes evenly.  Each finished chunk is handed
 //                       to the density warps through shared memory
-//   density  (4 warps): thread = grid point; rho += X.B, grad rho += X.dB streamed from global
-//   zmat     (4 warps): thread = grid point; functional, weight scaling, EXC/N_EL tile partials,
-//                       Z = 1/2 vrho B + 2 vgamma (grad rho . dB) streamed to global
+//   density  (4 warps): lane = 4 consecutive grid points, warp = every 4th basis row:
+//                       rho += X.B, grad rho += X.dB with 256-bit streaming loads
+//   zmat     (4 warps): functional, weight scaling, EXC/N_EL tile partials (thread = point), then
+//                       Z = 1/2 vrho B + 2 vgamma (grad rho . dB) with 256-bit loads/stores, rows walked
+//                       in reverse so the most recently streamed rows are still in L2
 // so the HBM-bound streams of the density and Z stages run underneath the DMMA work of the next
 // chunk / next tile instead of in kernels of their own, and X never leaves the SM.
 #include "kernels.cuh"
@@ -28,23 +32,40 @@ namespace {
 
 constexpr int FK = 16;       // basis rows (K) per pipeline stage
 constexpr int FN = 64;       // columns of X per chunk
-constexpr int FSTAGES = 4;
+constexpr int FSTAGES = 5;
 constexpr int P_LD = FN + 4;   // (ld mod 16) == 4: conflict-free DMMA B-fragment loads
-constexpr int X_LD = TP + 2;   // conflict-free C-fragment stores
+constexpr int X_LD = TP + 2;   // conflict-free C-fragment stores, rows stay 16-byte aligned
 constexpr int MMA_WARPS = 8, DEN_WARPS = 4, Z_WARPS = 4;
 constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THREADS = Z_WARPS * 32;
-constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + 32;
+// warps 0-7 MMA, 8-11 density, 12-15 functional+Z, 16 producer, 17-19 idle (they only complete the
+// producer's warpgroup so that setmaxnreg can hand its registers to the MMA warps)
+constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + 128;
+// launch allocation 20 warps x 96; after re-partitioning 8 x 128 + 8 x 96 + 4 x 24 (must not exceed it)
+constexpr int MMA_REGS = 128, PROD_REGS = 24;
 
 struct FusedSmem {
   double A[FSTAGES][FK][TP];    // TMA destination, dense + global XOR swizzle
   double P[FSTAGES][FK][P_LD];
   double X[FN][X_LD];
+  double dpart[DEN_WARPS][4][TP];  // per density warp partial sums
   double den[4][TP];
+  double fac[2][4][TP];            // 1/2 w vrho, 2 w vsigma grad rho per point
   double red[2][2][Z_WARPS];
   uint64_t full[FSTAGES], empty[FSTAGES];
   uint64_t xfull, xempty, denfull, denempty;
 };
 constexpr size_t FUSED_SMEM_BYTES = sizeof(FusedSmem) + 1024;
+static_assert(FUSED_SMEM_BYTES <= 232448, "fused kernel shared memory");
+
+__device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
 
 template <bool GGA>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
@@ -76,48 +97,63 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 
   if (warp < MMA_WARPS) {
     // ------------------------------------------------------------------ MMA warps
+    reg_inc<MMA_REGS>();
     const int g = lane >> 2, t = lane & 3;
-    // warps sharing an SM sub-partition (warp & 3) take complementary row blocks so that
-    // ragged tiles (npts < 128) leave no sub-partition without DMMA work
-    const int wn = warp >> 2;
-    const int wm = wn ? 3 - (warp & 3) : (warp & 3);
+    const int wm = warp >> 2;  // row half (64 points)
+    const int wn = warp & 3;   // column strip (16 columns) == SM sub-partition
     int s = 0;
     uint32_t ph = 0, xph = 0;
-    int a_idx[4];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) a_idx[mi] = (wm * 32 + mi * 8 + g) ^ (t << 2);
+    // swizzled column of point (wm*64 + mi*8 + g) in a row with (row & 3) == t:
+    // a0 ^ (mi << 3), i.e. a0 + 8*mi for even mi and (a0 ^ 8) + 8*(mi - 1) for odd mi
+    const int a_ev = (wm * 64 + g) ^ (t << 2), a_od = a_ev ^ 8;
+#define A_IDX(mi) ((((mi) & 1) ? a_od : a_ev) + ((mi) & ~1) * 8)
 
     for (int q = q_begin; q < q_end; ++q) {
       const DevTile tile = tiles[order[q]];
       const int nbe = pv.tasks[tile.task].nbe;
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
-      const int mi_cnt = min(4, max(0, (tile.npts - wm * 32 + 7) / 8));
+      const int mi_cnt = min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
       for (int c = 0; c < nn; ++c) {
-        const int ni_cnt = min(4, max(0, (nbe - c * FN - wn * 32 + 7) / 8));
+        const int ni_cnt = min(2, max(0, (nbe - c * FN - wn * 16 + 7) / 8));
+        const bool full_tile = mi_cnt == 8 && ni_cnt == 2;
         const bool active = mi_cnt > 0 && ni_cnt > 0;
-        double acc[4][4][2];
+        double acc[8][2][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+          for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
 
         for (int ks = 0; ks < nk; ++ks) {
           mbar_wait(&S.full[s], ph);
-          if (active) {
-            const double* as = &S.A[s][t][0];
-            const double* ps = &S.P[s][t][wn * 32 + g];
+          const double* as = &S.A[s][t][0];
+          const double* ps = &S.P[s][t][wn * 16 + g];
+          if (full_tile) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              double a[4], b[4];
+              double a[8], b[2];
 #pragma unroll
-              for (int mi = 0; mi < 4; ++mi) a[mi] = as[kk * 4 * TP + a_idx[mi]];
+              for (int mi = 0; mi < 8; ++mi) a[mi] = as[kk * 4 * TP + A_IDX(mi)];
 #pragma unroll
-              for (int ni = 0; ni < 4; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
+              for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
 #pragma unroll
-              for (int mi = 0; mi < 4; ++mi)
+              for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
+                for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+          } else if (active) {
+            // ragged tile / last column strip: all fragment loads up front, warp-uniform predicates
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              double a[8], b[2];
+#pragma unroll
+              for (int mi = 0; mi < 8; ++mi) a[mi] = as[kk * 4 * TP + A_IDX(mi)];
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
+#pragma unroll
+              for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni)
                   if (mi < mi_cnt && ni < ni_cnt) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
           }
@@ -127,67 +163,109 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         // hand the chunk of X to the density warps
         mbar_wait(&S.xempty, xph ^ 1);
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
+          for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              S.X[wn * 32 + ni * 8 + 2 * t + j][wm * 32 + mi * 8 + g] = acc[mi][ni][j];
+              S.X[wn * 16 + ni * 8 + 2 * t + j][wm * 64 + mi * 8 + g] = acc[mi][ni][j];
         mbar_arrive(&S.xfull);
         xph ^= 1;
       }
     }
   } else if (warp < MMA_WARPS + DEN_WARPS) {
     // ------------------------------------------------------------------ density warps
-    const int p = tid - MMA_THREADS;
+    const int p = tid - MMA_THREADS;       // point owned in the cross-warp reduction
+    const int dw = warp - MMA_WARPS;       // rows with (row & 3) == dw
+    const int p4 = lane * 4;               // 4 consecutive points
+    const int cofs = p4 ^ (dw << 2);       // their (swizzled) column in every row of this warp
     uint32_t xph = 0, dph = 0;
     for (int q = q_begin; q < q_end; ++q) {
       const DevTile tile = tiles[order[q]];
       const int nbe = pv.tasks[tile.task].nbe;
       const size_t ms = (size_t)pad16(nbe) * TP;
-      const double* __restrict__ Bt = ws + tile.ws_off;
+      const double* __restrict__ Bt = ws + tile.ws_off + cofs;
       const int nn = (nbe + FN - 1) / FN;
-      double r0 = 0., r1 = 0., r2 = 0., r3 = 0.;
+      double r0[4] = {0., 0., 0., 0.}, r1[4] = {0., 0., 0., 0.}, r2[4] = {0., 0., 0., 0.},
+             r3[4] = {0., 0., 0., 0.};
       for (int c = 0; c < nn; ++c) {
         const int n0 = c * FN;
         const int ncols = min(FN, nbe - n0);
         mbar_wait(&S.xfull, xph);
-        int n = 0;
-        for (; n + 8 <= ncols; n += 8) {
-          double x[8], b0[8], b1[8], b2[8], b3[8];
+        int n = dw;
+        for (; n + 4 < ncols; n += 8) {
+          double x[2][4], b0[2][4], b1[2][4], b2[2][4], b3[2][4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const size_t o = (size_t)(n0 + n + u) * TP + (p ^ ((u & 3) << 2));
-            b0[u] = Bt[o];
-            if (GGA) { b1[u] = Bt[o + ms]; b2[u] = Bt[o + 2 * ms]; b3[u] = Bt[o + 3 * ms]; }
-            x[u] = S.X[n + u][p];
+          for (int u = 0; u < 2; ++u) {
+            const double* src = Bt + (size_t)(n0 + n + 4 * u) * TP;
+            ldg256_stream(b0[u], src);
+            if (GGA) {
+              ldg256_stream(b1[u], src + ms);
+              ldg256_stream(b2[u], src + 2 * ms);
+              ldg256_stream(b3[u], src + 3 * ms);
+            }
+            lds4(x[u], &S.X[n + 4 * u][p4]);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            r0 = fma(x[u], b0[u], r0);
-            if (GGA) { r1 = fma(x[u], b1[u], r1); r2 = fma(x[u], b2[u], r2); r3 = fma(x[u], b3[u], r3); }
-          }
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              r0[j] = fma(x[u][j], b0[u][j], r0[j]);
+              if (GGA) {
+                r1[j] = fma(x[u][j], b1[u][j], r1[j]);
+                r2[j] = fma(x[u][j], b2[u][j], r2[j]);
+                r3[j] = fma(x[u][j], b3[u][j], r3[j]);
+              }
+            }
         }
-        for (; n < ncols; ++n) {
-          const size_t o = (size_t)(n0 + n) * TP + (p ^ ((n & 3) << 2));
-          const double x = S.X[n][p];
-          r0 = fma(x, Bt[o], r0);
-          if (GGA) { r1 = fma(x, Bt[o + ms], r1); r2 = fma(x, Bt[o + 2 * ms], r2); r3 = fma(x, Bt[o + 3 * ms], r3); }
+        if (n < ncols) {
+          double x[4], b0[4], b1[4], b2[4], b3[4];
+          const double* src = Bt + (size_t)(n0 + n) * TP;
+          ldg256_stream(b0, src);
+          if (GGA) {
+            ldg256_stream(b1, src + ms);
+            ldg256_stream(b2, src + 2 * ms);
+            ldg256_stream(b3, src + 3 * ms);
+          }
+          lds4(x, &S.X[n][p4]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            r0[j] = fma(x[j], b0[j], r0[j]);
+            if (GGA) {
+              r1[j] = fma(x[j], b1[j], r1[j]);
+              r2[j] = fma(x[j], b2[j], r2[j]);
+              r3[j] = fma(x[j], b3[j], r3[j]);
+            }
+          }
         }
         mbar_arrive(&S.xempty);
         xph ^= 1;
       }
+      // cross-warp reduction in fixed order
+      sts4(&S.dpart[dw][0][p4], r0);
+      if (GGA) {
+        sts4(&S.dpart[dw][1][p4], r1);
+        sts4(&S.dpart[dw][2][p4], r2);
+        sts4(&S.dpart[dw][3][p4], r3);
+      }
+      named_bar_sync(2, DEN_THREADS);
       mbar_wait(&S.denempty, dph ^ 1);
       // X carries the RKS factor 2 (eval_xmat fac = 2), the gradient another 2
-      S.den[0][p] = 2. * r0;
-      if (GGA) { S.den[1][p] = 4. * r1; S.den[2][p] = 4. * r2; S.den[3][p] = 4. * r3; }
+#pragma unroll
+      for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
+        const double v = (S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p]);
+        S.den[qn][p] = (qn == 0 ? 2. : 4.) * v;
+      }
       mbar_arrive(&S.denfull);
       dph ^= 1;
+      named_bar_sync(2, DEN_THREADS);  // dpart may be overwritten by the next tile
     }
   } else if (warp < MMA_WARPS + DEN_WARPS + Z_WARPS) {
     // ------------------------------------------------------------------ functional + Z warps
     const int p = tid - MMA_THREADS - DEN_THREADS;
     const int zw = p >> 5;
+    const int p4 = lane * 4;
+    const int cofs = p4 ^ (zw << 2);
     uint32_t dph = 0;
     int it = 0;
     for (int q = q_begin; q < q_end; ++q, ++it) {
@@ -196,8 +274,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int nbe = pv.tasks[tile.task].nbe;
       const int nbp = pad16(nbe);
       const size_t ms = (size_t)nbp * TP;
-      const double* __restrict__ Bt = ws + tile.ws_off;
-      double* __restrict__ Z = ws + tile.ws_off + (GGA ? 4 : 1) * ms;
+      const double* __restrict__ Bt = ws + tile.ws_off + cofs;
+      double* __restrict__ Z = ws + tile.ws_off + (GGA ? 4 : 1) * ms + cofs;
 
       mbar_wait(&S.denfull, dph);
       const double rho = S.den[0][p];
@@ -222,6 +300,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         e_loc = eps * rho;                  // :490-497
         n_loc = w * rho;
       }
+      double(*fac)[TP] = S.fac[it & 1];
+      fac[0][p] = a;
+      if (GGA) { fac[1][p] = fx; fac[2][p] = fy; fac[3][p] = fz; }
       // fixed-order tile partials of EXC / N_EL
       {
         double e = e_loc, nn = n_loc;
@@ -238,32 +319,65 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
           nel_part[part_off + tile_idx] = (red[4] + red[5]) + (red[6] + red[7]);
         }
       }
-      // Z rows (pad rows are never read as valid output rows)
-      int mu = 0;
-      for (; mu + 4 <= nbe; mu += 4) {
-        double b0[4], b1[4], b2[4], b3[4];
+      // Z rows (pad rows are never read as valid output rows); warp zw owns rows = zw (mod 4),
+      // last rows first: they were streamed most recently by the density warps
+      double a4[4], fx4[4], fy4[4], fz4[4];
+      lds4(a4, &fac[0][p4]);
+      if (GGA) { lds4(fx4, &fac[1][p4]); lds4(fy4, &fac[2][p4]); lds4(fz4, &fac[3][p4]); }
+      int mu = ((nbe - 1 - zw) & ~3) + zw;  // largest row <= nbe-1 with (row & 3) == zw
+      if (mu >= nbe) mu -= 4;
+      for (; mu - 4 >= 0; mu -= 8) {
+        double b0[2][4], b1[2][4], b2[2][4], b3[2][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const size_t o = (size_t)(mu + u) * TP + (p ^ (u << 2));
-          b0[u] = Bt[o];
-          if (GGA) { b1[u] = Bt[o + ms]; b2[u] = Bt[o + 2 * ms]; b3[u] = Bt[o + 3 * ms]; }
+        for (int u = 0; u < 2; ++u) {
+          const double* src = Bt + (size_t)(mu - 4 * u) * TP;
+          ldg256_stream(b0[u], src);
+          if (GGA) {
+            ldg256_stream(b1[u], src + ms);
+            ldg256_stream(b2[u], src + 2 * ms);
+            ldg256_stream(b3[u], src + 3 * ms);
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          double z = a * b0[u];
-          if (GGA) { z = fma(fx, b1[u], z); z = fma(fy, b2[u], z); z = fma(fz, b3[u], z); }
-          Z[(size_t)(mu + u) * TP + (p ^ (u << 2))] = z;
+        for (int u = 0; u < 2; ++u) {
+          double z[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            z[j] = a4[j] * b0[u][j];
+            if (GGA) {
+              z[j] = fma(fx4[j], b1[u][j], z[j]);
+              z[j] = fma(fy4[j], b2[u][j], z[j]);
+              z[j] = fma(fz4[j], b3[u][j], z[j]);
+            }
+          }
+          stg256(Z + (size_t)(mu - 4 * u) * TP, z);
         }
       }
-      for (; mu < nbe; ++mu) {
-        const size_t o = (size_t)mu * TP + (p ^ ((mu & 3) << 2));
-        double z = a * Bt[o];
-        if (GGA) { z = fma(fx, Bt[o + ms], z); z = fma(fy, Bt[o + 2 * ms], z); z = fma(fz, Bt[o + 3 * ms], z); }
-        Z[o] = z;
+      if (mu >= 0) {
+        double b0[4], b1[4], b2[4], b3[4], z[4];
+        const double* src = Bt + (size_t)mu * TP;
+        ldg256_stream(b0, src);
+        if (GGA) {
+          ldg256_stream(b1, src + ms);
+          ldg256_stream(b2, src + 2 * ms);
+          ldg256_stream(b3, src + 3 * ms);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          z[j] = a4[j] * b0[j];
+          if (GGA) {
+            z[j] = fma(fx4[j], b1[j], z[j]);
+            z[j] = fma(fy4[j], b2[j], z[j]);
+            z[j] = fma(fz4[j], b3[j], z[j]);
+          }
+        }
+        stg256(Z + (size_t)mu * TP, z);
       }
     }
   } else {
     // ------------------------------------------------------------------ producer warp
+    reg_dec<PROD_REGS>();
+    if (warp != MMA_WARPS + DEN_WARPS + Z_WARPS) return;
     int s = 0;
     uint32_t ph = 0;
     if (lane == 0) tma_prefetch_desc(&tmapA);
@@ -276,9 +390,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int* __restrict__ ao = pv.task_ao + task.ao_off;
       const int rowB = (int)(tile.ws_off / TP);
       for (int c = 0; c < nn; ++c) {
-        const int na = c * FN + 2 * lane;
-        const bool va = na < nbe, vb = na + 1 < nbe;
-        const int ca = va ? __ldg(ao + na) : 0, cb = vb ? __ldg(ao + na + 1) : 0;
+        // lane -> columns (lane, lane + 32): each warp-wide LDGSTS covers 32 consecutive local AOs
+        const int na = c * FN + lane, nb = na + 32;
+        const bool va = na < nbe, vb = nb < nbe;
+        const int ca = va ? __ldg(ao + na) : 0, cb = vb ? __ldg(ao + nb) : 0;
         for (int ks = 0; ks < nk; ++ks) {
           const int k0 = ks * FK;
           const int kmine = k0 + (lane & 15);
@@ -293,8 +408,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
             const long long rb = __shfl_sync(0xffffffffu, rb_mine, r);
             const bool vr = rb >= 0;
             const double* src = P + (vr ? rb : 0);
-            cp_async8_zfill(&S.P[s][r][2 * lane], src + ca, vr && va);
-            cp_async8_zfill(&S.P[s][r][2 * lane + 1], src + cb, vr && vb);
+            cp_async8_zfill(&S.P[s][r][lane], src + ca, vr && va);
+            cp_async8_zfill(&S.P[s][r][lane + 32], src + cb, vr && vb);
           }
           cp_async_mbar_arrive_noinc(&S.full[s]);
           if (++s == FSTAGES) { s = 0; ph ^= 1; }

@@ -48,7 +48,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 // all prior cp.async of this thread arrive on the barrier when they complete
@@ -79,12 +79,37 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }
 
+
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256) ---------------------------------
+// streamed once per stage of the pipeline: bypass L1 allocation
+__device__ __forceinline__ void ldg256_stream(double (&v)[4], const double* p) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]),
+               "d"(v[3])
+               : "memory");
+}
+
 // ---- DMMA -----------------------------------------------------------------------------
 // D(8x8) += A(8x4,row) * B(4x8,col); lane = 4*g + t holds A[g][t], B[t][g], C[g][2t..2t+1]
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+
+
+// ---- register re-partitioning between warp roles (all warps of a warpgroup must execute it) ---
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
