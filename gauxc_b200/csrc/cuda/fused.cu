@@ -8,7 +8,9 @@
 // (reference_local_host_work_driver.cxx eval_xmat :123-146, eval_uvvar_{lda,gga}_rks :150-163,
 // 242-268, eval_zmat_{lda,gga}_vxc_rks :586-604, 678-713; host driver :446-502).
 //
-// One CTA per SM walks a host-balanced list of tiles.  Five roles, 17 warps:
+// One persistent CTA per SM pulls tiles from a device-side queue (atomic counter, task order: the
+// tiles in flight share P_sub / VXC regions in L2; no static partition to go out of balance) and
+// broadcasts them to its roles through a 4-slot shared-memory ring.  Five roles, 17 warps:
 //   producer (1 warp) : TMA box loads of B^T (16 basis rows x 128 points) + LDGSTS gather of the
 //                       matching 16 x 64 block of P through the task's AO map, 5-stage mbarrier ring
 //   MMA      (8 warps): 128 x 64 chunk of X on the DMMA pipe (m8n8k4); warp tile 64 x 16 with the two
@@ -33,6 +35,7 @@ namespace {
 constexpr int FK = 16;       // basis rows (K) per pipeline stage
 constexpr int FN = 64;       // columns of X per chunk
 constexpr int FSTAGES = 5;
+constexpr int TQ = 4;         // tile-queue ring slots
 constexpr int P_LD = FN + 4;   // (ld mod 16) == 4: conflict-free DMMA B-fragment loads
 constexpr int X_LD = TP + 2;   // conflict-free C-fragment stores, rows stay 16-byte aligned
 constexpr int MMA_WARPS = 8, DEN_WARPS = 4, Z_WARPS = 4;
@@ -40,8 +43,8 @@ constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THRE
 // warps 0-7 MMA, 8-11 density, 12-15 functional+Z, 16 producer, 17-19 idle (they only complete the
 // producer's warpgroup so that setmaxnreg can hand its registers to the MMA warps)
 constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + 128;
-// launch allocation 20 warps x 96; after re-partitioning 8 x 128 + 8 x 96 + 4 x 24 (must not exceed it)
-constexpr int MMA_REGS = 128, PROD_REGS = 24;
+// launch allocation 20 warps x 96; after re-partitioning 8 x 120 + 8 x 96 + 4 x 40 (must not exceed it)
+constexpr int MMA_REGS = 120, PROD_REGS = 40;
 
 struct FusedSmem {
   double A[FSTAGES][FK][TP];    // TMA destination, dense + global XOR swizzle
@@ -53,6 +56,8 @@ struct FusedSmem {
   double red[2][2][Z_WARPS];
   uint64_t full[FSTAGES], empty[FSTAGES];
   uint64_t xfull, xempty, denfull, denempty;
+  uint64_t tqfull[TQ], tqempty[TQ];
+  int tq[TQ];  // tile index inside the batch, -1 = queue drained
 };
 constexpr size_t FUSED_SMEM_BYTES = sizeof(FusedSmem) + 1024;
 static_assert(FUSED_SMEM_BYTES <= 232448, "fused kernel shared memory");
@@ -70,8 +75,8 @@ __device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
 template <bool GGA>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView pv,
-                           const DevTile* __restrict__ tiles, const int* __restrict__ order,
-                           const int* __restrict__ cta_begin, double* __restrict__ ws,
+                           const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
+                           double* __restrict__ ws,
                            const double* __restrict__ P, int ldp, FunctionalDesc func,
                            double* __restrict__ exc_part, double* __restrict__ nel_part,
                            int part_off) {
@@ -80,7 +85,14 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q_begin = cta_begin[blockIdx.x], q_end = cta_begin[blockIdx.x + 1];
+  // consumer side of the tile queue: iteration `it` reads slot it % TQ
+  auto next_tile = [&](int it) {
+    const int slot = it & (TQ - 1);
+    mbar_wait(&S.tqfull[slot], (it / TQ) & 1);
+    const int idx = S.tq[slot];
+    mbar_arrive(&S.tqempty[slot]);
+    return idx;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < FSTAGES; ++s) {
@@ -91,6 +103,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     mbar_init(&S.xempty, DEN_THREADS);
     mbar_init(&S.denfull, DEN_THREADS);
     mbar_init(&S.denempty, Z_THREADS);
+    for (int i = 0; i < TQ; ++i) {
+      mbar_init(&S.tqfull[i], 1);
+      mbar_init(&S.tqempty[i], MMA_THREADS + DEN_THREADS + Z_THREADS);
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -108,8 +124,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     const int a_ev = (wm * 64 + g) ^ (t << 2), a_od = a_ev ^ 8;
 #define A_IDX(mi) ((((mi) & 1) ? a_od : a_ev) + ((mi) & ~1) * 8)
 
-    for (int q = q_begin; q < q_end; ++q) {
-      const DevTile tile = tiles[order[q]];
+    for (int it = 0;; ++it) {
+      const int tile_idx = next_tile(it);
+      if (tile_idx < 0) break;
+      const DevTile tile = tiles[tile_idx];
       const int nbe = pv.tasks[tile.task].nbe;
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
@@ -180,8 +198,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     const int p4 = lane * 4;               // 4 consecutive points
     const int cofs = p4 ^ (dw << 2);       // their (swizzled) column in every row of this warp
     uint32_t xph = 0, dph = 0;
-    for (int q = q_begin; q < q_end; ++q) {
-      const DevTile tile = tiles[order[q]];
+    for (int it = 0;; ++it) {
+      const int tile_idx = next_tile(it);
+      if (tile_idx < 0) break;
+      const DevTile tile = tiles[tile_idx];
       const int nbe = pv.tasks[tile.task].nbe;
       const size_t ms = (size_t)pad16(nbe) * TP;
       const double* __restrict__ Bt = ws + tile.ws_off + cofs;
@@ -267,9 +287,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     const int p4 = lane * 4;
     const int cofs = p4 ^ (zw << 2);
     uint32_t dph = 0;
-    int it = 0;
-    for (int q = q_begin; q < q_end; ++q, ++it) {
-      const int tile_idx = order[q];
+    for (int it = 0;; ++it) {
+      const int tile_idx = next_tile(it);
+      if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
       const int nbe = pv.tasks[tile.task].nbe;
       const int nbp = pad16(nbe);
@@ -381,8 +401,19 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     int s = 0;
     uint32_t ph = 0;
     if (lane == 0) tma_prefetch_desc(&tmapA);
-    for (int q = q_begin; q < q_end; ++q) {
-      const DevTile tile = tiles[order[q]];
+    for (int it = 0;; ++it) {
+      const int slot = it & (TQ - 1);
+      mbar_wait(&S.tqempty[slot], ((it / TQ) & 1) ^ 1);
+      int tile_idx = -1;
+      if (lane == 0) {
+        tile_idx = atomicAdd(counter, 1);
+        if (tile_idx >= ntiles) tile_idx = -1;
+        S.tq[slot] = tile_idx;
+        mbar_arrive(&S.tqfull[slot]);
+      }
+      tile_idx = __shfl_sync(0xffffffffu, tile_idx, 0);
+      if (tile_idx < 0) break;
+      const DevTile tile = tiles[tile_idx];
       const DevTask task = pv.tasks[tile.task];
       const int nbe = task.nbe;
       const int nk = pad16(nbe) / FK;
@@ -423,11 +454,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 
 int fused_threads() { return FUSED_THREADS; }
 
-void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, const int* order,
-                  const int* cta_begin, int ncta, double* ws, const double* P, int ldp,
+void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
+                  int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
                   cudaStream_t s) {
-  if (ncta <= 0) return;
+  if (ncta <= 0 || ntiles <= 0) return;
+  ncta = ncta < ntiles ? ncta : ntiles;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -438,10 +470,10 @@ void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* t
   }
   if (func.is_gga)
     fused_xmat_den_zmat_kernel<true><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
-        tmapA, pv, tiles, order, cta_begin, ws, P, ldp, func, exc_part, nel_part, part_off);
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off);
   else
     fused_xmat_den_zmat_kernel<false><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
-        tmapA, pv, tiles, order, cta_begin, ws, P, ldp, func, exc_part, nel_part, part_off);
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off);
 }
 
 }  // namespace gxb

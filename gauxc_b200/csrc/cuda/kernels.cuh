@@ -12,9 +12,9 @@ void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, do
 
 // K_F  fused persistent kernel: X = B P_sub (DMMA) -> rho / grad rho -> functional, weights,
 //      EXC / N_EL tile partials -> Z.  tmapA: box of 16 rows x 128 points over the workspace;
-//      order / cta_begin: host-balanced tile lists per CTA.
-void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, const int* order,
-                  const int* cta_begin, int ncta, double* ws, const double* P, int ldp,
+//      The ncta persistent CTAs pull tile indices [0, ntiles) from *counter (zeroed by the caller).
+void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
+                  int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
                   cudaStream_t s);
 

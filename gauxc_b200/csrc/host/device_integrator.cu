@@ -78,13 +78,13 @@ struct Schedule {
   };
   std::vector<Batch> batches;
   std::vector<gxb::VxcItem> items;
-  // fused kernel: per batch a permutation of the batch's tiles grouped per CTA (longest
-  // processing time first over `ncta` persistent CTAs) and the ncta+1 group offsets
-  std::vector<int> order, cta_begin;
+  // fused kernel: persistent CTAs pull tiles of the batch from a device-side queue (one counter
+  // per batch) in task order, so the tiles in flight at any time belong to the same / neighbouring
+  // parent atoms and their P_sub gathers and VXC scatters stay L2-resident
   int ncta = 0;
   DevBuf<gxb::DevTile> d_tiles;
   DevBuf<gxb::VxcItem> d_items;
-  DevBuf<int> d_order, d_cta_begin;
+  DevBuf<int> d_counters;
   size_t ws_doubles = 0;
   int max_batch_tiles = 0;
 };
@@ -134,10 +134,14 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
 
   if (basis.max_l() > 4) GAUXC_GENERIC_EXCEPTION("L > 4 Not Supported on Device");
 
-  // same ordering as the reference device driver (…exc_vxc.hpp:254-257, weights :41-44)
-  std::stable_sort(tasks.begin(), tasks.end(), [](const XCTask& a, const XCTask& b) {
-    return (a.points.size() * a.bfn_screening.nbe) > (b.points.size() * b.bfn_screening.nbe);
-  });
+  // Task order = the load balancer's (iParent, shell_list) order.  The reference device driver
+  // re-sorts by npts*nbe (…exc_vxc.hpp:254-257) to size its per-call batches; here the order is kept
+  // parent-major for L2 locality and the load is balanced by the device-side tile queue instead.
+  if (const char* e = std::getenv("GAUXC_B200_TASK_ORDER"))
+    if (std::string(e) == "cost")
+      std::stable_sort(tasks.begin(), tasks.end(), [](const XCTask& a, const XCTask& b) {
+        return (a.points.size() * a.bfn_screening.nbe) > (b.points.size() * b.bfn_screening.nbe);
+      });
 
   plan->nbf = bmap.nbf;
   plan->natoms = (int)mol.size();
@@ -243,7 +247,6 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   auto sc = std::make_shared<Schedule>();
   sc->tiles = plan.tiles;
   sc->ncta = ncta;
-  sc->order.resize(sc->tiles.size());
   size_t cur = 0, ws_max = 0;
   Schedule::Batch b{0, 0, 0, 0};
   auto close_batch = [&](int tile_end) {
@@ -271,33 +274,6 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
       q = e;
     }
     b.item_end = (int)sc->items.size();
-    // fused kernel tile lists: LPT over ncta persistent CTAs, cost ~ DMMA time + streamed bytes
-    {
-      const int nt = b.tile_end - b.tile_begin;
-      std::vector<int> idx(nt);
-      std::iota(idx.begin(), idx.end(), 0);
-      auto cost = [&](int i) {
-        const double n = plan.tasks[sc->tiles[b.tile_begin + i].task].nbe;
-        return n * (n + 256.);
-      };
-      std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return cost(x) > cost(y); });
-      std::vector<std::vector<int>> lists(ncta);
-      using QE = std::pair<double, int>;
-      std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
-      for (int c = 0; c < ncta; ++c) pq.push({0., c});
-      for (int i : idx) {
-        auto [load, c] = pq.top();
-        pq.pop();
-        lists[c].push_back(i);
-        pq.push({load + cost(i), c});
-      }
-      int o = 0;
-      for (int c = 0; c < ncta; ++c) {
-        sc->cta_begin.push_back(o);
-        for (int i : lists[c]) sc->order[b.tile_begin + o++] = i;
-      }
-      sc->cta_begin.push_back(o);
-    }
     sc->batches.push_back(b);
     sc->max_batch_tiles = std::max(sc->max_batch_tiles, b.tile_end - b.tile_begin);
     ws_max = std::max(ws_max, cur);
@@ -317,8 +293,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
-  sc->d_order.upload(sc->order);
-  sc->d_cta_begin.upload(sc->cta_begin);
+  sc->d_counters.alloc(std::max<size_t>(1, sc->batches.size()));
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
 }
@@ -583,7 +558,7 @@ static size_t workspace_bytes(const LoadBalancer& lb) {
   double frac = 0.9;
   if (auto* d = dynamic_cast<const DeviceRuntimeEnvironment*>(&lb.runtime()))
     if (d->fill_fraction() > 0.) frac = d->fill_fraction();
-  size_t cap = (size_t)4 << 30;  // default: 4 GiB of B/Z workspace per batch
+  size_t cap = (size_t)16 << 30;  // default: 16 GiB of B/Z workspace per batch
   if (const char* e = std::getenv("GAUXC_DEVICE_MEMORY_CAP")) cap = (size_t)std::atoll(e);
   return std::min<size_t>(cap, (size_t)(frac * free_b * 0.8));
 }
@@ -638,6 +613,7 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   const int nbf = plan.nbf;
 
   if (do_vxc) CUDA_CHECK(cudaMemsetAsync(dVXC, 0, sizeof(double) * (size_t)nbf * nbf, s));
+  CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
   CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
   double kms[4] = {0, 0, 0, 0};
   long long launches = 0;
@@ -657,8 +633,7 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     if (ev) CUDA_CHECK(cudaEventRecord(ev[0], s));
     gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[1], s));
-    gxb::launch_fused(I.tmapA, pv, tl, sc.d_order.p + b.tile_begin,
-                      sc.d_cta_begin.p + ib * (size_t)(sc.ncta + 1), sc.ncta, I.d_ws.p, dP, nbf,
+    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, dP, nbf,
                       func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[2], s));
     if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
