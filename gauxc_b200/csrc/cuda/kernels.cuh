@@ -20,8 +20,9 @@ void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* t
 
 // K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe, scatter-added (lower triangle) into VXC.
 //      tmapV: box of 128 rows x 16 points over the workspace.
+//      ncta persistent CTAs pull items [0, nitems) from *counter (zeroed by the caller).
 void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
-                int nitems, bool gga, double* VXC, int ldv, cudaStream_t s);
+                int nitems, int* counter, int ncta, bool gga, double* VXC, int ldv, cudaStream_t s);
 
 // finalisation
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

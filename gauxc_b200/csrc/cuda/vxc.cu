@@ -11,6 +11,10 @@
 // run of that task's tiles (K = points).  Both operands arrive as TMA boxes of 128 basis rows x
 // 16 points straight from the swizzled workspace (dense + conflict-free, device_plan.hpp) through
 // a 5-stage mbarrier ring fed by one producer thread; 16 MMA warps (4 x 4, warp tile 32 x 32).
+// The kernel is PERSISTENT: one CTA per SM pulls items from a device-side queue (atomic counter,
+// task order -> the VXC region being scattered into stays in L2) and the producer runs ahead into
+// the next item's loads while the MMA warps scatter the current one, so the many small items of
+// large sparse systems (tasks of ~50 points) do not pay a launch + pipeline fill each.
 // M + M^T is folded into the LOWER triangle of VXC with FP64 reductions (RED.ADD.F64).  For LDA
 // Z = diag(1/2 w vrho) B makes M symmetric: only blocks mblk >= nblk are scheduled (`sym`).
 #include "kernels.cuh"
@@ -22,46 +26,77 @@ namespace {
 
 constexpr int VK = 16;  // points (K) per stage
 constexpr int VSTAGES = 5;
+constexpr int VQ = 4;   // item-queue ring slots
 constexpr int V_MMA_WARPS = 16;
 constexpr int V_MMA_THREADS = V_MMA_WARPS * 32;
-constexpr int V_THREADS = V_MMA_THREADS + 32;
+// warps 0-15 MMA, 16 producer, 17-19 idle (complete the producer's warpgroup for setmaxnreg)
+constexpr int V_THREADS = V_MMA_THREADS + 128;
+// launch allocation 20 warps x 96; after re-partitioning 16 x 112 + 4 x 32
+constexpr int V_MMA_REGS = 112, V_PROD_REGS = 32;
+
+struct VxcSlot {
+  int nbe, ao_off, m0, n0, nks, diag, pad0, pad1;  // nks < 0: queue drained
+};
 
 struct VxcSmem {
   double A[VSTAGES][VXC_BLK][VK];
   double Z[VSTAGES][VXC_BLK][VK];
   uint64_t full[VSTAGES], empty[VSTAGES];
+  uint64_t qfull[VQ], qempty[VQ];
+  VxcSlot q[VQ];
 };
 constexpr size_t VXC_SMEM_BYTES = sizeof(VxcSmem) + 1024;
 
 __global__ void __launch_bounds__(V_THREADS, 1)
 vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile* __restrict__ tiles,
-           const VxcItem* __restrict__ items, int zmat, int sym, double* __restrict__ VXC, int ldv) {
+           const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int sym,
+           double* __restrict__ VXC, int ldv) {
   extern __shared__ uint8_t smem_raw[];
   VxcSmem& S = *reinterpret_cast<VxcSmem*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const VxcItem item = items[blockIdx.x];
-  const DevTask task = pv.tasks[item.task];
-  const int nbe = task.nbe;
-  const int nbp = pad16(nbe);
-  const int m0 = item.mblk * VXC_BLK, n0 = item.nblk * VXC_BLK;
 
   if (tid == 0) {
     for (int s = 0; s < VSTAGES; ++s) {
       mbar_init(&S.full[s], 1);
       mbar_init(&S.empty[s], V_MMA_THREADS);
     }
+    for (int i = 0; i < VQ; ++i) {
+      mbar_init(&S.qfull[i], 1);
+      mbar_init(&S.qempty[i], V_MMA_THREADS);
+    }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == V_MMA_WARPS) {
+  if (warp >= V_MMA_WARPS) {
     // ---------------------------------------------------------------- producer (one thread)
-    if (lane == 0) {
-      tma_prefetch_desc(&tmapV);
-      int s = 0;
-      uint32_t ph = 0;
+    reg_dec<V_PROD_REGS>();
+    if (warp != V_MMA_WARPS || lane != 0) return;
+    tma_prefetch_desc(&tmapV);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0;; ++it) {
+      const int slot = it & (VQ - 1);
+      mbar_wait(&S.qempty[slot], ((it / VQ) & 1) ^ 1);
+      const int idx = atomicAdd(counter, 1);
+      if (idx >= nitems) {
+        S.q[slot].nks = -1;
+        mbar_arrive(&S.qfull[slot]);
+        break;
+      }
+      const VxcItem item = items[idx];
+      const DevTask task = pv.tasks[item.task];
+      const int nbp = pad16(task.nbe);
+      const int m0 = item.mblk * VXC_BLK, n0 = item.nblk * VXC_BLK;
+      int nks_total = 0;
+      for (int q = item.tile_begin; q < item.tile_end; ++q) nks_total += (tiles[q].npts + VK - 1) / VK;
+      VxcSlot sl;
+      sl.nbe = task.nbe; sl.ao_off = task.ao_off; sl.m0 = m0; sl.n0 = n0; sl.nks = nks_total;
+      sl.diag = (sym && item.mblk == item.nblk) ? 1 : 0; sl.pad0 = sl.pad1 = 0;
+      S.q[slot] = sl;
+      mbar_arrive(&S.qfull[slot]);
       for (int q = item.tile_begin; q < item.tile_end; ++q) {
         const DevTile tl = tiles[q];
         const int rowB = (int)(tl.ws_off / TP);
@@ -80,41 +115,54 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
   }
 
   // ------------------------------------------------------------------ MMA warps
+  reg_inc<V_MMA_REGS>();
   const int g = lane >> 2, t = lane & 3;
   // sub-partition = warp & 3 = (wm + wn) & 3: idle row / column blocks of ragged output blocks are
   // spread over all four DMMA pipes
   const int wm = warp >> 2;
   const int wn = ((warp & 3) - wm) & 3;
-  const int mi_cnt = min(4, max(0, (nbe - m0 - wm * 32 + 7) / 8));
-  const int ni_cnt = min(4, max(0, (nbe - n0 - wn * 32 + 7) / 8));
-  const bool diag = sym && item.mblk == item.nblk;
-  const bool active = mi_cnt > 0 && ni_cnt > 0 && !(diag && wn > wm);
+  const int sw = (g & 3) << 2;
+  int s = 0;
+  uint32_t ph = 0;
 
-  double acc[4][4][2];
-#pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+  for (int it = 0;; ++it) {
+    const int slot = it & (VQ - 1);
+    mbar_wait(&S.qfull[slot], (it / VQ) & 1);
+    const VxcSlot sl = S.q[slot];
+    mbar_arrive(&S.qempty[slot]);
+    if (sl.nks < 0) break;
+    const int nbe = sl.nbe, m0 = sl.m0, n0 = sl.n0;
+    const int mi_cnt = min(4, max(0, (nbe - m0 - wm * 32 + 7) / 8));
+    const int ni_cnt = min(4, max(0, (nbe - n0 - wn * 32 + 7) / 8));
+    const bool diag = sl.diag != 0;
+    const bool active = mi_cnt > 0 && ni_cnt > 0 && !(diag && wn > wm);
+    const bool full_blk = active && mi_cnt == 4 && ni_cnt == 4;
 
-  {
-    int s = 0;
-    uint32_t ph = 0;
-    const int sw = (g & 3) << 2;
-    for (int q = item.tile_begin; q < item.tile_end; ++q) {
-      const int nks = (tiles[q].npts + VK - 1) / VK;
-      for (int ks = 0; ks < nks; ++ks) {
-        mbar_wait(&S.full[s], ph);
-        if (active) {
-          const double* as = &S.A[s][wm * 32 + g][0];
-          const double* zs = &S.Z[s][wn * 32 + g][0];
+    double acc[4][4][2];
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int col = (kk * 4 + t) ^ sw;
-            double a[4], b[4];
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * VK + col];
+      for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+
+    for (int ks = 0; ks < sl.nks; ++ks) {
+      mbar_wait(&S.full[s], ph);
+      if (active) {
+        const double* as = &S.A[s][wm * 32 + g][0];
+        const double* zs = &S.Z[s][wn * 32 + g][0];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = zs[ni * 8 * VK + col];
+        for (int kk = 0; kk < 4; ++kk) {
+          const int col = (kk * 4 + t) ^ sw;
+          double a[4], b[4];
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * VK + col];
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) b[ni] = zs[ni * 8 * VK + col];
+          if (full_blk) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          } else {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -122,39 +170,39 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
                 if (mi < mi_cnt && ni < ni_cnt) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
           }
         }
-        mbar_arrive(&S.empty[s]);
-        if (++s == VSTAGES) { s = 0; ph ^= 1; }
       }
+      mbar_arrive(&S.empty[s]);
+      if (++s == VSTAGES) { s = 0; ph ^= 1; }
     }
-  }
-  if (!active) return;
+    if (!active) continue;
 
-  // scatter: VXC_sub = M + M^T, only the lower triangle of the full matrix is accumulated
-  const int* __restrict__ ao = pv.task_ao + task.ao_off;
+    // scatter: VXC_sub = M + M^T, only the lower triangle of the full matrix is accumulated
+    const int* __restrict__ ao = pv.task_ao + sl.ao_off;
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      if (mi >= mi_cnt || ni >= ni_cnt) continue;
-      const int mu = m0 + wm * 32 + mi * 8 + g;
-      if (mu >= nbe) continue;
-      const int gm = __ldg(ao + mu);
+      for (int ni = 0; ni < 4; ++ni) {
+        if (mi >= mi_cnt || ni >= ni_cnt) continue;
+        const int mu = m0 + wm * 32 + mi * 8 + g;
+        if (mu >= nbe) continue;
+        const int gm = __ldg(ao + mu);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int nu = n0 + wn * 32 + ni * 8 + 2 * t + j;
-        if (nu >= nbe) continue;
-        double v = acc[mi][ni][j];
-        if (sym) {
-          if (diag && nu > mu) continue;  // M symmetric: the mirror entry carries it
-          v *= 2.;
-        } else if (mu == nu) {
-          v *= 2.;
+        for (int j = 0; j < 2; ++j) {
+          const int nu = n0 + wn * 32 + ni * 8 + 2 * t + j;
+          if (nu >= nbe) continue;
+          double v = acc[mi][ni][j];
+          if (sym) {
+            if (diag && nu > mu) continue;  // M symmetric: the mirror entry carries it
+            v *= 2.;
+          } else if (mu == nu) {
+            v *= 2.;
+          }
+          const int gn = __ldg(ao + nu);
+          const int hi = max(gm, gn), lo = min(gm, gn);
+          atomicAdd(VXC + (size_t)lo * ldv + hi, v);
         }
-        const int gn = __ldg(ao + nu);
-        const int hi = max(gm, gn), lo = min(gm, gn);
-        atomicAdd(VXC + (size_t)lo * ldv + hi, v);
       }
-    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -208,15 +256,16 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int n, int ld) {
 }  // namespace
 
 void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
-                int nitems, bool gga, double* VXC, int ldv, cudaStream_t s) {
-  if (nitems <= 0) return;
+                int nitems, int* counter, int ncta, bool gga, double* VXC, int ldv, cudaStream_t s) {
+  if (nitems <= 0 || ncta <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(vxc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VXC_SMEM_BYTES);
     attr_set = true;
   }
-  vxc_kernel<<<nitems, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapV, pv, tiles, items, gga ? 4 : 1, gga ? 0 : 1,
-                                                       VXC, ldv);
+  ncta = ncta < nitems ? ncta : nitems;
+  vxc_kernel<<<ncta, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapV, pv, tiles, items, nitems, counter,
+                                                      gga ? 4 : 1, gga ? 0 : 1, VXC, ldv);
 }
 
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

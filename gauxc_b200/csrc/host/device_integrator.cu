@@ -293,7 +293,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
-  sc->d_counters.alloc(std::max<size_t>(1, sc->batches.size()));
+  sc->d_counters.alloc(std::max<size_t>(1, 2 * sc->batches.size()));  // fused + vxc queue heads
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
 }
@@ -639,8 +639,8 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
     launches += 2;
     if (do_vxc) {
-      gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin, gga,
-                      dVXC, nbf, s);
+      gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                      sc.d_counters.p + sc.batches.size() + ib, sc.ncta, gga, dVXC, nbf, s);
       ++launches;
     }
     if (ev) CUDA_CHECK(cudaEventRecord(ev[4], s));
