@@ -10,9 +10,10 @@
 //
 // One persistent CTA per SM pulls tiles from a device-side queue (atomic counter, task order: the
 // tiles in flight share P_sub / VXC regions in L2; no static partition to go out of balance) and
-// broadcasts them to its roles through a 4-slot shared-memory ring.  Five roles, 17 warps:
-//   producer (1 warp) : TMA box loads of B^T (16 basis rows x 128 points) + LDGSTS gather of the
-//                       matching 16 x 64 block of P through the task's AO map, 5-stage mbarrier ring
+// broadcasts them to its roles through a 4-slot shared-memory ring.  Five roles, 20 warps:
+//   producer (4 warps): TMA box loads of B^T (16 basis rows x 128 points) + LDGSTS gather of the
+//                       matching 16 x 64 block of P through the task's AO map (4 rows per warp),
+//                       5-stage mbarrier ring
 //   MMA      (8 warps): 128 x 64 chunk of X on the DMMA pipe (m8n8k4); warp tile 64 x 16 with the two
 //                       row halves of a column strip on the SAME SM sub-partition, so ragged tiles
 //                       (npts < 128) load the four DMMA pipes evenly.  Each finished chunk is handed
@@ -38,11 +39,12 @@ constexpr int FSTAGES = 5;
 constexpr int TQ = 4;         // tile-queue ring slots
 constexpr int P_LD = FN + 4;   // (ld mod 16) == 4: conflict-free DMMA B-fragment loads
 constexpr int X_LD = TP + 2;   // conflict-free C-fragment stores, rows stay 16-byte aligned
-constexpr int MMA_WARPS = 8, DEN_WARPS = 4, Z_WARPS = 4;
+constexpr int MMA_WARPS = 8, DEN_WARPS = 4, Z_WARPS = 4, PROD_WARPS = 4;
 constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THREADS = Z_WARPS * 32;
-// warps 0-7 MMA, 8-11 density, 12-15 functional+Z, 16 producer, 17-19 idle (they only complete the
-// producer's warpgroup so that setmaxnreg can hand its registers to the MMA warps)
-constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + 128;
+// warps 0-7 MMA, 8-11 density, 12-15 functional+Z, 16-19 producers (one warpgroup per role family so
+// that setmaxnreg can move registers from the producers to the MMA warps)
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS;
 // launch allocation 20 warps x 96; after re-partitioning 8 x 120 + 8 x 96 + 4 x 40 (must not exceed it)
 constexpr int MMA_REGS = 120, PROD_REGS = 40;
 
@@ -96,7 +98,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 
   if (tid == 0) {
     for (int s = 0; s < FSTAGES; ++s) {
-      mbar_init(&S.full[s], 32);            // 32 producer lanes (cp.async arrivals) + TMA bytes
+      mbar_init(&S.full[s], PROD_THREADS);  // producer lanes (cp.async arrivals) + TMA bytes
       mbar_init(&S.empty[s], MMA_THREADS);
     }
     mbar_init(&S.xfull, MMA_THREADS);
@@ -105,7 +107,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     mbar_init(&S.denempty, Z_THREADS);
     for (int i = 0; i < TQ; ++i) {
       mbar_init(&S.tqfull[i], 1);
-      mbar_init(&S.tqempty[i], MMA_THREADS + DEN_THREADS + Z_THREADS);
+      mbar_init(&S.tqempty[i], MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS - 32);
     }
     mbar_fence_init();
   }
@@ -395,23 +397,30 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       }
     }
   } else {
-    // ------------------------------------------------------------------ producer warp
+    // ------------------------------------------------------------------ producer warps
+    // warp pw gathers rows 4pw..4pw+3 of every 16-row stage of P; warp 0 also owns the tile queue
+    // and the TMA loads of B^T
     reg_dec<PROD_REGS>();
-    if (warp != MMA_WARPS + DEN_WARPS + Z_WARPS) return;
+    const int pw = warp - (MMA_WARPS + DEN_WARPS + Z_WARPS);
     int s = 0;
     uint32_t ph = 0;
-    if (lane == 0) tma_prefetch_desc(&tmapA);
+    if (pw == 0 && lane == 0) tma_prefetch_desc(&tmapA);
     for (int it = 0;; ++it) {
-      const int slot = it & (TQ - 1);
-      mbar_wait(&S.tqempty[slot], ((it / TQ) & 1) ^ 1);
-      int tile_idx = -1;
-      if (lane == 0) {
-        tile_idx = atomicAdd(counter, 1);
-        if (tile_idx >= ntiles) tile_idx = -1;
-        S.tq[slot] = tile_idx;
-        mbar_arrive(&S.tqfull[slot]);
+      int tile_idx;
+      if (pw == 0) {
+        const int slot = it & (TQ - 1);
+        mbar_wait(&S.tqempty[slot], ((it / TQ) & 1) ^ 1);
+        tile_idx = -1;
+        if (lane == 0) {
+          tile_idx = atomicAdd(counter, 1);
+          if (tile_idx >= ntiles) tile_idx = -1;
+          S.tq[slot] = tile_idx;
+          mbar_arrive(&S.tqfull[slot]);
+        }
+        tile_idx = __shfl_sync(0xffffffffu, tile_idx, 0);
+      } else {
+        tile_idx = next_tile(it);
       }
-      tile_idx = __shfl_sync(0xffffffffu, tile_idx, 0);
       if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
       const DevTask task = pv.tasks[tile.task];
@@ -427,20 +436,20 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         const int ca = va ? __ldg(ao + na) : 0, cb = vb ? __ldg(ao + nb) : 0;
         for (int ks = 0; ks < nk; ++ks) {
           const int k0 = ks * FK;
-          const int kmine = k0 + (lane & 15);
+          const int kmine = k0 + pw * 4 + (lane & 3);
           const long long rb_mine = kmine < nbe ? (long long)__ldg(ao + kmine) * ldp : -1;
           mbar_wait(&S.empty[s], ph ^ 1);
-          if (lane == 0) {
+          if (pw == 0 && lane == 0) {
             mbar_expect_tx(&S.full[s], FK * TP * sizeof(double));
             tma_load_2d(&S.A[s][0][0], &tmapA, &S.full[s], 0, rowB + k0);
           }
 #pragma unroll
-          for (int r = 0; r < FK; ++r) {
+          for (int r = 0; r < 4; ++r) {
             const long long rb = __shfl_sync(0xffffffffu, rb_mine, r);
             const bool vr = rb >= 0;
             const double* src = P + (vr ? rb : 0);
-            cp_async8_zfill(&S.P[s][r][lane], src + ca, vr && va);
-            cp_async8_zfill(&S.P[s][r][lane + 32], src + cb, vr && vb);
+            cp_async8_zfill(&S.P[s][pw * 4 + r][lane], src + ca, vr && va);
+            cp_async8_zfill(&S.P[s][pw * 4 + r][lane + 32], src + cb, vr && vb);
           }
           cp_async_mbar_arrive_noinc(&S.full[s]);
           if (++s == FSTAGES) { s = 0; ph ^= 1; }
