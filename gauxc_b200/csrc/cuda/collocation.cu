@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(TP) collocation_kernel(PlanView pv,
   const DevTile tile = tiles[blockIdx.x];
   const DevTask task = pv.tasks[tile.task];
   const int i = threadIdx.x;
+  if (i >= tile_width(tile.npts)) return;  // columns beyond the tile width are never read
   const bool ok = i < tile.npts;
   const int ip = tile.pt_off + (ok ? i : 0);
   const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];

@@ -27,6 +27,8 @@ namespace gxb {
 constexpr int TP = 128;  // points per tile
 
 GXB_HOST_DEVICE inline int pad16(int nbe) { return (nbe + 15) & ~15; }
+// columns of a tile that are ever written / read: npts rounded up to 32
+GXB_HOST_DEVICE inline int tile_width(int npts) { return (npts + 31) & ~31; }
 GXB_HOST_DEVICE inline int swz(int row, int i) { return i ^ ((row & 3) << 2); }
 
 struct DevShell {

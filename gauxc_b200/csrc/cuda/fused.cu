@@ -45,8 +45,8 @@ constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THRE
 // that setmaxnreg can move registers from the producers to the MMA warps)
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS;
-// launch allocation 20 warps x 96; after re-partitioning 8 x 120 + 8 x 96 + 4 x 40 (must not exceed it)
-constexpr int MMA_REGS = 120, PROD_REGS = 40;
+// launch allocation 20 warps x 96; after re-partitioning 8 x 120 + 8 x 96 + 4 x 48 (must not exceed it)
+constexpr int MMA_REGS = 120, PROD_REGS = 48;
 
 struct FusedSmem {
   double A[FSTAGES][FK][TP];    // TMA destination, dense + global XOR swizzle
@@ -210,9 +210,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int nn = (nbe + FN - 1) / FN;
       double r0[4] = {0., 0., 0., 0.}, r1[4] = {0., 0., 0., 0.}, r2[4] = {0., 0., 0., 0.},
              r3[4] = {0., 0., 0., 0.};
+      const bool lane_on = p4 < tile_width(tile.npts);  // columns beyond the tile width do not exist
       for (int c = 0; c < nn; ++c) {
         const int n0 = c * FN;
-        const int ncols = min(FN, nbe - n0);
+        const int ncols = lane_on ? min(FN, nbe - n0) : 0;
         mbar_wait(&S.xfull, xph);
         int n = dw;
         for (; n + 4 < ncols; n += 8) {
@@ -347,7 +348,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       lds4(a4, &fac[0][p4]);
       if (GGA) { lds4(fx4, &fac[1][p4]); lds4(fy4, &fac[2][p4]); lds4(fz4, &fac[3][p4]); }
       int mu = ((nbe - 1 - zw) & ~3) + zw;  // largest row <= nbe-1 with (row & 3) == zw
-      if (mu >= nbe) mu -= 4;
+      if (p4 >= tile_width(tile.npts)) mu = -1;  // columns beyond the tile width do not exist
       for (; mu - 4 >= 0; mu -= 8) {
         double b0[2][4], b1[2][4], b2[2][4], b3[2][4];
 #pragma unroll
@@ -434,10 +435,17 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         const int na = c * FN + lane, nb = na + 32;
         const bool va = na < nbe, vb = nb < nbe;
         const int ca = va ? __ldg(ao + na) : 0, cb = vb ? __ldg(ao + nb) : 0;
+        // row bases of the NEXT stage are fetched while this stage is issued (the AO map lookup is a
+        // dependent global load)
+        const int kl = pw * 4 + (lane & 3);
+        int ao_next = kl < nbe ? __ldg(ao + kl) : -1;
         for (int ks = 0; ks < nk; ++ks) {
           const int k0 = ks * FK;
-          const int kmine = k0 + pw * 4 + (lane & 3);
-          const long long rb_mine = kmine < nbe ? (long long)__ldg(ao + kmine) * ldp : -1;
+          const long long rb_mine = ao_next >= 0 ? (long long)ao_next * ldp : -1;
+          {
+            const int kn = k0 + FK + kl;
+            ao_next = (ks + 1 < nk && kn < nbe) ? __ldg(ao + kn) : -1;
+          }
           mbar_wait(&S.empty[s], ph ^ 1);
           if (pw == 0 && lane == 0) {
             mbar_expect_tx(&S.full[s], FK * TP * sizeof(double));
