@@ -430,6 +430,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int nn = (nbe + FN - 1) / FN;
       const int* __restrict__ ao = pv.task_ao + task.ao_off;
       const int rowB = (int)(tile.ws_off / TP);
+      const int W = tile_width(tile.npts);
       for (int c = 0; c < nn; ++c) {
         // lane -> columns (lane, lane + 32): each warp-wide LDGSTS covers 32 consecutive local AOs
         const int na = c * FN + lane, nb = na + 32;
@@ -447,9 +448,14 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
             ao_next = (ks + 1 < nk && kn < nbe) ? __ldg(ao + kn) : -1;
           }
           mbar_wait(&S.empty[s], ph ^ 1);
-          if (pw == 0 && lane == 0) {
-            mbar_expect_tx(&S.full[s], FK * TP * sizeof(double));
-            tma_load_2d(&S.A[s][0][0], &tmapA, &S.full[s], 0, rowB + k0);
+          if (pw == 0) {
+            // B^T rows: one bulk copy per row of only the W columns the tile owns (shared-memory
+            // pitch stays 128 points, so the MMA addressing is independent of W)
+            if (lane == 0) mbar_expect_tx(&S.full[s], FK * W * sizeof(double));
+            __syncwarp();
+            if (lane < FK)
+              bulk_load_1d(&S.A[s][lane][0], ws + (size_t)(rowB + k0 + lane) * TP, W * sizeof(double),
+                           &S.full[s]);
           }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {

@@ -30,9 +30,10 @@ void launch_reduce_partials(const double* exc_part, const double* nel_part, int 
 void launch_symmetrize(double* VXC, int nbf, int ldv, cudaStream_t s);
 
 // SSF weights (in place on pv.w)
+//   nbr_idx / nbr_dist [natoms][natoms]: per atom, all atoms sorted by distance from it (itself first)
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab, const double* dist_nearest, int natoms,
-                        cudaStream_t s);
+                        const double* rab, const double* dist_nearest, const int* nbr_idx,
+                        const double* nbr_dist, int natoms, cudaStream_t s);
 
 // FP64 peak probes (DMMA m8n8k4 and DFMA), return achieved TFLOP/s
 double probe_dmma_tflops(int iters);

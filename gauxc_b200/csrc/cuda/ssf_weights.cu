@@ -8,11 +8,22 @@
 //     (B < C: g(mu_CB);  B > C: 1 - g(mu_BC)),  mu = (r_i - r_j) / RAB (a true division)
 //   * w *= P_parent / sum_C P_C, sum in ascending C
 // Instead of materialising natoms distances per point (the reference device path stores a
-// natoms x npts scratch, xc_device_data.hpp:449-451) distances are recomputed, and a
-// candidate C is dropped at once when the atom nearest to the point already forces
-// P_C = 0 exactly (mu >= 0.64 against the nearest atom), which is what the host's pair
-// loop produces for that C.  The host additionally skips pairs whose two partials are both
-// <= 1e-13; that only perturbs terms below 1e-13 of the sum.
+// natoms x npts scratch, xc_device_data.hpp:449-451) distances are recomputed, and every loop over
+// atoms is cut off EXACTLY with the triangle inequality around an anchor atom A = the atom nearest
+// to the tile's first point (found by a block-wide scan; tiles are spatially compact, so r_A is
+// small for every point of the tile), whose neighbours arrive sorted by R_AB (nbr_idx / nbr_dist,
+// built once on the host).  With kappa = (1 + 0.64) / (1 - 0.64) and r_X the distance of the point
+// to atom X (r_X >= R_AX - r_A):
+//   * the nearest atom lies within R_AC <= 2 r_A;
+//   * r_C >= kappa r_min  =>  mu(C, nearest) >= 0.64  =>  P_C = 0 exactly: no candidate C beyond
+//     R_AC - r_A >= kappa r_min;
+//   * r_B >= kappa r_C  =>  mu(C, B) <= -0.64  =>  the factor s(mu_CB) is exactly 1: the product over
+//     B stops at R_AB - r_A >= kappa r_C (and earlier as soon as it reaches 0).
+// That is what the host's full pair loop produces for those terms, so the result is unchanged while
+// the cost per point drops from O(natoms^2) to O(near atoms^2) -- 1231-atom ubiquitin and the
+// 2499-atom water cluster need this.  Products / sums run in neighbour order instead of index
+// order (a reordering of exact factors 0 and 1 plus O(1e-16) rounding).  The host additionally
+// skips pairs whose two partials are both <= 1e-13; that only perturbs terms below 1e-13 of the sum.
 #include "kernels.cuh"
 
 namespace gxb {
@@ -31,9 +42,40 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
                                                   const double* __restrict__ atoms,
                                                   const double* __restrict__ rab,
                                                   const double* __restrict__ dist_nearest,
+                                                  const int* __restrict__ nbr_idx,
+                                                  const double* __restrict__ nbr_dist,
                                                   int natoms) {
   const DevTile tile = tiles[blockIdx.x];
   const int i = threadIdx.x;
+
+  // anchor atom of the tile: nearest atom to the tile's first point
+  __shared__ double s_best[TP / 32];
+  __shared__ int s_arg[TP / 32];
+  int anchor;
+  {
+    const double ax = pv.px[tile.pt_off], ay = pv.py[tile.pt_off], az = pv.pz[tile.pt_off];
+    double best = 1e300;
+    int arg = 0;
+    for (int A = i; A < natoms; A += TP) {
+      const double dx = ax - atoms[3 * A], dy = ay - atoms[3 * A + 1], dz = az - atoms[3 * A + 2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < best) { best = d2; arg = A; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+      if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if ((i & 31) == 0) { s_best[i >> 5] = best; s_arg[i >> 5] = arg; }
+    __syncthreads();
+    best = s_best[0]; arg = s_arg[0];
+#pragma unroll
+    for (int w = 1; w < TP / 32; ++w)
+      if (s_best[w] < best || (s_best[w] == best && s_arg[w] < arg)) { best = s_best[w]; arg = s_arg[w]; }
+    anchor = arg;
+  }
+
   if (i >= tile.npts) return;
   const int ip = tile.pt_off + i;
   const int par = pv.tasks[tile.task].iParent;
@@ -47,16 +89,26 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   const double r_par = dist(par);
   if (r_par < 0.5 * (1. - magic_ssf) * dist_nearest[par]) return;
 
-  // nearest atom
-  double rmin = r_par;
-  int imin = par;
-  for (int A = 0; A < natoms; ++A) {
+  const int* __restrict__ nb = nbr_idx + (size_t)anchor * natoms;     // nb[0] == anchor
+  const double* __restrict__ nd = nbr_dist + (size_t)anchor * natoms;  // ascending R(anchor, .)
+  const double r_anc = dist(anchor);
+  constexpr double kappa = (1. + magic_ssf) / (1. - magic_ssf) * (1. + 1e-9);  // + rounding margin
+
+  // nearest atom: r_C >= R(anchor, C) - r_anc > r_anc once R(anchor, C) > 2 r_anc
+  double rmin = r_anc;
+  int imin = anchor;
+  for (int k = 1; k < natoms; ++k) {
+    if (nd[k] > 2. * r_anc * (1. + 1e-9)) break;
+    const int A = nb[k];
     const double r = dist(A);
     if (r < rmin) { rmin = r; imin = A; }
   }
 
   double sum = 0., p_par = 0.;
-  for (int C = 0; C < natoms; ++C) {
+  const double c_cut = kappa * rmin;
+  for (int kc = 0; kc < natoms; ++kc) {
+    if (nd[kc] - r_anc >= c_cut) break;  // every remaining C has P_C == 0
+    const int C = nb[kc];
     const double rC = dist(C);
     if (C != imin) {
       const double R = rab[(size_t)C * natoms + imin];
@@ -66,7 +118,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
     }
     double Pc = 1.;
     const double* __restrict__ rabC = rab + (size_t)C * natoms;
-    for (int Bq = 0; Bq < natoms; ++Bq) {
+    const double b_cut = kappa * rC;
+    for (int kb = 0; kb < natoms; ++kb) {
+      if (nd[kb] - r_anc >= b_cut) break;  // every remaining factor is exactly 1
+      const int Bq = nb[kb];
       if (Bq == C) continue;
       const double rB = dist(Bq);
       const double R = rabC[Bq];
@@ -92,10 +147,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
 }  // namespace
 
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab, const double* dist_nearest, int natoms,
-                        cudaStream_t s) {
+                        const double* rab, const double* dist_nearest, const int* nbr_idx,
+                        const double* nbr_dist, int natoms, cudaStream_t s) {
   if (ntiles <= 0) return;
-  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab, dist_nearest, natoms);
+  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab, dist_nearest, nbr_idx, nbr_dist, natoms);
 }
 
 }  // namespace gxb

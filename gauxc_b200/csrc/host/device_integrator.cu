@@ -101,7 +101,8 @@ struct DevicePlan {
   DevBuf<gxb::DevTile> d_tiles;
   DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
   DevBuf<double> d_px, d_py, d_pz, d_w;
-  DevBuf<double> d_atoms, d_rab, d_dist_nearest;
+  DevBuf<double> d_atoms, d_rab, d_dist_nearest, d_nbr_dist;
+  DevBuf<int> d_nbr_idx;  // per atom: all atoms sorted by distance from it (SSF loop cut-offs)
   double f_dense = 0., sum_nbe_npts = 0.;
   std::map<int, std::shared_ptr<Schedule>> schedules;  // key: nmat
   size_t schedule_ws_bytes = 0;
@@ -276,6 +277,24 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
   plan->d_atoms.upload(atoms);
   plan->d_rab.upload(meta.rab);
   plan->d_dist_nearest.upload(meta.dist_nearest);
+  {
+    const size_t na = mol.size();
+    std::vector<int> nbr_idx(na * na);
+    std::vector<double> nbr_dist(na * na);
+#pragma omp parallel for schedule(static)
+    for (size_t a = 0; a < na; ++a) {
+      int* idx = nbr_idx.data() + a * na;
+      const double* r = meta.rab.data() + a * na;
+      std::iota(idx, idx + na, 0);
+      std::sort(idx, idx + na, [&](int x, int y) {
+        if (x == (int)a || y == (int)a) return x == (int)a && y != (int)a;  // the atom itself first
+        return r[x] < r[y] || (r[x] == r[y] && x < y);
+      });
+      for (size_t k = 0; k < na; ++k) nbr_dist[a * na + k] = (idx[k] == (int)a) ? 0. : r[idx[k]];
+    }
+    plan->d_nbr_idx.upload(nbr_idx);
+    plan->d_nbr_dist.upload(nbr_dist);
+  }
   CUDA_CHECK(cudaDeviceSynchronize());
   return plan;
 }
@@ -515,7 +534,8 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, 0));
   gxb::launch_ssf_weights(plan->view(), plan->d_tiles.p, (int)plan->tiles.size(), plan->d_atoms.p,
-                          plan->d_rab.p, plan->d_dist_nearest.p, plan->natoms, 0);
+                          plan->d_rab.p, plan->d_dist_nearest.p, plan->d_nbr_idx.p, plan->d_nbr_dist.p,
+                          plan->natoms, 0);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(e1, 0));
   // copy_weights_to_tasks: the host XCTask list stays the source of truth for other consumers
