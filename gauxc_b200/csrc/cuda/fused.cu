@@ -45,8 +45,9 @@ constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THRE
 // that setmaxnreg can move registers from the producers to the MMA warps)
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS;
-// launch allocation 20 warps x 96; after re-partitioning 8 x 120 + 8 x 96 + 4 x 48 (must not exceed it)
-constexpr int MMA_REGS = 120, PROD_REGS = 48;
+// launch allocation 20 warps x 96; after re-partitioning 8 x 112 (MMA) + 4 x 112 (density) + 4 x 96 (Z)
+// + 4 x 48 (producers) (must not exceed it)
+constexpr int MMA_REGS = 112, DEN_REGS = 112, PROD_REGS = 48;
 
 struct FusedSmem {
   double A[FSTAGES][FK][TP];    // TMA destination, dense + global XOR swizzle
@@ -82,9 +83,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
                            const double* __restrict__ P, int ldp, FunctionalDesc func,
                            double* __restrict__ exc_part, double* __restrict__ nel_part,
                            int part_off) {
-  extern __shared__ uint8_t smem_raw[];
-  FusedSmem& S = *reinterpret_cast<FusedSmem*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no pointer arithmetic on the base: the compiler must see shared-space accesses (LDS/STS, not
+  // generic LD/ST) in the fragment loads
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 127u)) __trap();  // TMA destinations need 128 B
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // consumer side of the tile queue: iteration `it` reads slot it % TQ
@@ -136,6 +139,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int mi_cnt = min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
       for (int c = 0; c < nn; ++c) {
         const int ni_cnt = min(2, max(0, (nbe - c * FN - wn * 16 + 7) / 8));
+        // LDA: only rho = sum_n B_n X_n is needed, a quadratic form in B, so the K loop of column
+        // chunk c stops at the diagonal block (P' = lower triangle of P with a halved diagonal)
+        const int nkc = GGA ? nk : min(nk, (FN / FK) * (c + 1));
         const bool full_tile = mi_cnt == 8 && ni_cnt == 2;
         const bool active = mi_cnt > 0 && ni_cnt > 0;
         double acc[8][2][2];
@@ -144,7 +150,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 #pragma unroll
           for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
 
-        for (int ks = 0; ks < nk; ++ks) {
+        for (int ks = 0; ks < nkc; ++ks) {
           mbar_wait(&S.full[s], ph);
           const double* as = &S.A[s][t][0];
           const double* ps = &S.P[s][t][wn * 16 + g];
@@ -195,6 +201,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     }
   } else if (warp < MMA_WARPS + DEN_WARPS) {
     // ------------------------------------------------------------------ density warps
+    reg_inc<DEN_REGS>();
     const int p = tid - MMA_THREADS;       // point owned in the cross-warp reduction
     const int dw = warp - MMA_WARPS;       // rows with (row & 3) == dw
     const int p4 = lane * 4;               // 4 consecutive points
@@ -273,11 +280,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       }
       named_bar_sync(2, DEN_THREADS);
       mbar_wait(&S.denempty, dph ^ 1);
-      // X carries the RKS factor 2 (eval_xmat fac = 2), the gradient another 2
+      // X carries the RKS factor 2 (eval_xmat fac = 2), the gradient another 2; the LDA path sums
+      // the lower triangle of the quadratic form only (another 2)
 #pragma unroll
       for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
         const double v = (S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p]);
-        S.den[qn][p] = (qn == 0 ? 2. : 4.) * v;
+        S.den[qn][p] = ((qn == 0 && GGA) ? 2. : 4.) * v;
       }
       mbar_arrive(&S.denfull);
       dph ^= 1;
@@ -440,12 +448,13 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         // dependent global load)
         const int kl = pw * 4 + (lane & 3);
         int ao_next = kl < nbe ? __ldg(ao + kl) : -1;
-        for (int ks = 0; ks < nk; ++ks) {
+        const int nkc = GGA ? nk : min(nk, (FN / FK) * (c + 1));
+        for (int ks = 0; ks < nkc; ++ks) {
           const int k0 = ks * FK;
           const long long rb_mine = ao_next >= 0 ? (long long)ao_next * ldp : -1;
           {
             const int kn = k0 + FK + kl;
-            ao_next = (ks + 1 < nk && kn < nbe) ? __ldg(ao + kn) : -1;
+            ao_next = (ks + 1 < nkc && kn < nbe) ? __ldg(ao + kn) : -1;
           }
           mbar_wait(&S.empty[s], ph ^ 1);
           if (pw == 0) {
@@ -462,8 +471,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
             const long long rb = __shfl_sync(0xffffffffu, rb_mine, r);
             const bool vr = rb >= 0;
             const double* src = P + (vr ? rb : 0);
-            cp_async8_zfill(&S.P[s][pw * 4 + r][lane], src + ca, vr && va);
-            cp_async8_zfill(&S.P[s][pw * 4 + r][lane + 32], src + cb, vr && vb);
+            const int k = k0 + pw * 4 + r;  // LDA: rows k <= n only (see the MMA warps)
+            cp_async8_zfill(&S.P[s][pw * 4 + r][lane], src + ca, vr && va && (GGA || k <= na));
+            cp_async8_zfill(&S.P[s][pw * 4 + r][lane + 32], src + cb, vr && vb && (GGA || k <= nb));
           }
           cp_async_mbar_arrive_noinc(&S.full[s]);
           if (++s == FSTAGES) { s = 0; ph ^= 1; }

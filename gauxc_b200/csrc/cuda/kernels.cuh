@@ -28,6 +28,8 @@ void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* til
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,
                             cudaStream_t s);
 void launch_symmetrize(double* VXC, int nbf, int ldv, cudaStream_t s);
+// LDA density operand P' (lower triangle of (P + P^T)/2, diagonal halved), ld = nbf
+void launch_sym_half(const double* P, int ldp, double* out, int nbf, cudaStream_t s);
 
 // SSF weights (in place on pv.w)
 //   nbr_idx / nbr_dist [natoms][natoms]: per atom, all atoms sorted by distance from it (itself first)

@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(V_THREADS, 1)
 vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile* __restrict__ tiles,
            const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int sym,
            double* __restrict__ VXC, int ldv) {
-  extern __shared__ uint8_t smem_raw[];
-  VxcSmem& S = *reinterpret_cast<VxcSmem*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no pointer arithmetic on the base: the compiler must see shared-space accesses (LDS/STS, not
+  // generic LD/ST) in the fragment loads
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  VxcSmem& S = *reinterpret_cast<VxcSmem*>(smem_raw);
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 127u)) __trap();  // TMA destinations need 128 B
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -253,7 +255,31 @@ __global__ void symmetrize_kernel(double* __restrict__ A, int n, int ld) {
   if (ti < n && tj < n && tj > ti) A[(size_t)tj * ld + ti] = tile[threadIdx.x][threadIdx.y];
 }
 
+// LDA density operand: P' = lower triangle of (P + P^T)/2 with the diagonal halved, so that
+// rho = B.(P B) = 2 B.(P' B) is summed over k <= n only (fused.cu, LDA K loop).  Exact for a
+// symmetric P ((a + a)/2 == a); for a non-symmetric P it is the same quadratic form as the host's.
+__global__ void sym_half_kernel(const double* __restrict__ P, int ldp, double* __restrict__ out, int n) {
+  __shared__ double tile[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;
+  if (bj > bi) return;
+  {
+    const int r = bj * 32 + threadIdx.x, c = bi * 32 + threadIdx.y;  // mirror block, element (r, c)
+    tile[threadIdx.y][threadIdx.x] = (r < n && c < n) ? P[(size_t)c * ldp + r] : 0.;
+  }
+  __syncthreads();
+  const int i = bi * 32 + threadIdx.x, j = bj * 32 + threadIdx.y;
+  if (i < n && j < n && i >= j) {
+    const double a = P[(size_t)j * ldp + i], b = tile[threadIdx.x][threadIdx.y];  // P(i,j), P(j,i)
+    out[(size_t)j * n + i] = (i == j) ? 0.5 * a : 0.5 * (a + b);
+  }
+}
+
 }  // namespace
+
+void launch_sym_half(const double* P, int ldp, double* out, int nbf, cudaStream_t s) {
+  const int nb = (nbf + 31) / 32;
+  if (nb > 0) sym_half_kernel<<<dim3(nb, nb), dim3(32, 32), 0, s>>>(P, ldp, out, nbf);
+}
 
 void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
                 int nitems, int* counter, int ncta, bool gga, double* VXC, int ldv, cudaStream_t s) {

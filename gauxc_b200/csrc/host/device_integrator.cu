@@ -564,7 +564,7 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
 // ------------------------------------------------------------------------------------
 struct XCIntegrator::Impl {
   cudaStream_t stream = nullptr;
-  DevBuf<double> dP, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
+  DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
   CUtensorMap tmapA{}, tmapV{};  // TMA views of d_ws: 16 rows x 128 points / 128 rows x 16 points
   int ncta = 0;
   std::shared_ptr<DevicePlan> plan;
@@ -682,8 +682,19 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   if (do_vxc) CUDA_CHECK(cudaMemsetAsync(dVXC, 0, sizeof(double) * (size_t)nbf * nbf, s));
   CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
   CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
-  double kms[4] = {0, 0, 0, 0};
   long long launches = 0;
+  if (!gga) {
+    // LDA needs rho only: the fused kernel walks the lower triangle of the quadratic form (half the
+    // DMMA work of X = P_sub B) over P' prepared here, inside the timed region
+    if (I.dPtri.n != (size_t)nbf * nbf) {
+      I.dPtri.alloc((size_t)nbf * nbf);
+      CUDA_CHECK(cudaMemsetAsync(I.dPtri.p, 0, sizeof(double) * (size_t)nbf * nbf, s));
+    }
+    gxb::launch_sym_half(dP, nbf, I.dPtri.p, nbf, s);
+    dP = I.dPtri.p;
+    ++launches;
+  }
+  double kms[4] = {0, 0, 0, 0};
   // profile mode brackets every kernel with events on the launching stream; they are read
   // after the final synchronise, so the pipeline is not stalled by the measurement
   if (I.profile)
