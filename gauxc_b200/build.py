@@ -37,12 +37,12 @@ def _deps_mtime():
     return m
 
 
-def _compile(src, hdr_m, verbose):
-    obj = os.path.join(BUILD, src.replace("/", "_") + ".o")
+def _compile(src, hdr_m, verbose, defs=(), bdir=None):
+    obj = os.path.join(bdir or BUILD, src.replace("/", "_") + ".o")
     srcp = os.path.join(CSRC, src)
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), hdr_m):
         return obj, ""
-    cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-c", srcp, "-o", obj]
+    cmd = [NVCC] + ARCH + COMMON + ["-D" + d for d in defs] + ["-x", "cu", "-c", srcp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -72,6 +72,23 @@ def build_library(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
+
+
+def build_variant(suffix, defs):
+    """Diagnostic build of the library with extra -D macros (timing experiments, e.g. GXB_KNOCKOUT);
+    written next to the product library as libgauxc_b200_<suffix>.so and loaded only when
+    GAUXC_B200_LIB points at it."""
+    bdir = os.path.join(BUILD, suffix)
+    os.makedirs(bdir, exist_ok=True)
+    hdr_m = _deps_mtime()
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = [o for o, _ in ex.map(lambda s: _compile(s, hdr_m, False, defs, bdir), SOURCES)]
+    out = os.path.join(HERE, "libgauxc_b200_%s.so" % suffix)
+    cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
 
 
 def build_oracle(force=False):

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgauxc_b200.so")
+# GAUXC_B200_LIB: load a diagnostic build of the same library (gauxc_b200.build.build_variant)
+_LIB_PATH = os.environ.get("GAUXC_B200_LIB") or os.path.join(_HERE, "libgauxc_b200.so")
 
 
 class GauXCError(RuntimeError):

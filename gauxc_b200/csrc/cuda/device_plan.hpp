@@ -49,14 +49,19 @@ struct DevTile {
   int task;
   int pt_off;  // global point offset of the tile's first point
   int npts;    // <= TP
-  int pad;
+  int nbe;     // copy of the task's nbe / ao_off: the kernels need no dependent DevTask load
   int64_t ws_off;  // offset (in doubles) of the tile's matrices inside the batch workspace
+  int ao_off;
+  int pad;
 };
 
-// one unit of the VXC rank update: output block (mblk,nblk) of task `task`, accumulated
-// over tiles [tile_begin, tile_end) of the current batch
+// one unit of the VXC rank update: output block (mblk,nblk) of one task, accumulated over a run of
+// `ntiles` consecutive tiles of that task in the current batch.  Self-contained (32 bytes, one
+// load): the tiles of a task lie back to back in the workspace (row stride nmat * pad16(nbe)),
+// all full (TP points = TP/16 K steps) except possibly the last one (nks_last K steps).
 struct VxcItem {
-  int task, mblk, nblk, tile_begin, tile_end, pad0, pad1, pad2;
+  int nbe, ao_off, mblk, nblk;
+  int row0, ntiles, nks_last, pad;  // row0: workspace row (ws_off / TP) of the first tile
 };
 constexpr int VXC_BLK = 128;  // output block edge of the VXC rank update
 

@@ -29,6 +29,12 @@
 #include "ptx.cuh"
 #include "xc_functionals.cuh"
 
+// GXB_KNOCKOUT (diagnostic builds only, results are garbage): bit 0 removes the density / Z global
+// streams, bit 1 the P gather, bit 2 the B^T bulk loads -- to time what each costs the DMMA pipe.
+#ifndef GXB_KNOCKOUT
+#define GXB_KNOCKOUT 0
+#endif
+
 namespace gxb {
 
 namespace {
@@ -65,6 +71,14 @@ struct FusedSmem {
 constexpr size_t FUSED_SMEM_BYTES = sizeof(FusedSmem) + 1024;
 static_assert(FUSED_SMEM_BYTES <= 232448, "fused kernel shared memory");
 
+__device__ __forceinline__ void ldg_stream(double (&v)[4], const double* p) {
+  if (GXB_KNOCKOUT & 1) { v[0] = v[1] = v[2] = v[3] = 1.; return; }
+  ldg256_stream(v, p);
+}
+__device__ __forceinline__ void stg_stream(double* p, const double (&v)[4]) {
+  if (GXB_KNOCKOUT & 1) { if (v[0] == 1.2345e-300) stg256(p, v); return; }
+  stg256(p, v);
+}
 __device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
   const double2 b = *reinterpret_cast<const double2*>(p + 2);
@@ -73,6 +87,27 @@ __device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
 __device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
   *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+// One pipeline stage (16 K rows) of a warp's 64 x 16 tile restricted to its first MI row blocks.
+// Straight-line, UNPREDICATED DMMAs: a predicated mma.sync costs a WARPSYNC per instruction, so
+// ragged tiles dispatch (warp-uniformly, once per stage) to the variant with MI rounded up to even;
+// rows / columns beyond the tile multiply stale-but-finite or zero-filled operands and are never read.
+template <int MI>
+__device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* __restrict__ as,
+                                          const double* __restrict__ ps, int a_ev, int a_od) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    double a[MI], b[2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * TP + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
 }
 
 template <bool GGA>
@@ -127,13 +162,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     // swizzled column of point (wm*64 + mi*8 + g) in a row with (row & 3) == t:
     // a0 ^ (mi << 3), i.e. a0 + 8*mi for even mi and (a0 ^ 8) + 8*(mi - 1) for odd mi
     const int a_ev = (wm * 64 + g) ^ (t << 2), a_od = a_ev ^ 8;
-#define A_IDX(mi) ((((mi) & 1) ? a_od : a_ev) + ((mi) & ~1) * 8)
 
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
-      const int nbe = pv.tasks[tile.task].nbe;
+      const int nbe = tile.nbe;
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
       const int mi_cnt = min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
@@ -142,8 +176,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         // LDA: only rho = sum_n B_n X_n is needed, a quadratic form in B, so the K loop of column
         // chunk c stops at the diagonal block (P' = lower triangle of P with a halved diagonal)
         const int nkc = GGA ? nk : min(nk, (FN / FK) * (c + 1));
-        const bool full_tile = mi_cnt == 8 && ni_cnt == 2;
         const bool active = mi_cnt > 0 && ni_cnt > 0;
+        const int mi_var = (mi_cnt + 1) >> 1;
         double acc[8][2][2];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
@@ -154,33 +188,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
           mbar_wait(&S.full[s], ph);
           const double* as = &S.A[s][t][0];
           const double* ps = &S.P[s][t][wn * 16 + g];
-          if (full_tile) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              double a[8], b[2];
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi) a[mi] = as[kk * 4 * TP + A_IDX(mi)];
-#pragma unroll
-              for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-            }
-          } else if (active) {
-            // ragged tile / last column strip: all fragment loads up front, warp-uniform predicates
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              double a[8], b[2];
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi) a[mi] = as[kk * 4 * TP + A_IDX(mi)];
-#pragma unroll
-              for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
-#pragma unroll
-              for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 2; ++ni)
-                  if (mi < mi_cnt && ni < ni_cnt) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          if (active) {
+            switch (mi_var) {
+              case 4: mma_stage<8>(acc, as, ps, a_ev, a_od); break;
+              case 3: mma_stage<6>(acc, as, ps, a_ev, a_od); break;
+              case 2: mma_stage<4>(acc, as, ps, a_ev, a_od); break;
+              default: mma_stage<2>(acc, as, ps, a_ev, a_od); break;
             }
           }
           mbar_arrive(&S.empty[s]);
@@ -211,7 +224,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
-      const int nbe = pv.tasks[tile.task].nbe;
+      const int nbe = tile.nbe;
       const size_t ms = (size_t)pad16(nbe) * TP;
       const double* __restrict__ Bt = ws + tile.ws_off + cofs;
       const int nn = (nbe + FN - 1) / FN;
@@ -228,11 +241,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const double* src = Bt + (size_t)(n0 + n + 4 * u) * TP;
-            ldg256_stream(b0[u], src);
+            ldg_stream(b0[u], src);
             if (GGA) {
-              ldg256_stream(b1[u], src + ms);
-              ldg256_stream(b2[u], src + 2 * ms);
-              ldg256_stream(b3[u], src + 3 * ms);
+              ldg_stream(b1[u], src + ms);
+              ldg_stream(b2[u], src + 2 * ms);
+              ldg_stream(b3[u], src + 3 * ms);
             }
             lds4(x[u], &S.X[n + 4 * u][p4]);
           }
@@ -251,11 +264,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
         if (n < ncols) {
           double x[4], b0[4], b1[4], b2[4], b3[4];
           const double* src = Bt + (size_t)(n0 + n) * TP;
-          ldg256_stream(b0, src);
+          ldg_stream(b0, src);
           if (GGA) {
-            ldg256_stream(b1, src + ms);
-            ldg256_stream(b2, src + 2 * ms);
-            ldg256_stream(b3, src + 3 * ms);
+            ldg_stream(b1, src + ms);
+            ldg_stream(b2, src + 2 * ms);
+            ldg_stream(b3, src + 3 * ms);
           }
           lds4(x, &S.X[n][p4]);
 #pragma unroll
@@ -302,7 +315,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
-      const int nbe = pv.tasks[tile.task].nbe;
+      const int nbe = tile.nbe;
       const int nbp = pad16(nbe);
       const size_t ms = (size_t)nbp * TP;
       const double* __restrict__ Bt = ws + tile.ws_off + cofs;
@@ -362,11 +375,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const double* src = Bt + (size_t)(mu - 4 * u) * TP;
-          ldg256_stream(b0[u], src);
+          ldg_stream(b0[u], src);
           if (GGA) {
-            ldg256_stream(b1[u], src + ms);
-            ldg256_stream(b2[u], src + 2 * ms);
-            ldg256_stream(b3[u], src + 3 * ms);
+            ldg_stream(b1[u], src + ms);
+            ldg_stream(b2[u], src + 2 * ms);
+            ldg_stream(b3[u], src + 3 * ms);
           }
         }
 #pragma unroll
@@ -381,17 +394,17 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
               z[j] = fma(fz4[j], b3[u][j], z[j]);
             }
           }
-          stg256(Z + (size_t)(mu - 4 * u) * TP, z);
+          stg_stream(Z + (size_t)(mu - 4 * u) * TP, z);
         }
       }
       if (mu >= 0) {
         double b0[4], b1[4], b2[4], b3[4], z[4];
         const double* src = Bt + (size_t)mu * TP;
-        ldg256_stream(b0, src);
+        ldg_stream(b0, src);
         if (GGA) {
-          ldg256_stream(b1, src + ms);
-          ldg256_stream(b2, src + 2 * ms);
-          ldg256_stream(b3, src + 3 * ms);
+          ldg_stream(b1, src + ms);
+          ldg_stream(b2, src + 2 * ms);
+          ldg_stream(b3, src + 3 * ms);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -402,7 +415,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
             z[j] = fma(fz4[j], b3[j], z[j]);
           }
         }
-        stg256(Z + (size_t)mu * TP, z);
+        stg_stream(Z + (size_t)mu * TP, z);
       }
     }
   } else {
@@ -432,11 +445,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       }
       if (tile_idx < 0) break;
       const DevTile tile = tiles[tile_idx];
-      const DevTask task = pv.tasks[tile.task];
-      const int nbe = task.nbe;
+      const int nbe = tile.nbe;
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
-      const int* __restrict__ ao = pv.task_ao + task.ao_off;
+      const int* __restrict__ ao = pv.task_ao + tile.ao_off;
       const int rowB = (int)(tile.ws_off / TP);
       const int W = tile_width(tile.npts);
       for (int c = 0; c < nn; ++c) {
@@ -460,9 +472,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
           if (pw == 0) {
             // B^T rows: one bulk copy per row of only the W columns the tile owns (shared-memory
             // pitch stays 128 points, so the MMA addressing is independent of W)
-            if (lane == 0) mbar_expect_tx(&S.full[s], FK * W * sizeof(double));
+            if (lane == 0 && !(GXB_KNOCKOUT & 4)) mbar_expect_tx(&S.full[s], FK * W * sizeof(double));
             __syncwarp();
-            if (lane < FK)
+            if (lane < FK && !(GXB_KNOCKOUT & 4))
               bulk_load_1d(&S.A[s][lane][0], ws + (size_t)(rowB + k0 + lane) * TP, W * sizeof(double),
                            &S.full[s]);
           }
@@ -472,6 +484,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
             const bool vr = rb >= 0;
             const double* src = P + (vr ? rb : 0);
             const int k = k0 + pw * 4 + r;  // LDA: rows k <= n only (see the MMA warps)
+            if (GXB_KNOCKOUT & 2) continue;
             cp_async8_zfill(&S.P[s][pw * 4 + r][lane], src + ca, vr && va && (GGA || k <= na));
             cp_async8_zfill(&S.P[s][pw * 4 + r][lane + 32], src + cb, vr && vb && (GGA || k <= nb));
           }

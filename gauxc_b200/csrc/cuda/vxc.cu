@@ -47,6 +47,28 @@ struct VxcSmem {
 };
 constexpr size_t VXC_SMEM_BYTES = sizeof(VxcSmem) + 1024;
 
+// One K step (16 points) of a warp's 32 x 32 tile restricted to MI x NI 8 x 8 blocks: straight-line,
+// UNPREDICATED DMMAs (a predicated mma.sync costs a WARPSYNC each); ragged blocks dispatch once per
+// K step to the variant with the counts rounded up to even -- rows beyond nbe are zero pad rows or
+// rows of the neighbouring matrix (finite), and their accumulators are never scattered.
+template <int MI, int NI>
+__device__ __forceinline__ void vxc_step(double (&acc)[4][4][2], const double* __restrict__ as,
+                                         const double* __restrict__ zs, int t, int sw) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int col = (kk * 4 + t) ^ sw;
+    double a[MI], b[NI];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) a[mi] = as[mi * 8 * VK + col];
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) b[ni] = zs[ni * 8 * VK + col];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+  }
+}
+
 __global__ void __launch_bounds__(V_THREADS, 1)
 vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile* __restrict__ tiles,
            const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int sym,
@@ -79,31 +101,57 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
     tma_prefetch_desc(&tmapV);
     int s = 0;
     uint32_t ph = 0;
+    const int tile_rows = zmat + 1;  // matrices per tile: the row stride of a tile is tile_rows * pad16(nbe)
+    // the item record is self-contained (no dependent task / tile loads) and fetched ONE ITEM AHEAD,
+    // so the queue pop + metadata latency hides behind the TMA issue loop of the current item
+    auto fetch = [&](int idx) {
+      VxcItem r;
+      if (idx < nitems) {
+        const int4* src = reinterpret_cast<const int4*>(items + idx);
+        const int4 a = __ldg(src), b = __ldg(src + 1);
+        r.nbe = a.x; r.ao_off = a.y; r.mblk = a.z; r.nblk = a.w;
+        r.row0 = b.x; r.ntiles = b.y; r.nks_last = b.z; r.pad = b.w;
+      } else {
+        r.nbe = r.ao_off = r.mblk = r.nblk = r.row0 = r.ntiles = r.nks_last = r.pad = 0;
+      }
+      return r;
+    };
+    // queue pops run two items ahead and record loads one item ahead, so neither latency is on the
+    // critical path of an item -- except near the end of the queue (fewer than `margin` items left),
+    // where holding popped items would unbalance the tail: there the next item is popped only after
+    // the current one has been issued
+    const int margin = 4 * (int)gridDim.x;
+    auto pop = [&]() { return atomicAdd(counter, 1); };
+    int idx = pop();
+    int idx1 = (idx + margin < nitems) ? pop() : -1;
+    VxcItem item = fetch(idx);
     for (int it = 0;; ++it) {
       const int slot = it & (VQ - 1);
       mbar_wait(&S.qempty[slot], ((it / VQ) & 1) ^ 1);
-      const int idx = atomicAdd(counter, 1);
       if (idx >= nitems) {
         S.q[slot].nks = -1;
         mbar_arrive(&S.qfull[slot]);
         break;
       }
-      const VxcItem item = items[idx];
-      const DevTask task = pv.tasks[item.task];
-      const int nbp = pad16(task.nbe);
+      VxcItem nxt = item;
+      int idx2 = -1;
+      if (idx1 >= 0) {
+        nxt = fetch(idx1);
+        if (idx1 + margin < nitems) idx2 = pop();
+      }
+      const int nbp = pad16(item.nbe);
       const int m0 = item.mblk * VXC_BLK, n0 = item.nblk * VXC_BLK;
-      int nks_total = 0;
-      for (int q = item.tile_begin; q < item.tile_end; ++q) nks_total += (tiles[q].npts + VK - 1) / VK;
       VxcSlot sl;
-      sl.nbe = task.nbe; sl.ao_off = task.ao_off; sl.m0 = m0; sl.n0 = n0; sl.nks = nks_total;
+      sl.nbe = item.nbe; sl.ao_off = item.ao_off; sl.m0 = m0; sl.n0 = n0;
+      sl.nks = (item.ntiles - 1) * (TP / VK) + item.nks_last;
       sl.diag = (sym && item.mblk == item.nblk) ? 1 : 0; sl.pad0 = sl.pad1 = 0;
       S.q[slot] = sl;
       mbar_arrive(&S.qfull[slot]);
-      for (int q = item.tile_begin; q < item.tile_end; ++q) {
-        const DevTile tl = tiles[q];
-        const int rowB = (int)(tl.ws_off / TP);
+      const int stride = tile_rows * nbp;
+      for (int q = 0; q < item.ntiles; ++q) {
+        const int rowB = item.row0 + q * stride;
         const int rowZ = rowB + zmat * nbp;
-        const int nks = (tl.npts + VK - 1) / VK;
+        const int nks = (q + 1 < item.ntiles) ? TP / VK : item.nks_last;
         for (int ks = 0; ks < nks; ++ks) {
           mbar_wait(&S.empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&S.full[s], 2 * VXC_BLK * VK * sizeof(double));
@@ -112,6 +160,13 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
           if (++s == VSTAGES) { s = 0; ph ^= 1; }
         }
       }
+      if (idx1 < 0) {  // tail of the queue: lazy pop
+        idx1 = pop();
+        nxt = fetch(idx1);
+      }
+      item = nxt;
+      idx = idx1;
+      idx1 = idx2;
     }
     return;
   }
@@ -138,7 +193,16 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
     const int ni_cnt = min(4, max(0, (nbe - n0 - wn * 32 + 7) / 8));
     const bool diag = sl.diag != 0;
     const bool active = mi_cnt > 0 && ni_cnt > 0 && !(diag && wn > wm);
-    const bool full_blk = active && mi_cnt == 4 && ni_cnt == 4;
+    const int var = (mi_cnt > 2 ? 2 : 0) | (ni_cnt > 2 ? 1 : 0);
+    // global AO indices of the warp's 32 rows / 32 columns, lane = row (column): requested now, read
+    // through shuffles in the scatter, so their latency hides behind the K loop
+    const int* __restrict__ ao = pv.task_ao + sl.ao_off;
+    int ao_r = -1, ao_c = -1;
+    {
+      const int r = m0 + wm * 32 + lane, c = n0 + wn * 32 + lane;
+      if (r < nbe) ao_r = __ldg(ao + r);
+      if (c < nbe) ao_c = __ldg(ao + c);
+    }
 
     double acc[4][4][2];
 #pragma unroll
@@ -151,26 +215,11 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
       if (active) {
         const double* as = &S.A[s][wm * 32 + g][0];
         const double* zs = &S.Z[s][wn * 32 + g][0];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int col = (kk * 4 + t) ^ sw;
-          double a[4], b[4];
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi) a[mi] = as[mi * 8 * VK + col];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) b[ni] = zs[ni * 8 * VK + col];
-          if (full_blk) {
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-          } else {
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni)
-                if (mi < mi_cnt && ni < ni_cnt) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-          }
+        switch (var) {
+          case 3: vxc_step<4, 4>(acc, as, zs, t, sw); break;
+          case 2: vxc_step<4, 2>(acc, as, zs, t, sw); break;
+          case 1: vxc_step<2, 4>(acc, as, zs, t, sw); break;
+          default: vxc_step<2, 2>(acc, as, zs, t, sw); break;
         }
       }
       mbar_arrive(&S.empty[s]);
@@ -179,19 +228,24 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
     if (!active) continue;
 
     // scatter: VXC_sub = M + M^T, only the lower triangle of the full matrix is accumulated
-    const int* __restrict__ ao = pv.task_ao + sl.ao_off;
+    int gm[4], gn[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) gm[mi] = __shfl_sync(0xffffffffu, ao_r, mi * 8 + g);
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) gn[ni][j] = __shfl_sync(0xffffffffu, ao_c, ni * 8 + 2 * t + j);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         if (mi >= mi_cnt || ni >= ni_cnt) continue;
         const int mu = m0 + wm * 32 + mi * 8 + g;
-        if (mu >= nbe) continue;
-        const int gm = __ldg(ao + mu);
+        if (gm[mi] < 0) continue;  // mu >= nbe
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int nu = n0 + wn * 32 + ni * 8 + 2 * t + j;
-          if (nu >= nbe) continue;
+          if (gn[ni][j] < 0) continue;  // nu >= nbe
           double v = acc[mi][ni][j];
           if (sym) {
             if (diag && nu > mu) continue;  // M symmetric: the mirror entry carries it
@@ -199,8 +253,7 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
           } else if (mu == nu) {
             v *= 2.;
           }
-          const int gn = __ldg(ao + nu);
-          const int hi = max(gm, gn), lo = min(gm, gn);
+          const int hi = max(gm[mi], gn[ni][j]), lo = min(gm[mi], gn[ni][j]);
           atomicAdd(VXC + (size_t)lo * ldv + hi, v);
         }
       }

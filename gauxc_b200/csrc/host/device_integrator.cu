@@ -249,6 +249,8 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
       tl.task = (int)it;
       tl.pt_off = d.pt_off + p0;
       tl.npts = std::min(gxb::TP, d.npts - p0);
+      tl.nbe = d.nbe;
+      tl.ao_off = d.ao_off;
       plan->tiles.push_back(tl);
     }
     plan->f_dense += 4. * double(d.nbe) * double(d.nbe) * double(d.npts);
@@ -326,20 +328,45 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
       while (e < b.tile_end && sc->tiles[e].task == sc->tiles[q].task) ++e;
       const int nbe = plan.tasks[sc->tiles[q].task].nbe;
       const int nb = (nbe + gxb::VXC_BLK - 1) / gxb::VXC_BLK;
-      for (int c = q; c < e; c += tiles_per_item)
+      const size_t need = (size_t)nmat * gxb::pad16(nbe) * gxb::TP;
+      for (int c = q; c < e; c += tiles_per_item) {
+        const int ce = std::min(e, c + tiles_per_item);
+        for (int t = c; t < ce; ++t) {
+          // what the self-contained item record relies on
+          if (sc->tiles[t].ws_off != sc->tiles[c].ws_off + (int64_t)((t - c) * need) ||
+              (t + 1 < ce && sc->tiles[t].npts != gxb::TP))
+            GAUXC_GENERIC_EXCEPTION("Inconsistent Tile Layout In VXC Item");
+        }
         for (int im = 0; im < nb; ++im)
           for (int in = 0; in < (sym ? im + 1 : nb); ++in) {
             gxb::VxcItem it{};
-            it.task = sc->tiles[q].task;
+            it.nbe = nbe;
+            it.ao_off = plan.tasks[sc->tiles[q].task].ao_off;
             it.mblk = im;
             it.nblk = in;
-            it.tile_begin = c - b.tile_begin;
-            it.tile_end = std::min(e, c + tiles_per_item) - b.tile_begin;
+            it.row0 = (int)(sc->tiles[c].ws_off / gxb::TP);
+            it.ntiles = ce - c;
+            it.nks_last = (sc->tiles[ce - 1].npts + 15) / 16;
             sc->items.push_back(it);
           }
+      }
       q = e;
     }
     b.item_end = (int)sc->items.size();
+    // Few items per CTA (small molecules): the persistent CTAs drain the queue in a handful of pops,
+    // so one long item popped last would dominate the kernel.  Longest-first order then bounds the
+    // tail by the smallest items; L2 locality of the task order is irrelevant at that size.  Large
+    // batches keep the task order (VXC regions stay L2-resident) -- their tail is negligible.
+    if (b.item_end - b.item_begin < 64 * ncta) {
+      auto cost = [](const gxb::VxcItem& x) {
+        const long long rows = std::min(gxb::VXC_BLK, x.nbe - x.mblk * gxb::VXC_BLK);
+        const long long cols = std::min(gxb::VXC_BLK, x.nbe - x.nblk * gxb::VXC_BLK);
+        const long long nks = (long long)(x.ntiles - 1) * (gxb::TP / 16) + x.nks_last;
+        return rows * cols * nks;
+      };
+      std::stable_sort(sc->items.begin() + b.item_begin, sc->items.begin() + b.item_end,
+                       [&](const gxb::VxcItem& x, const gxb::VxcItem& y) { return cost(x) > cost(y); });
+    }
     sc->batches.push_back(b);
     sc->max_batch_tiles = std::max(sc->max_batch_tiles, b.tile_end - b.tile_begin);
     ws_max = std::max(ws_max, cur);
@@ -903,6 +930,7 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   for (int p0 = 0; p0 < npts; p0 += gxb::TP) {
     gxb::DevTile t{};
     t.task = 0; t.pt_off = p0; t.npts = (int)std::min<int64_t>(gxb::TP, npts - p0);
+    t.nbe = nbe; t.ao_off = 0;
     t.ws_off = (int64_t)tiles.size() * nmat * gxb::pad16(nbe) * gxb::TP;
     tiles.push_back(t);
   }
