@@ -137,7 +137,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
   if (tid == 0) {
     for (int s = 0; s < FSTAGES; ++s) {
       mbar_init(&S.full[s], PROD_THREADS);  // producer lanes (cp.async arrivals) + TMA bytes
-      mbar_init(&S.empty[s], MMA_THREADS);
+      mbar_init(&S.empty[s], MMA_WARPS);  // one elected arrive per MMA warp
     }
     mbar_init(&S.xfull, MMA_THREADS);
     mbar_init(&S.xempty, DEN_THREADS);
@@ -196,7 +196,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
               default: mma_stage<2>(acc, as, ps, a_ev, a_od); break;
             }
           }
-          mbar_arrive(&S.empty[s]);
+          // release the stage: one arrive per warp (256 per-thread arrives on one mbarrier would
+          // serialise in the shared-memory atomic unit every stage)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.empty[s]);
           if (++s == FSTAGES) { s = 0; ph ^= 1; }
         }
         // hand the chunk of X to the density warps

@@ -84,11 +84,11 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
   if (tid == 0) {
     for (int s = 0; s < VSTAGES; ++s) {
       mbar_init(&S.full[s], 1);
-      mbar_init(&S.empty[s], V_MMA_THREADS);
+      mbar_init(&S.empty[s], V_MMA_WARPS);  // one elected arrive per MMA warp
     }
     for (int i = 0; i < VQ; ++i) {
       mbar_init(&S.qfull[i], 1);
-      mbar_init(&S.qempty[i], V_MMA_THREADS);
+      mbar_init(&S.qempty[i], V_MMA_WARPS);
     }
     mbar_fence_init();
   }
@@ -186,7 +186,8 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
     const int slot = it & (VQ - 1);
     mbar_wait(&S.qfull[slot], (it / VQ) & 1);
     const VxcSlot sl = S.q[slot];
-    mbar_arrive(&S.qempty[slot]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.qempty[slot]);
     if (sl.nks < 0) break;
     const int nbe = sl.nbe, m0 = sl.m0, n0 = sl.n0;
     const int mi_cnt = min(4, max(0, (nbe - m0 - wm * 32 + 7) / 8));
@@ -222,7 +223,10 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
           default: vxc_step<2, 2>(acc, as, zs, t, sw); break;
         }
       }
-      mbar_arrive(&S.empty[s]);
+      // one arrive per warp: 512 per-thread arrives on one mbarrier would serialise in the
+      // shared-memory atomic unit every K step
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[s]);
       if (++s == VSTAGES) { s = 0; ph ^= 1; }
     }
     if (!active) continue;
