@@ -95,12 +95,12 @@ __device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
 // rows / columns beyond the tile multiply stale-but-finite or zero-filled operands and are never read.
 template <int MI>
 __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* __restrict__ as,
-                                          const double* __restrict__ ps, int a_ev, int a_od) {
+                                          const double* __restrict__ ps, int a_ev, int a_od, int ap) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     double a[MI], b[2];
 #pragma unroll
-    for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * TP + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
+    for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * ap + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
 #pragma unroll
@@ -112,7 +112,7 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
 
 template <bool GGA>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView pv,
+fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
                            const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
                            double* __restrict__ ws,
                            const double* __restrict__ P, int ldp, FunctionalDesc func,
@@ -171,6 +171,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
       const int mi_cnt = min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
+      const int ap = tile_width(tile.npts);  // shared-memory pitch of the B^T box of this tile
       for (int c = 0; c < nn; ++c) {
         const int ni_cnt = min(2, max(0, (nbe - c * FN - wn * 16 + 7) / 8));
         // LDA: only rho = sum_n B_n X_n is needed, a quadratic form in B, so the K loop of column
@@ -186,14 +187,14 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 
         for (int ks = 0; ks < nkc; ++ks) {
           mbar_wait(&S.full[s], ph);
-          const double* as = &S.A[s][t][0];
+          const double* as = &S.A[s][0][0] + t * ap;
           const double* ps = &S.P[s][t][wn * 16 + g];
           if (active) {
             switch (mi_var) {
-              case 4: mma_stage<8>(acc, as, ps, a_ev, a_od); break;
-              case 3: mma_stage<6>(acc, as, ps, a_ev, a_od); break;
-              case 2: mma_stage<4>(acc, as, ps, a_ev, a_od); break;
-              default: mma_stage<2>(acc, as, ps, a_ev, a_od); break;
+              case 4: mma_stage<8>(acc, as, ps, a_ev, a_od, ap); break;
+              case 3: mma_stage<6>(acc, as, ps, a_ev, a_od, ap); break;
+              case 2: mma_stage<4>(acc, as, ps, a_ev, a_od, ap); break;
+              default: mma_stage<2>(acc, as, ps, a_ev, a_od, ap); break;
             }
           }
           // release the stage: one arrive per warp (256 per-thread arrives on one mbarrier would
@@ -429,7 +430,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
     const int pw = warp - (MMA_WARPS + DEN_WARPS + Z_WARPS);
     int s = 0;
     uint32_t ph = 0;
-    if (pw == 0 && lane == 0) tma_prefetch_desc(&tmapA);
+    if (pw == 0 && lane < 4) tma_prefetch_desc(&tmaps.m[lane]);
     for (int it = 0;; ++it) {
       int tile_idx;
       if (pw == 0) {
@@ -473,13 +474,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
           }
           mbar_wait(&S.empty[s], ph ^ 1);
           if (pw == 0) {
-            // B^T rows: one bulk copy per row of only the W columns the tile owns (shared-memory
-            // pitch stays 128 points, so the MMA addressing is independent of W)
-            if (lane == 0 && !(GXB_KNOCKOUT & 4)) mbar_expect_tx(&S.full[s], FK * W * sizeof(double));
-            __syncwarp();
-            if (lane < FK && !(GXB_KNOCKOUT & 4))
-              bulk_load_1d(&S.A[s][lane][0], ws + (size_t)(rowB + k0 + lane) * TP, W * sizeof(double),
-                           &S.full[s]);
+            // B^T: ONE tensor copy of 16 rows x the W columns the tile owns (one descriptor per
+            // width; the box lands dense with pitch W, which the MMA warps address with)
+            if (lane == 0 && !(GXB_KNOCKOUT & 4)) {
+              mbar_expect_tx(&S.full[s], FK * W * sizeof(double));
+              tma_load_2d(&S.A[s][0][0], &tmaps.m[W / 32 - 1], &S.full[s], 0, rowB + k0);
+            }
           }
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
@@ -503,7 +503,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ CUtensorMap tmapA, PlanView p
 
 int fused_threads() { return FUSED_THREADS; }
 
-void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
+void launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                   int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
                   cudaStream_t s) {

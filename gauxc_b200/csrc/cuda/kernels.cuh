@@ -6,14 +6,19 @@
 
 namespace gxb {
 
+// TMA descriptors of the B^T operand of the fused kernel: boxes of 16 rows x (32, 64, 96, 128) points
+struct TmapSet {
+  CUtensorMap m[4];
+};
+
 // K_A  basis collocation (+gradient): writes B (dBx,dBy,dBz) [nbe][TP] per tile
 void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws,
                         bool gradient, cudaStream_t s);
 
 // K_F  fused persistent kernel: X = B P_sub (DMMA) -> rho / grad rho -> functional, weights,
-//      EXC / N_EL tile partials -> Z.  tmapA: box of 16 rows x 128 points over the workspace;
+//      EXC / N_EL tile partials -> Z.  tmapA: boxes of 16 rows x W points over the workspace;
 //      The ncta persistent CTAs pull tile indices [0, ntiles) from *counter (zeroed by the caller).
-void launch_fused(const CUtensorMap& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
+void launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                   int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
                   cudaStream_t s);

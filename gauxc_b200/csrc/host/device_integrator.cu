@@ -592,7 +592,8 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
 struct XCIntegrator::Impl {
   cudaStream_t stream = nullptr;
   DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
-  CUtensorMap tmapA{}, tmapV{};  // TMA views of d_ws: 16 rows x 128 points / 128 rows x 16 points
+  gxb::TmapSet tmapA{};  // TMA views of d_ws: 16 rows x (32..128) points
+  CUtensorMap tmapV{};   // 128 rows x 16 points
   int ncta = 0;
   std::shared_ptr<DevicePlan> plan;
   std::shared_ptr<Schedule> sched;
@@ -696,7 +697,8 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     if (I.sched->ws_doubles) {
       // TMA may read (never use) rows of a neighbouring matrix: keep every byte finite
       CUDA_CHECK(cudaMemsetAsync(I.d_ws.p, 0, I.sched->ws_doubles * sizeof(double), s));
-      I.tmapA = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, gxb::TP, 16);
+      for (int w = 0; w < 4; ++w)
+        I.tmapA.m[w] = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 32 * (w + 1), 16);
       I.tmapV = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 16, gxb::VXC_BLK);
     }
     I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
