@@ -93,11 +93,13 @@ __device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
 // Straight-line, UNPREDICATED DMMAs: a predicated mma.sync costs a WARPSYNC per instruction, so
 // ragged tiles dispatch (warp-uniformly, once per stage) to the variant with MI rounded up to even;
 // rows / columns beyond the tile multiply stale-but-finite or zero-filled operands and are never read.
-template <int MI>
+// KB..KE: the 4-row K steps of the stage this warp takes (all four, or one half in the split-K mode
+// of short tiles).
+template <int MI, int KB = 0, int KE = 4>
 __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* __restrict__ as,
                                           const double* __restrict__ ps, int a_ev, int a_od, int ap) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = KB; kk < KE; ++kk) {
     double a[MI], b[2];
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * ap + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
@@ -161,7 +163,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     uint32_t ph = 0, xph = 0;
     // swizzled column of point (wm*64 + mi*8 + g) in a row with (row & 3) == t:
     // a0 ^ (mi << 3), i.e. a0 + 8*mi for even mi and (a0 ^ 8) + 8*(mi - 1) for odd mi
-    const int a_ev = (wm * 64 + g) ^ (t << 2), a_od = a_ev ^ 8;
+    const int a_ev_full = (wm * 64 + g) ^ (t << 2), a_ev_short = g ^ (t << 2);
 
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
@@ -170,7 +172,13 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       const int nbe = tile.nbe;
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
-      const int mi_cnt = min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
+      // Short tiles (<= 64 points) would leave the wm = 1 warps idle and every sub-partition with a
+      // single MMA warp: there both row halves work on the SAME 64 rows and split each stage's K
+      // steps (wm = 0: rows 0-7 of the stage, wm = 1: rows 8-15); the two partial X are added in
+      // shared memory when the chunk is handed over.
+      const bool split = tile.npts <= 64;
+      const int a_ev = split ? a_ev_short : a_ev_full, a_od = a_ev ^ 8;
+      const int mi_cnt = split ? (tile.npts + 7) / 8 : min(8, max(0, (tile.npts - wm * 64 + 7) / 8));
       const int ap = tile_width(tile.npts);  // shared-memory pitch of the B^T box of this tile
       for (int c = 0; c < nn; ++c) {
         const int ni_cnt = min(2, max(0, (nbe - c * FN - wn * 16 + 7) / 8));
@@ -190,11 +198,27 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
           const double* as = &S.A[s][0][0] + t * ap;
           const double* ps = &S.P[s][t][wn * 16 + g];
           if (active) {
-            switch (mi_var) {
-              case 4: mma_stage<8>(acc, as, ps, a_ev, a_od, ap); break;
-              case 3: mma_stage<6>(acc, as, ps, a_ev, a_od, ap); break;
-              case 2: mma_stage<4>(acc, as, ps, a_ev, a_od, ap); break;
-              default: mma_stage<2>(acc, as, ps, a_ev, a_od, ap); break;
+            if (!split) {
+              switch (mi_var) {
+                case 4: mma_stage<8>(acc, as, ps, a_ev, a_od, ap); break;
+                case 3: mma_stage<6>(acc, as, ps, a_ev, a_od, ap); break;
+                case 2: mma_stage<4>(acc, as, ps, a_ev, a_od, ap); break;
+                default: mma_stage<2>(acc, as, ps, a_ev, a_od, ap); break;
+              }
+            } else if (wm == 0) {
+              switch (mi_var) {
+                case 4: mma_stage<8, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
+                case 3: mma_stage<6, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
+                case 2: mma_stage<4, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
+                default: mma_stage<2, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
+              }
+            } else {
+              switch (mi_var) {
+                case 4: mma_stage<8, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
+                case 3: mma_stage<6, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
+                case 2: mma_stage<4, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
+                default: mma_stage<2, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
+              }
             }
           }
           // release the stage: one arrive per warp (256 per-thread arrives on one mbarrier would
@@ -205,13 +229,34 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         }
         // hand the chunk of X to the density warps
         mbar_wait(&S.xempty, xph ^ 1);
+        if (!split) {
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+          for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 2; ++ni)
+            for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              S.X[wn * 16 + ni * 8 + 2 * t + j][wm * 64 + mi * 8 + g] = acc[mi][ni][j];
+              for (int j = 0; j < 2; ++j)
+                S.X[wn * 16 + ni * 8 + 2 * t + j][wm * 64 + mi * 8 + g] = acc[mi][ni][j];
+        } else {
+          // split-K: the wm = 1 partial goes to shared memory first, wm = 0 adds its own on top
+          if (wm == 1) {
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) S.X[wn * 16 + ni * 8 + 2 * t + j][mi * 8 + g] = acc[mi][ni][j];
+          }
+          named_bar_sync(3, MMA_THREADS);
+          if (wm == 0) {
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) S.X[wn * 16 + ni * 8 + 2 * t + j][mi * 8 + g] += acc[mi][ni][j];
+          }
+        }
         mbar_arrive(&S.xfull);
         xph ^= 1;
       }
