@@ -296,19 +296,46 @@ def main():
     k_names = ["collocation", "xmat_density(DMMA)", "func_zmat", "vxc(DMMA)"]
     k_ms = (kms / args.steps).tolist()
     nb = max(1, int(st["nbatches"]))
+    gga = s.func_name.upper().startswith("PBE")
+    hbm_peak = peaks.get("hbm_gbs")
+    # per-kernel rooflines: algorithmic work per step / CUDA-event time of that kernel.
+    # The contractions are charged 2 nbe^2 npts flops each for LDA and GGA alike (the LDA kernels
+    # execute about half of that: triangular quadratic form for rho, SYRK for VXC).
+    colloc_bytes = st["sum_nbe_npts"] * 8 * (4 if gga else 1) + 32.0 * st["npts"]
+
+    def tensor_entry(name, ms):
+        a = 0.5 * f_dense / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": name, "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": a / dmma_peak, "ms_per_step": ms, "launches_per_step": nb,
+                "avg_launch_ms": ms / nb, "flops_per_launch": 0.5 * f_dense / nb}
+
+    per_kernel = [
+        {"kernel": "collocation_kernel", "bound": "hbm", "achieved": colloc_bytes / (k_ms[0] * 1e-3) / 1e9
+         if k_ms[0] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+         "frac": (colloc_bytes / (k_ms[0] * 1e-3) / 1e9 / hbm_peak) if k_ms[0] > 0 and hbm_peak else None,
+         "ms_per_step": k_ms[0], "launches_per_step": nb, "avg_launch_ms": k_ms[0] / nb,
+         "bytes_per_launch": colloc_bytes / nb},
+        tensor_entry("fused_xmat_den_zmat_kernel (X = P_sub B on DMMA + rho/grad rho + functional + Z)", k_ms[1]),
+        tensor_entry("vxc_kernel (VXC_sub = B^T Z + Z^T B on DMMA + scatter-add)", k_ms[3]),
+    ]
+    dom = max(per_kernel[1:], key=lambda e: e["ms_per_step"])  # the dominant kernel of the step
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(args.workload, {}).get(dom["kernel"].split(" ")[0])
+    except Exception:
+        pass
     dense_ms = k_ms[1] + k_ms[3]
-    achieved = f_dense / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "xmat_density_kernel + vxc_kernel (FP64 DMMA m8n8k4 contractions)",
-                "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s", "frac": achieved / dmma_peak,
-                "peak_source": "FP64 DMMA register-resident probe run in this process (MEASURED_PEAKS.json "
-                               "holds HBM/bf16 only)",
-                "flops_per_step": f_dense, "launches_per_step": 2 * nb,
-                "avg_launch_ms": dense_ms / (2 * nb), "traffic": None,
-                "xmat_tflops": 0.5 * f_dense / (k_ms[1] * 1e-3) / 1e12 if k_ms[1] > 0 else None,
-                "vxc_tflops": 0.5 * f_dense / (k_ms[3] * 1e-3) / 1e12 if k_ms[3] > 0 else None,
+    roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dmma_peak,
+                "unit": "TFLOP/s", "frac": dom["frac"],
+                "peak_source": "FP64 DMMA (mma.sync m8n8k4) register-resident probe run in this process; "
+                               "MEASURED_PEAKS.json holds HBM/bf16 only (tcgen05 has no FP64 kind)",
+                "flops_per_launch": dom["flops_per_launch"], "launches_per_step": nb,
+                "avg_launch_ms": dom["avg_launch_ms"], "traffic": traffic,
+                "both_contractions_tflops": f_dense / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0,
                 "kernel_ms_per_step": dict(zip(k_names, k_ms)),
                 "whole_path_fp64_frac": f_dense / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
-                "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peak_src}
+                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "per_kernel": per_kernel}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu = None

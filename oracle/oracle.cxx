@@ -236,9 +236,11 @@ struct Basis {
 // real solid harmonics of order l in CCA order m=-l..l as combinations of cartesian monomials
 // (gau2grid "spherical CCA"; (l,0,0)-normalised cartesians)
 struct SphTerm { int a, b, c; double f; };
-const std::vector<std::vector<SphTerm>>& sph_table(int l) {
-  static std::vector<std::vector<std::vector<SphTerm>>> T;
-  if (T.empty()) {
+// Built once through a thread-safe function-local static (C++11): the first caller may well be an
+// OpenMP worker of oracle_exc_vxc.
+std::vector<std::vector<std::vector<SphTerm>>> build_sph_table() {
+  std::vector<std::vector<std::vector<SphTerm>>> T;
+  {
     T.resize(5);
     const double s3 = std::sqrt(3.);
     T[0] = {{{0, 0, 0, 1.}}};
@@ -267,6 +269,10 @@ const std::vector<std::vector<SphTerm>>& sph_table(int l) {
             {{3, 0, 1, c70 / 4}, {1, 2, 1, -3 * c70 / 4}},
             {{4, 0, 0, c35 / 8}, {2, 2, 0, -6 * c35 / 8}, {0, 4, 0, c35 / 8}}};
   }
+  return T;
+}
+const std::vector<std::vector<SphTerm>>& sph_table(int l) {
+  static const std::vector<std::vector<std::vector<SphTerm>>> T = build_sph_table();
   return T[l];
 }
 
