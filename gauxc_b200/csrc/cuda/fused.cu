@@ -71,13 +71,21 @@ struct FusedSmem {
 constexpr size_t FUSED_SMEM_BYTES = sizeof(FusedSmem) + 1024;
 static_assert(FUSED_SMEM_BYTES <= 232448, "fused kernel shared memory");
 
-__device__ __forceinline__ void ldg_stream(double (&v)[4], const double* p) {
+// L2 priorities of the two streaming passes over a tile's B / dB rows: the density pass marks them
+// evict_last (the Z pass of the same tile re-reads them a few hundred microseconds later), the Z
+// pass reads and writes evict_first (nothing touches those lines again before the VXC kernel).
+#ifndef GXB_L2_HINTS
+#define GXB_L2_HINTS 1
+#endif
+__device__ __forceinline__ void ldg_stream(double (&v)[4], const double* p, uint64_t pol) {
   if (GXB_KNOCKOUT & 1) { v[0] = v[1] = v[2] = v[3] = 1.; return; }
-  ldg256_stream(v, p);
+  if (GXB_L2_HINTS) ldg256_stream_hint(v, p, pol);
+  else ldg256_stream(v, p);
 }
-__device__ __forceinline__ void stg_stream(double* p, const double (&v)[4]) {
+__device__ __forceinline__ void stg_stream(double* p, const double (&v)[4], uint64_t pol) {
   if (GXB_KNOCKOUT & 1) { if (v[0] == 1.2345e-300) stg256(p, v); return; }
-  stg256(p, v);
+  if (GXB_L2_HINTS) stg256_hint(p, v, pol);
+  else stg256(p, v);
 }
 __device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
@@ -269,6 +277,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     const int p4 = lane * 4;               // 4 consecutive points
     const int cofs = p4 ^ (dw << 2);       // their (swizzled) column in every row of this warp
     uint32_t xph = 0, dph = 0;
+    const uint64_t pol_keep = l2_policy_evict_last();
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
@@ -290,11 +299,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const double* src = Bt + (size_t)(n0 + n + 4 * u) * TP;
-            ldg_stream(b0[u], src);
+            ldg_stream(b0[u], src, pol_keep);
             if (GGA) {
-              ldg_stream(b1[u], src + ms);
-              ldg_stream(b2[u], src + 2 * ms);
-              ldg_stream(b3[u], src + 3 * ms);
+              ldg_stream(b1[u], src + ms, pol_keep);
+              ldg_stream(b2[u], src + 2 * ms, pol_keep);
+              ldg_stream(b3[u], src + 3 * ms, pol_keep);
             }
             lds4(x[u], &S.X[n + 4 * u][p4]);
           }
@@ -313,11 +322,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         if (n < ncols) {
           double x[4], b0[4], b1[4], b2[4], b3[4];
           const double* src = Bt + (size_t)(n0 + n) * TP;
-          ldg_stream(b0, src);
+          ldg_stream(b0, src, pol_keep);
           if (GGA) {
-            ldg_stream(b1, src + ms);
-            ldg_stream(b2, src + 2 * ms);
-            ldg_stream(b3, src + 3 * ms);
+            ldg_stream(b1, src + ms, pol_keep);
+            ldg_stream(b2, src + 2 * ms, pol_keep);
+            ldg_stream(b3, src + 3 * ms, pol_keep);
           }
           lds4(x, &S.X[n][p4]);
 #pragma unroll
@@ -360,6 +369,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     const int p4 = lane * 4;
     const int cofs = p4 ^ (zw << 2);
     uint32_t dph = 0;
+    const uint64_t pol_drop = l2_policy_evict_first();
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
@@ -424,11 +434,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const double* src = Bt + (size_t)(mu - 4 * u) * TP;
-          ldg_stream(b0[u], src);
+          ldg_stream(b0[u], src, pol_drop);
           if (GGA) {
-            ldg_stream(b1[u], src + ms);
-            ldg_stream(b2[u], src + 2 * ms);
-            ldg_stream(b3[u], src + 3 * ms);
+            ldg_stream(b1[u], src + ms, pol_drop);
+            ldg_stream(b2[u], src + 2 * ms, pol_drop);
+            ldg_stream(b3[u], src + 3 * ms, pol_drop);
           }
         }
 #pragma unroll
@@ -443,17 +453,17 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
               z[j] = fma(fz4[j], b3[u][j], z[j]);
             }
           }
-          stg_stream(Z + (size_t)(mu - 4 * u) * TP, z);
+          stg_stream(Z + (size_t)(mu - 4 * u) * TP, z, pol_drop);
         }
       }
       if (mu >= 0) {
         double b0[4], b1[4], b2[4], b3[4], z[4];
         const double* src = Bt + (size_t)mu * TP;
-        ldg_stream(b0, src);
+        ldg_stream(b0, src, pol_drop);
         if (GGA) {
-          ldg_stream(b1, src + ms);
-          ldg_stream(b2, src + 2 * ms);
-          ldg_stream(b3, src + 3 * ms);
+          ldg_stream(b1, src + ms, pol_drop);
+          ldg_stream(b2, src + 2 * ms, pol_drop);
+          ldg_stream(b3, src + 3 * ms, pol_drop);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -464,7 +474,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
             z[j] = fma(fz4[j], b3[j], z[j]);
           }
         }
-        stg_stream(Z + (size_t)mu * TP, z);
+        stg_stream(Z + (size_t)mu * TP, z, pol_drop);
       }
     }
   } else {

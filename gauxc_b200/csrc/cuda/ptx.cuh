@@ -101,6 +101,28 @@ __device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
                : "memory");
 }
 
+// ---- L2 eviction-priority hints -------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void ldg256_stream_hint(double (&v)[4], const double* p, uint64_t pol) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;\n"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+               : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void stg256_hint(double* p, const double (&v)[4], uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(p), "d"(v[0]), "d"(v[1]),
+               "d"(v[2]), "d"(v[3]), "l"(pol)
+               : "memory");
+}
+
 // ---- DMMA -----------------------------------------------------------------------------
 // D(8x8) += A(8x4,row) * B(4x8,col); lane = 4*g + t holds A[g][t], B[t][g], C[g][2t..2t+1]
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
