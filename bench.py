@@ -190,6 +190,11 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    # torchrun pins OMP_NUM_THREADS=1; the host-side setup (grid, screening, task merge -- outside the
+    # timed region) is OpenMP code, so give every rank its share of the host cores instead
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world_env))
 
     import torch
     import torch.distributed as dist
