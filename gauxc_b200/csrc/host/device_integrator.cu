@@ -357,15 +357,19 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
     // so one long item popped last would dominate the kernel.  Longest-first order then bounds the
     // tail by the smallest items; L2 locality of the task order is irrelevant at that size.  Large
     // batches keep the task order (VXC regions stay L2-resident) -- their tail is negligible.
+    auto cost = [](const gxb::VxcItem& x) {
+      const long long rows = std::min(gxb::VXC_BLK, x.nbe - x.mblk * gxb::VXC_BLK);
+      const long long cols = std::min(gxb::VXC_BLK, x.nbe - x.nblk * gxb::VXC_BLK);
+      const long long nks = (long long)(x.ntiles - 1) * (gxb::TP / 16) + x.nks_last;
+      return rows * cols * nks;
+    };
+    auto by_cost = [&](const gxb::VxcItem& x, const gxb::VxcItem& y) { return cost(x) > cost(y); };
     if (b.item_end - b.item_begin < 64 * ncta) {
-      auto cost = [](const gxb::VxcItem& x) {
-        const long long rows = std::min(gxb::VXC_BLK, x.nbe - x.mblk * gxb::VXC_BLK);
-        const long long cols = std::min(gxb::VXC_BLK, x.nbe - x.nblk * gxb::VXC_BLK);
-        const long long nks = (long long)(x.ntiles - 1) * (gxb::TP / 16) + x.nks_last;
-        return rows * cols * nks;
-      };
-      std::stable_sort(sc->items.begin() + b.item_begin, sc->items.begin() + b.item_end,
-                       [&](const gxb::VxcItem& x, const gxb::VxcItem& y) { return cost(x) > cost(y); });
+      std::stable_sort(sc->items.begin() + b.item_begin, sc->items.begin() + b.item_end, by_cost);
+    } else {
+      // large batch: only the END of the queue is ordered longest-first, so the last pops of the
+      // persistent CTAs are the cheapest items of that stretch
+      std::stable_sort(sc->items.begin() + (b.item_end - 8 * ncta), sc->items.begin() + b.item_end, by_cost);
     }
     sc->batches.push_back(b);
     sc->max_batch_tiles = std::max(sc->max_batch_tiles, b.tile_end - b.tile_begin);

@@ -223,6 +223,41 @@ def test_edge_cases_ragged_tasks_and_leading_dimensions(orc):
         assert np.all(Vbig[nbf:] == 7.0)  # padding rows untouched
 
 
+def test_lda_triangular_density_matches_host_for_nonsymmetric_P(orc):
+    """The LDA path evaluates rho as a quadratic form over tril((P + P^T)/2) (fused.cu / sym_half_kernel);
+    the host multiplies by P as given.  Both are the same quadratic form, also when P is not symmetric
+    (the reference never symmetrises P, reference_local_host_work_driver.cxx:123-146), and tasks of
+    every tile shape (<= 64 points: split-K; 65..128; several tiles) must agree."""
+    atoms = systems.geometry("taxol")[:24]
+    shells = systems.make_basis_shells(atoms, "def2-svp")
+    _, basis, lb = make_lb(atoms, shells, "FineGrid", device=True)
+    rng = np.random.default_rng(11)
+    nbf, nsh = basis.nbf(), basis.nshells()
+    npts = [17, 64, 65, 96, 128, 200, 333]
+    lists = [sorted(rng.choice(nsh, size=k, replace=False).tolist()) for k in (nsh, nsh // 2, nsh, 40, nsh, 70, nsh)]
+    cen = np.array([a[1:] for a in atoms])
+    pts = cen[rng.integers(0, len(atoms), sum(npts))] + rng.standard_normal((sum(npts), 3)) * 0.8
+    w = rng.uniform(0.01, 0.1, sum(npts))
+    lb.set_tasks(npts, [0] * len(npts), [1.8] * len(npts), pts, w, [len(l) for l in lists],
+                 [x for l in lists for x in l], True)
+    P = systems.synthetic_density(atoms, shells)
+    A = rng.standard_normal((nbf, nbf)) * 1e-3
+    Pn = np.asfortranarray(P + (A - A.T))  # same symmetric part, antisymmetric noise on top
+    tasks = lb.export_tasks()
+    for func in ("SVWN5", "SPW92"):
+        integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func), lb)
+        exc_s, vxc_s = integ.eval_exc_vxc(P)
+        exc_n, vxc_n = integ.eval_exc_vxc(Pn)
+        ref = orc.exc_vxc(basis.flat(), nbf, Pn, tasks, func)
+        assert abs(exc_n - ref["exc"]) <= TOL and np.abs(vxc_n - ref["vxc"]).max() <= TOL
+        assert abs(exc_n - exc_s) <= 1e-11 and np.abs(vxc_n - vxc_s).max() <= 1e-11
+    # GGA reads the full P on both sides: a symmetric P is the contract there (tested above)
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional("PBE"), lb)
+    exc, vxc = integ.eval_exc_vxc(P)
+    ref = orc.exc_vxc(basis.flat(), nbf, P, tasks, "PBE")
+    assert abs(exc - ref["exc"]) <= TOL and np.abs(vxc - ref["vxc"]).max() <= TOL
+
+
 def test_empty_task_list_gives_zero():
     atoms = systems.geometry("water")
     shells = systems.make_basis_shells(atoms, "cc-pvdz")
