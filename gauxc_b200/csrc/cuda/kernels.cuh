@@ -37,9 +37,10 @@ void launch_symmetrize(double* VXC, int nbf, int ldv, cudaStream_t s);
 void launch_sym_half(const double* P, int ldp, double* out, int nbf, cudaStream_t s);
 
 // SSF weights (in place on pv.w)
+//   rab_inv [natoms][natoms]: 1 / R_AB (0 on the diagonal);
 //   nbr_idx / nbr_dist [natoms][natoms]: per atom, all atoms sorted by distance from it (itself first)
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab, const double* dist_nearest, const int* nbr_idx,
+                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
                         const double* nbr_dist, int natoms, cudaStream_t s);
 
 // FP64 peak probes (DMMA m8n8k4 and DFMA), return achieved TFLOP/s

@@ -5,7 +5,10 @@
 // reference's CUDA kernel (cuda_ssf_1d.cu:24-128), whose algorithm differs:
 //   * cutoff: r_parent < 0.5*(1-0.64)*dist_nearest  -> weight unchanged
 //   * P_C = prod_{B != C} s(mu_CB) accumulated in ascending B, with the host's operand order
-//     (B < C: g(mu_CB);  B > C: 1 - g(mu_BC)),  mu = (r_i - r_j) / RAB (a true division)
+//     (B < C: g(mu_CB);  B > C: 1 - g(mu_BC)),  mu = (r_i - r_j) * (1 / RAB) with the reciprocal
+//     precomputed on the host and g() multiplying by 1 / 0.64 = 1.5625: the kernel is FP64-ALU bound
+//     and the host's two divisions per pair were half of its FP64 work; mu moves by at most an ulp,
+//     which the continuous s(mu) turns into O(1e-16) of a weight (golden test: 1e-13 relative)
 //   * w *= P_parent / sum_C P_C, sum in ascending C
 // Instead of materialising natoms distances per point (the reference device path stores a
 // natoms x npts scratch, xc_device_data.hpp:449-451) distances are recomputed, and every loop over
@@ -33,14 +36,14 @@ namespace {
 constexpr double magic_ssf = 0.64;
 
 __device__ __forceinline__ double g_frisch(double mu) {
-  const double s = mu / magic_ssf;
+  const double s = mu * 1.5625;  // 1 / 0.64 (exactly representable; the host divides by 0.64)
   const double s2 = s * s, s3 = s * s2, s5 = s3 * s2, s7 = s5 * s2;
   return (35. * (s - s3) + 21. * s5 - 5. * s7) / 16.;
 }
 
 __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __restrict__ tiles,
                                                   const double* __restrict__ atoms,
-                                                  const double* __restrict__ rab,
+                                                  const double* __restrict__ rab_inv,
                                                   const double* __restrict__ dist_nearest,
                                                   const int* __restrict__ nbr_idx,
                                                   const double* __restrict__ nbr_dist,
@@ -111,27 +114,27 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
     const int C = nb[kc];
     const double rC = dist(C);
     if (C != imin) {
-      const double R = rab[(size_t)C * natoms + imin];
+      const double Rinv = rab_inv[(size_t)C * natoms + imin];
       // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
-      const double mu = (C > imin) ? (rC - rmin) / R : -((rmin - rC) / R);
+      const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
       if (mu >= magic_ssf) continue;  // P_C == 0
     }
     double Pc = 1.;
-    const double* __restrict__ rabC = rab + (size_t)C * natoms;
+    const double* __restrict__ rabC = rab_inv + (size_t)C * natoms;
     const double b_cut = kappa * rC;
     for (int kb = 0; kb < natoms; ++kb) {
       if (nd[kb] - r_anc >= b_cut) break;  // every remaining factor is exactly 1
       const int Bq = nb[kb];
       if (Bq == C) continue;
       const double rB = dist(Bq);
-      const double R = rabC[Bq];
+      const double Rinv = rabC[Bq];
       if (Bq < C) {
-        const double mu = (rC - rB) / R;
+        const double mu = (rC - rB) * Rinv;
         if (mu <= -magic_ssf) continue;
         if (mu >= magic_ssf) { Pc = 0.; break; }
         Pc *= 0.5 * (1. - g_frisch(mu));
       } else {
-        const double mu = (rB - rC) / R;
+        const double mu = (rB - rC) * Rinv;
         if (mu <= -magic_ssf) { Pc = 0.; break; }
         if (mu >= magic_ssf) continue;
         const double gq = 0.5 * (1. - g_frisch(mu));
@@ -147,10 +150,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
 }  // namespace
 
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab, const double* dist_nearest, const int* nbr_idx,
+                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
                         const double* nbr_dist, int natoms, cudaStream_t s) {
   if (ntiles <= 0) return;
-  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab, dist_nearest, nbr_idx, nbr_dist, natoms);
+  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab_inv, dist_nearest, nbr_idx, nbr_dist, natoms);
 }
 
 }  // namespace gxb

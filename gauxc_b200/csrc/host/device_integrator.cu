@@ -277,7 +277,12 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
   plan->d_pz.upload(pz);
   plan->d_w.upload(w);
   plan->d_atoms.upload(atoms);
-  plan->d_rab.upload(meta.rab);
+  {
+    // the SSF kernel multiplies by 1 / R_AB (an FP64 division costs ~15 FP64 operations per pair)
+    std::vector<double> rab_inv(meta.rab.size());
+    for (size_t q = 0; q < rab_inv.size(); ++q) rab_inv[q] = meta.rab[q] > 0. ? 1. / meta.rab[q] : 0.;
+    plan->d_rab.upload(rab_inv);
+  }
   plan->d_dist_nearest.upload(meta.dist_nearest);
   {
     const size_t na = mol.size();
