@@ -54,7 +54,7 @@ def test_c_client_matches_the_python_binding(client):
     a_h = [3.42525091, 0.62391373, 0.16885540]
 
     def sh(l, a, c, at):
-        return dict(l=l, pure=True, alpha=a, coeff=c, origin=list(at[1:]), tol=1e-10)
+        return dict(l=l, pure=True, exps=a, coefs=c, origin=list(at[1:]), tol=1e-10)
 
     shells = [sh(0, a_o1, c_s, atoms[0]), sh(0, a_o2, c_2s, atoms[0]), sh(1, a_o2, c_2p, atoms[0]),
               sh(0, a_h, c_s, atoms[1]), sh(0, a_h, c_s, atoms[2])]
