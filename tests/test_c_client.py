@@ -11,6 +11,7 @@ from conftest import ROOT
 from gauxc_b200 import capi
 
 SRC = os.path.join(ROOT, "tests", "c_client", "exc_vxc_client.c")
+SRC_CPP = os.path.join(ROOT, "tests", "c_client", "exc_vxc_client.cpp")
 LIBDIR = os.path.join(ROOT, "gauxc_b200")
 
 
@@ -22,6 +23,41 @@ def client(tmp_path_factory):
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
+
+
+@pytest.fixture(scope="module")
+def client_cpp(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("cpp_client") / "exc_vxc_client_cpp")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC_CPP,
+           "-o", exe, "-L", LIBDIR, "-lgauxc_b200", "-Wl,-rpath," + LIBDIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_facade_client_compiles_links_and_fails_loudly_without_a_gpu(client_cpp):
+    """include/gauxc_b200.hpp: the reference's C++ API surface for this path (factories, MatrixType
+    facade, exceptions) header-only over the C ABI; same contract as the C client."""
+    r = subprocess.run([client_cpp], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.startswith("nbf 7, ") and 170000 < int(r.stderr.split()[2]) <= 175230
+    if capi.device_count() == 0:
+        assert r.stdout.startswith("NO_DEVICE"), r.stdout
+    else:
+        assert r.stdout.startswith("EXC "), r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_facade_client_matches_the_c_client(client, client_cpp):
+    a = subprocess.run([client], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([client_cpp], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    ta, tb = a.stdout.split(), b.stdout.split()
+    assert ta[0] == tb[0] == "EXC" and ta[5] == tb[5]
+    va = np.array([float(x) for x in ta[7:]])
+    vb = np.array([float(x) for x in tb[7:]])
+    assert abs(float(ta[1]) - float(tb[1])) <= 1e-12 and np.abs(va - vb).max() <= 1e-12
+    assert abs(float(ta[3]) - float(tb[3])) <= 1e-10
 
 
 def test_c_client_compiles_links_and_fails_loudly_without_a_gpu(client):
