@@ -222,6 +222,81 @@ void eval_func(const Func& f, int npts, const double* rho, const double* sigma, 
   }
 }
 
+// ---- spin-polarised LDA (UKS) -------------------------------------------
+// Inputs rho_+ / rho_- (eval_uvvar_lda_uks, reference_local_host_work_driver.cxx:166-188), outputs
+// eps (energy per particle of the TOTAL density) and d(rho eps)/d rho_sigma, the interleaved layout
+// ExchCXX / libxc use for polarised LDA.  Pinned by cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks.
+void f_slater_pol(double ra, double rb, double& e, double& va, double& vb) {
+  const double rho = ra + rb;
+  if (rho <= 1e-24) { e = va = vb = 0; return; }
+  // exact spin scaling E_x[ra, rb] = (E_x[2 ra] + E_x[2 rb]) / 2
+  const double cx = -0.75 * std::cbrt(3. / PI);
+  auto per_spin = [&](double r, double& en, double& v) {
+    if (r <= 0.) { en = v = 0; return; }
+    const double t = std::cbrt(2. * r);
+    en = cx * t * r;        // (1/2) cx (2 r)^(4/3)
+    v = 4. / 3. * cx * t;   // d en / d r
+  };
+  double ea, eb;
+  per_spin(ra, ea, va);
+  per_spin(rb, eb, vb);
+  e = (ea + eb) / rho;
+}
+
+// one VWN fit eps(x = sqrt(rs)) and d eps/d rs for a parameter set (A, b, c, x0)
+void vwn_fit(double A, double b, double c, double x0, double rs, double& e, double& de_drs) {
+  const double x = std::sqrt(rs);
+  auto Xf = [&](double y) { return y * y + b * y + c; };
+  const double Q = std::sqrt(4. * c - b * b);
+  const double X = Xf(x), Xp = 2. * x + b;
+  const double at = std::atan(Q / Xp);
+  e = A * (std::log(x * x / X) + 2. * b / Q * at -
+           b * x0 / Xf(x0) * (std::log((x - x0) * (x - x0) / X) + 2. * (b + 2. * x0) / Q * at));
+  const double dat = -2. * Q / (Xp * Xp + Q * Q);
+  const double de_dx = A * ((2. / x - Xp / X) + 2. * b / Q * dat -
+                            b * x0 / Xf(x0) * ((2. / (x - x0) - Xp / X) + 2. * (b + 2. * x0) / Q * dat));
+  de_drs = de_dx / (2. * x);
+}
+// libxc XC_LDA_C_VWN_RPA (what ExchCXX's Kernel::VWN5 evaluates, see f_vwn5): para- and ferromagnetic
+// RPA fits interpolated with f(zeta) = ((1+z)^(4/3) + (1-z)^(4/3) - 2) / (2^(4/3) - 2)
+void f_vwn5_pol(double ra, double rb, double& e, double& va, double& vb) {
+  const double rho = ra + rb;
+  if (rho <= 1e-24) { e = va = vb = 0; return; }
+  const double rs = std::cbrt(3. / (4. * PI * rho));
+  double z = (ra - rb) / rho;
+  z = std::min(1., std::max(-1., z));
+  double eP, dP, eF, dF;
+  vwn_fit(0.0310907, 13.0720, 42.7198, -0.409286, rs, eP, dP);
+  vwn_fit(0.01554535, 20.1231, 101.578, -0.743294, rs, eF, dF);
+  const double den = std::cbrt(2.) * 2. - 2.;
+  const double op = std::cbrt(1. + z), om = std::cbrt(1. - z);
+  const double fz = (op * (1. + z) + om * (1. - z) - 2.) / den;
+  const double dfz = 4. / 3. * (op - om) / den;
+  e = eP + (eF - eP) * fz;
+  const double de_drs = dP + (dF - dP) * fz;
+  const double de_dz = (eF - eP) * dfz;
+  // d(rho e)/d rho_sigma = e - rs/3 de/drs + (+-1 - z) de/dz
+  const double common = e - rs / 3. * de_drs;
+  va = common + (1. - z) * de_dz;
+  vb = common - (1. + z) * de_dz;
+}
+
+void eval_func_pol_lda(const Func& f, int npts, const double* rho2, double* eps, double* vrho2) {
+  for (int i = 0; i < npts; ++i) {
+    double E = 0, VA = 0, VB = 0;
+    for (int k = 0; k < f.nkern; ++k) {
+      double e = 0, va = 0, vb = 0;
+      switch (f.kern[k]) {
+        case K_SLATER_X: f_slater_pol(rho2[2 * i], rho2[2 * i + 1], e, va, vb); break;
+        case K_VWN5_C: f_vwn5_pol(rho2[2 * i], rho2[2 * i + 1], e, va, vb); break;
+        default: e = va = vb = std::nan(""); break;  // not restated for UKS yet
+      }
+      E += f.coeff[k] * e; VA += f.coeff[k] * va; VB += f.coeff[k] * vb;
+    }
+    eps[i] = E; vrho2[2 * i] = VA; vrho2[2 * i + 1] = VB;
+  }
+}
+
 // ----------------------------------------------------------------------------------
 // collocation: gau2grid semantics (gg_collocation / gg_collocation_deriv1), host layout
 // basis_eval[mu + ipt*nbe]
@@ -598,6 +673,116 @@ void oracle_exc_vxc(int nshells_total, const int32_t* l, const int32_t* pure, co
   Acc E, N, F;
   for (int t = 0; t < ntasks; ++t) { E.add(exc_t[t]); N.add(nel_t[t]); F.add(flops_t[t]); }
   out3[0] = E.value(); out3[1] = N.value(); out3[2] = F.value();
+}
+
+
+// UKS, LDA: reference_replicated_xc_host_integrator_exc_vxc.hpp:107-601 with is_uks (Ps = P_alpha +
+// P_beta, Pz = P_alpha - P_beta): X_s = 1.0 Ps_sub B, X_z = 1.0 Pz_sub B (:387-396),
+// eval_uvvar_lda_uks (driver.cxx:166-188), polarised functional, weights (:453-457), N_EL / EXC with the
+// total density (:490-497), eval_zmat_lda_vxc_uks (driver.cxx:607-634), inc_vxc for VXCs and VXCz,
+// symmetrise both.  out3 = {EXC, N_EL, dense flops}.
+void oracle_exc_vxc_uks_lda(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                            const double* alpha, const double* coeff, const double* origin, int nbf,
+                            const double* Ps, const double* Pz, int ldp, int ntasks, const int32_t* task_npts,
+                            const int32_t* task_nshells, const int32_t* shell_lists, const double* points,
+                            const double* weights, int nkern, const int* kern, const double* kcoeff,
+                            double* VXCs, double* VXCz, double* out3) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  Func func{};
+  func.nkern = nkern; func.is_gga = 0;
+  for (int k = 0; k < nkern; ++k) { func.kern[k] = kern[k]; func.coeff[k] = kcoeff[k]; }
+  std::vector<int> first_ao(nshells_total + 1, 0);
+  for (int s = 0; s < nshells_total; ++s) first_ao[s + 1] = first_ao[s] + B.size(s);
+  std::vector<size_t> poff(ntasks + 1, 0), soff(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) {
+    poff[t + 1] = poff[t] + task_npts[t];
+    soff[t + 1] = soff[t] + task_nshells[t];
+  }
+  std::fill(VXCs, VXCs + (size_t)nbf * nbf, 0.);
+  std::fill(VXCz, VXCz + (size_t)nbf * nbf, 0.);
+  std::vector<double> exc_t(ntasks, 0.), nel_t(ntasks, 0.), flops_t(ntasks, 0.);
+  sph_table(0);  // built before the parallel region
+
+#pragma omp parallel
+  {
+    std::vector<double> ev, Xs, Xz, Zs, Zz, scr, Psub, den2, eps, vrho2;
+    std::vector<int> ao;
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; ++iT) {
+      const int npts = task_npts[iT];
+      const int nsh = task_nshells[iT];
+      const int32_t* sl = shell_lists + soff[iT];
+      const double* pts = points + 3 * poff[iT];
+      const double* w = weights + poff[iT];
+      ao.clear();
+      for (int q = 0; q < nsh; ++q)
+        for (int a = first_ao[sl[q]]; a < first_ao[sl[q] + 1]; ++a) ao.push_back(a);
+      const int nbe = (int)ao.size();
+      const size_t nn = (size_t)nbe * npts;
+      ev.resize(nn); Xs.resize(nn); Xz.resize(nn); Zs.resize(nn); Zz.resize(nn);
+      scr.resize((size_t)nbe * nbe); Psub.resize((size_t)nbe * nbe);
+      den2.resize(2 * (size_t)npts); eps.resize(npts); vrho2.resize(2 * (size_t)npts);
+      collocation(B, nsh, sl, npts, pts, nbe, false, ev.data(), nullptr, nullptr, nullptr);
+      for (int pass = 0; pass < 2; ++pass) {
+        const double* P = pass == 0 ? Ps : Pz;
+        for (int j = 0; j < nbe; ++j)
+          for (int i = 0; i < nbe; ++i) Psub[i + (size_t)j * nbe] = P[ao[i] + (size_t)ao[j] * ldp];
+        gemm_nn(nbe, npts, nbe, 1.0, Psub.data(), nbe, ev.data(), nbe, (pass == 0 ? Xs : Xz).data(), nbe);
+      }
+      for (int i = 0; i < npts; ++i) {
+        const double* bi = ev.data() + (size_t)i * nbe;
+        const double *xs = Xs.data() + (size_t)i * nbe, *xz = Xz.data() + (size_t)i * nbe;
+        double rs = 0, rz = 0;
+        for (int m = 0; m < nbe; ++m) { rs += bi[m] * xs[m]; rz += bi[m] * xz[m]; }
+        den2[2 * i] = 0.5 * (rs + rz);
+        den2[2 * i + 1] = 0.5 * (rs - rz);
+      }
+      eval_func_pol_lda(func, npts, den2.data(), eps.data(), vrho2.data());
+      Acc e_acc, n_acc;
+      for (int i = 0; i < npts; ++i) {
+        eps[i] *= w[i];
+        vrho2[2 * i] *= w[i];
+        vrho2[2 * i + 1] *= w[i];
+        const double den = den2[2 * i] + den2[2 * i + 1];
+        n_acc.add(w[i] * den);
+        e_acc.add(eps[i] * den);
+      }
+      exc_t[iT] = e_acc.value();
+      nel_t[iT] = n_acc.value();
+      for (int i = 0; i < npts; ++i) {
+        const double* bi = ev.data() + (size_t)i * nbe;
+        double *zs = Zs.data() + (size_t)i * nbe, *zz = Zz.data() + (size_t)i * nbe;
+        const double factp = 0.5 * vrho2[2 * i], factm = 0.5 * vrho2[2 * i + 1];
+        const double fs = 0.5 * (factp + factm), fz = 0.5 * (factp - factm);
+        for (int m = 0; m < nbe; ++m) { zs[m] = fs * bi[m]; zz[m] = fz * bi[m]; }
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        double* V = pass == 0 ? VXCs : VXCz;
+        syr2k_ln(nbe, npts, ev.data(), nbe, (pass == 0 ? Zs : Zz).data(), nbe, scr.data(), nbe);
+        for (int j = 0; j < nbe; ++j)
+          for (int i = j; i < nbe; ++i) {
+#pragma omp atomic
+            V[ao[i] + (size_t)ao[j] * nbf] += scr[i + (size_t)j * nbe];
+          }
+      }
+      flops_t[iT] = 8. * double(nbe) * double(nbe) * double(npts);
+    }
+  }
+  for (double* V : {VXCs, VXCz})
+    for (int j = 0; j < nbf; ++j)
+      for (int i = j + 1; i < nbf; ++i) V[j + (size_t)i * nbf] = V[i + (size_t)j * nbf];
+  Acc E, N, F;
+  for (int t = 0; t < ntasks; ++t) { E.add(exc_t[t]); N.add(nel_t[t]); F.add(flops_t[t]); }
+  out3[0] = E.value(); out3[1] = N.value(); out3[2] = F.value();
+}
+
+// polarised LDA functional on its own (unit tests: spin-unpolarised limit, finite differences)
+void oracle_functional_pol_lda(int nkern, const int* kern, const double* coeff, int npts, const double* rho2,
+                               double* eps, double* vrho2) {
+  Func f{};
+  f.nkern = nkern; f.is_gga = 0;
+  for (int k = 0; k < nkern; ++k) { f.kern[k] = kern[k]; f.coeff[k] = coeff[k]; }
+  eval_func_pol_lda(f, npts, rho2, eps, vrho2);
 }
 
 }  // extern "C"

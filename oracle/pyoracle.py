@@ -20,6 +20,7 @@ KERN = dict(SLATER_X=0, VWN5_C=1, PBE_X=2, PBE_C=3, PW92_C=5)
 FUNCTIONALS = {
     "SVWN5": (False, [("SLATER_X", 1.0), ("VWN5_C", 1.0)]),
     "LDA": (False, [("SLATER_X", 1.0)]),
+    "VWN5": (False, [("VWN5_C", 1.0)]),
     "SPW92": (False, [("SLATER_X", 1.0), ("PW92_C", 1.0)]),
     "PBE": (True, [("PBE_X", 1.0), ("PBE_C", 1.0)]),
     "PBE0": (True, [("PBE_X", 0.75), ("PBE_C", 1.0)]),
@@ -130,6 +131,38 @@ def exc_vxc(flat_basis, nbf, P, tasks, func_name, task_stride=1):
                          Pf.shape[0], len(tn), _i(tn), _i(ts), _i(sl), _d(pts), _d(w), nk, kern, coef,
                          int(gga), int(task_stride), _d(vxc), _d(out3))
     return dict(exc=out3[0], nel=out3[1], flops=out3[2], vxc=vxc)
+
+
+def exc_vxc_uks(flat_basis, nbf, Ps, Pz, tasks, func_name):
+    """UKS, LDA functionals (SVWN5, LDA, VWN5): (Ps, Pz) = (P_alpha + P_beta, P_alpha - P_beta)."""
+    l, pure, nprim, alpha, coeff, origin = flat_basis
+    gga, nk, kern, coef = _func(func_name)
+    if gga:
+        raise NotImplementedError("the UKS oracle covers LDA functionals (the reference's UKS GGA fixture is BLYP)")
+    Psf = np.asfortranarray(np.asarray(Ps, np.float64))
+    Pzf = np.asfortranarray(np.asarray(Pz, np.float64))
+    tn = np.ascontiguousarray(tasks["npts"], np.int32)
+    ts = np.ascontiguousarray(tasks["nshells"], np.int32)
+    sl = np.ascontiguousarray(tasks["shell_lists"], np.int32)
+    pts = np.ascontiguousarray(tasks["points"], np.float64)
+    w = np.ascontiguousarray(tasks["weights"], np.float64)
+    vs, vz = np.zeros((nbf, nbf), order="F"), np.zeros((nbf, nbf), order="F")
+    out3 = np.zeros(3)
+    lib().oracle_exc_vxc_uks_lda(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), nbf, _d(Psf),
+                                 _d(Pzf), Psf.shape[0], len(tn), _i(tn), _i(ts), _i(sl), _d(pts), _d(w), nk, kern,
+                                 coef, _d(vs), _d(vz), _d(out3))
+    return dict(exc=out3[0], nel=out3[1], flops=out3[2], vxc_s=vs, vxc_z=vz)
+
+
+def functional_pol_lda(func_name, rho_a, rho_b):
+    """Spin-polarised LDA: eps (per particle of rho_a + rho_b), d(rho eps)/d rho_a, d(rho eps)/d rho_b."""
+    gga, nk, kern, coef = _func(func_name)
+    assert not gga
+    r2 = np.ascontiguousarray(np.stack([rho_a, rho_b], 1).ravel(), np.float64)
+    n = len(rho_a)
+    eps, v2 = np.zeros(n), np.zeros(2 * n)
+    lib().oracle_functional_pol_lda(nk, kern, coef, n, _d(r2), _d(eps), _d(v2))
+    return eps, v2[0::2].copy(), v2[1::2].copy()
 
 
 # ---- oracle/_ref: the reference's own gau2grid, compiled from /root/reference -----------------

@@ -8,6 +8,8 @@ bench time reads /root/reference (it does not exist on the GPU box).
 Sources (all under /root/reference/tests/):
   ref_data/benzene_{svwn5,pbe0}_cc-pvdz_ufg_ssf[_robust_prune|_treutler_prune].hdf5
       consumed by tests/xc_integrator.cxx:405-426       -> benzene_*.npz
+  ref_data/cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks.hdf5
+      consumed by tests/xc_integrator.cxx:455-459 (UKS LDA)  -> cytosine_svwn5_..._uks.npz
   ref_data/water_cc-pVDZ_collocation.hdf5
       consumed by tests/collocation.cxx:45-91           -> water_collocation.npz
   ref_data/benzene_weights_ssf.hdf5
@@ -64,6 +66,16 @@ def conv_xc(name):
     o["EXC"] = f.array("/EXC")
     np.savez_compressed(f"{OUT}/{name}.npz", **o)
     print(name, "EXC", o["EXC"], "nbf", o["DENSITY"].shape)
+
+
+def conv_xc_uks(name):
+    """UKS fixtures (tests/xc_integrator.cxx:448-472): scalar and z densities / potentials."""
+    f = H5File(f"{REF}/ref_data/{name}.hdf5")
+    o = mol_basis(f)
+    for k in ("DENSITY_SCALAR", "DENSITY_Z", "VXC_SCALAR", "VXC_Z", "EXC"):
+        o[k] = f.array("/" + k)
+    np.savez_compressed(f"{OUT}/{name}.npz", **o)
+    print(name, "EXC", o["EXC"], "nbf", o["DENSITY_SCALAR"].shape)
 
 
 def conv_basis_only(name, out):
@@ -178,6 +190,7 @@ if __name__ == "__main__":
     for n in ("benzene_svwn5_cc-pvdz_ufg_ssf", "benzene_pbe0_cc-pvdz_ufg_ssf",
               "benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "benzene_svwn5_cc-pvdz_ufg_ssf_treutler_prune"):
         conv_xc(n)
+    conv_xc_uks("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks")
     conv_basis_only("benzene_m062x_def2-svp_ufg_ssf", "benzene_def2-svp_basis")
     conv_collocation()
     conv_weights()
