@@ -105,6 +105,8 @@ def lib():
         "gauxc_integrator_eval_exc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
         "gauxc_integrator_eval_exc_vxc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, _dp, C.c_int64]),
         "gauxc_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
+        "gauxc_integrator_eval_exc_vxc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
+                                                     _dp, _dp, C.c_int64, _dp, C.c_int64]),
         "gauxc_b200_nccl_get_unique_id": (None, [S, C.c_char_p]),
         "gauxc_b200_nccl_init": (None, [S, C.c_char_p, C.c_int, C.c_int]),
         "gauxc_b200_nccl_finalize": (None, [S]),
@@ -414,6 +416,17 @@ class XCIntegrator(_Obj):
         exc = C.c_double(0.)
         _call("gauxc_integrator_eval_exc_vxc_rks", self.h, m, n, _d(Pf), max(m, 1), C.byref(exc), _d(vxc), max(n, 1))
         return exc.value, vxc
+
+    def eval_exc_vxc_uks(self, Ps, Pz):
+        """UKS EXC / VXC_s / VXC_z (LDA functionals); Ps = P_alpha + P_beta, Pz = P_alpha - P_beta."""
+        Psf = np.asfortranarray(np.asarray(Ps, dtype=np.float64))
+        Pzf = np.asfortranarray(np.asarray(Pz, dtype=np.float64))
+        m, n = Psf.shape
+        vs, vz = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+        exc = C.c_double(0.)
+        _call("gauxc_integrator_eval_exc_vxc_uks", self.h, m, n, _d(Psf), max(m, 1), _d(Pzf), max(m, 1),
+              C.byref(exc), _d(vs), max(n, 1), _d(vz), max(n, 1))
+        return exc.value, vs, vz
 
     def eval_exc_vxc_raw(self, m, n, P, ldp, vxc, ldv):
         exc = C.c_double(0.)

@@ -120,14 +120,20 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
   }
 }
 
-template <bool GGA>
+// SPIN = 0: RKS (P = P_alpha, factor 2 inside).  UKS (LDA functionals) runs the kernel twice per batch:
+// SPIN = 1 with P = Ps = P_alpha + P_beta only stores rho_s per point (uks_den); SPIN = 2 with P = Pz
+// forms rho_z, rho_+- = (rho_s +- rho_z)/2, evaluates the polarised functional and writes BOTH
+// Z_s (matrix 1) and Z_z (matrix 2) -- eval_uvvar_lda_uks / eval_zmat_lda_vxc_uks of the reference host
+// driver (reference_local_host_work_driver.cxx:166-188, 607-634; X factor 1.0, driver :387-396).
+template <bool GGA, int SPIN>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
                            const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
                            double* __restrict__ ws,
                            const double* __restrict__ P, int ldp, FunctionalDesc func,
                            double* __restrict__ exc_part, double* __restrict__ nel_part,
-                           int part_off) {
+                           int part_off, double* __restrict__ uks_den) {
+  static_assert(SPIN == 0 || !GGA, "UKS is implemented for LDA functionals");
   // no pointer arithmetic on the base: the compiler must see shared-space accesses (LDS/STS, not
   // generic LD/ST) in the fragment loads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -384,7 +390,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
 #pragma unroll
       for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
         const double v = (S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p]);
-        S.den[qn][p] = ((qn == 0 && GGA) ? 2. : 4.) * v;
+        S.den[qn][p] = (SPIN != 0 ? 2. : (qn == 0 && GGA) ? 2. : 4.) * v;  // UKS: X factor 1.0
       }
       mbar_arrive(&S.denfull);
       dph ^= 1;
@@ -407,6 +413,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       const size_t ms = (size_t)nbp * TP;
       const double* __restrict__ Bt = ws + tile.ws_off + cofs;
       double* __restrict__ Z = ws + tile.ws_off + (GGA ? 4 : 1) * ms + cofs;
+      double* __restrict__ Zz = Z + ms;  // UKS: Z_z follows Z_s
 
       mbar_wait(&S.denfull, dph);
       const double rho = S.den[0][p];
@@ -416,8 +423,22 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       dph ^= 1;
 
       const bool ok = p < tile.npts;
+      if (SPIN == 1) {  // UKS pass over Ps: keep rho_s for the pass over Pz, nothing else to do
+        if (ok) uks_den[tile.pt_off + p] = rho;
+        continue;
+      }
       double a = 0., fx = 0., fy = 0., fz = 0., e_loc = 0., n_loc = 0.;
-      if (ok) {
+      if (ok && SPIN == 2) {
+        const double w = pv.w[tile.pt_off + p];
+        const double rho_s = uks_den[tile.pt_off + p], rho_z = rho;
+        const XcOutPol xc = eval_functional_pol_lda(func, 0.5 * (rho_s + rho_z), 0.5 * (rho_s - rho_z));
+        const double eps = xc.eps * w;  // host driver :453-457
+        const double factp = 0.5 * (xc.va * w), factm = 0.5 * (xc.vb * w);
+        a = 0.5 * (factp + factm);   // Z_s = a B
+        fx = 0.5 * (factp - factm);  // Z_z = fx B
+        e_loc = eps * rho_s;         // :490-497, total density
+        n_loc = w * rho_s;
+      } else if (ok) {
         const double w = pv.w[tile.pt_off + p];
         const double sigma = GGA ? dx * dx + dy * dy + dz * dz : 0.;
         const XcOut xc = eval_functional(func, rho, sigma);
@@ -433,7 +454,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       }
       double(*fac)[TP] = S.fac[it & 1];
       fac[0][p] = a;
-      if (GGA) { fac[1][p] = fx; fac[2][p] = fy; fac[3][p] = fz; }
+      if (GGA || SPIN == 2) fac[1][p] = fx;
+      if (GGA) { fac[2][p] = fy; fac[3][p] = fz; }
       // fixed-order tile partials of EXC / N_EL
       {
         double e = e_loc, nn = n_loc;
@@ -454,7 +476,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       // last rows first: they were streamed most recently by the density warps
       double a4[4], fx4[4], fy4[4], fz4[4];
       lds4(a4, &fac[0][p4]);
-      if (GGA) { lds4(fx4, &fac[1][p4]); lds4(fy4, &fac[2][p4]); lds4(fz4, &fac[3][p4]); }
+      if (GGA || SPIN == 2) lds4(fx4, &fac[1][p4]);
+      if (GGA) { lds4(fy4, &fac[2][p4]); lds4(fz4, &fac[3][p4]); }
       int mu = ((nbe - 1 - zw) & ~3) + zw;  // largest row <= nbe-1 with (row & 3) == zw
       if (p4 >= tile_width(tile.npts)) mu = -1;  // columns beyond the tile width do not exist
       for (; mu - 4 >= 0; mu -= 8) {
@@ -482,6 +505,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
             }
           }
           stg_stream(Z + (size_t)(mu - 4 * u) * TP, z, pol_drop);
+          if (SPIN == 2) {  // Z_z = fz B from the same row of B
+            double zz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zz[j] = fx4[j] * b0[u][j];
+            stg_stream(Zz + (size_t)(mu - 4 * u) * TP, zz, pol_drop);
+          }
         }
       }
       if (mu >= 0) {
@@ -503,6 +532,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
           }
         }
         stg_stream(Z + (size_t)mu * TP, z, pol_drop);
+        if (SPIN == 2) {
+          double zz[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zz[j] = fx4[j] * b0[j];
+          stg_stream(Zz + (size_t)mu * TP, zz, pol_drop);
+        }
       }
     }
   } else {
@@ -589,23 +624,33 @@ int fused_threads() { return FUSED_THREADS; }
 void launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                   int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
-                  cudaStream_t s) {
+                  cudaStream_t s, int spin, double* uks_den) {
   if (ncta <= 0 || ntiles <= 0) return;
   ncta = ncta < ntiles ? ncta : ntiles;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)FUSED_SMEM_BYTES);
-    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)FUSED_SMEM_BYTES);
+    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)FUSED_SMEM_BYTES);
+    cudaFuncSetAttribute(fused_xmat_den_zmat_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)FUSED_SMEM_BYTES);
     attr_set = true;
   }
-  if (func.is_gga)
-    fused_xmat_den_zmat_kernel<true><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
-        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off);
+  if (spin == 1)
+    fused_xmat_den_zmat_kernel<false, 1><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off, uks_den);
+  else if (spin == 2)
+    fused_xmat_den_zmat_kernel<false, 2><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off, uks_den);
+  else if (func.is_gga)
+    fused_xmat_den_zmat_kernel<true, 0><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off, nullptr);
   else
-    fused_xmat_den_zmat_kernel<false><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
-        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off);
+    fused_xmat_den_zmat_kernel<false, 0><<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(
+        tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func, exc_part, nel_part, part_off, nullptr);
 }
 
 }  // namespace gxb

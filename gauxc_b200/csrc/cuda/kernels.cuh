@@ -21,13 +21,15 @@ void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, do
 void launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                   int* counter, int ncta, double* ws, const double* P, int ldp,
                   FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
-                  cudaStream_t s);
+                  cudaStream_t s, int spin = 0, double* uks_den = nullptr);
 
 // K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe, scatter-added (lower triangle) into VXC.
-//      tmapV: box of 128 rows x 16 points over the workspace.
+//      tmapV: box of 128 rows x 16 points over the workspace; Z is matrix `zmat` of the `nmat` matrices of
+//      a tile (RKS: LDA 1 of 2, GGA 4 of 5; UKS LDA: Z_s 1 and Z_z 2 of 3); sym: M = B^T Z symmetric (LDA).
 //      ncta persistent CTAs pull items [0, nitems) from *counter (zeroed by the caller).
 void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
-                int nitems, int* counter, int ncta, bool gga, double* VXC, int ldv, cudaStream_t s);
+                int nitems, int* counter, int ncta, int zmat, int nmat, bool sym, double* VXC, int ldv,
+                cudaStream_t s);
 
 // finalisation
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

@@ -71,8 +71,8 @@ __device__ __forceinline__ void vxc_step(double (&acc)[4][4][2], const double* _
 
 __global__ void __launch_bounds__(V_THREADS, 1)
 vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile* __restrict__ tiles,
-           const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int sym,
-           double* __restrict__ VXC, int ldv) {
+           const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int nmat,
+           int sym, double* __restrict__ VXC, int ldv) {
   // no pointer arithmetic on the base: the compiler must see shared-space accesses (LDS/STS, not
   // generic LD/ST) in the fragment loads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,7 +101,7 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const DevTile
     tma_prefetch_desc(&tmapV);
     int s = 0;
     uint32_t ph = 0;
-    const int tile_rows = zmat + 1;  // matrices per tile: the row stride of a tile is tile_rows * pad16(nbe)
+    const int tile_rows = nmat;  // matrices per tile: the row stride of a tile is nmat * pad16(nbe)
     // the item record is self-contained (no dependent task / tile loads) and fetched ONE ITEM AHEAD,
     // so the queue pop + metadata latency hides behind the TMA issue loop of the current item
     auto fetch = [&](int idx) {
@@ -339,7 +339,8 @@ void launch_sym_half(const double* P, int ldp, double* out, int nbf, cudaStream_
 }
 
 void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* tiles, const VxcItem* items,
-                int nitems, int* counter, int ncta, bool gga, double* VXC, int ldv, cudaStream_t s) {
+                int nitems, int* counter, int ncta, int zmat, int nmat, bool sym, double* VXC, int ldv,
+                cudaStream_t s) {
   if (nitems <= 0 || ncta <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -347,8 +348,8 @@ void launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const DevTile* til
     attr_set = true;
   }
   ncta = ncta < nitems ? ncta : nitems;
-  vxc_kernel<<<ncta, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapV, pv, tiles, items, nitems, counter,
-                                                      gga ? 4 : 1, gga ? 0 : 1, VXC, ldv);
+  vxc_kernel<<<ncta, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapV, pv, tiles, items, nitems, counter, zmat, nmat,
+                                                      sym ? 1 : 0, VXC, ldv);
 }
 
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

@@ -172,4 +172,77 @@ GXB_HD XcOut eval_functional(const FunctionalDesc& f, double rho, double sigma) 
   return t;
 }
 
+// ---- spin-polarised LDA (UKS) -----------------------------------------------------------------
+// Inputs rho_+ / rho_- (eval_uvvar_lda_uks, reference_local_host_work_driver.cxx:166-188); eps is the
+// energy per particle of the total density, va / vb = d(rho eps)/d rho_+-.  Same published forms as the
+// oracle (exact spin scaling of Slater exchange; libxc lda_c_vwn_rpa: para-/ferromagnetic RPA fits
+// interpolated with f(zeta)), pinned by the reference's cytosine SVWN5 UKS fixture.
+struct XcOutPol {
+  double eps, va, vb;
+};
+
+GXB_HD XcOutPol slater_x_pol(double ra, double rb) {
+  XcOutPol o{0., 0., 0.};
+  const double rho = ra + rb;
+  if (rho <= 1e-24) return o;
+  const double cx = -0.73855876638202240588;  // -(3/4)(3/pi)^(1/3)
+  double ea = 0., eb = 0.;
+  if (ra > 0.) { const double t = cbrt(2. * ra); ea = cx * t * ra; o.va = (4. / 3.) * cx * t; }
+  if (rb > 0.) { const double t = cbrt(2. * rb); eb = cx * t * rb; o.vb = (4. / 3.) * cx * t; }
+  o.eps = (ea + eb) / rho;
+  return o;
+}
+
+GXB_HD void vwn_fit(double A, double b, double c, double x0, double rs, double& e, double& de_drs) {
+  const double Q = sqrt(4. * c - b * b);
+  const double X0 = x0 * x0 + b * x0 + c;
+  const double x = sqrt(rs);
+  const double X = rs + b * x + c;
+  const double tx = 2. * x + b;
+  const double at = atan(Q / tx);
+  const double xm = x - x0;
+  const double k0 = b * x0 / X0;
+  e = A * (log(rs / X) + (2. * b / Q) * at - k0 * (log(xm * xm / X) + (2. * (b + 2. * x0) / Q) * at));
+  const double den = tx * tx + Q * Q;
+  const double de_dx = A * (2. / x - tx / X - 4. * b / den - k0 * (2. / xm - tx / X - 4. * (b + 2. * x0) / den));
+  de_drs = de_dx / (2. * x);
+}
+
+GXB_HD XcOutPol vwn5_c_pol(double ra, double rb) {
+  XcOutPol o{0., 0., 0.};
+  const double rho = ra + rb;
+  if (rho <= 1e-24) return o;
+  const double rs = cbrt(0.75 / (M_PI * rho));
+  double z = (ra - rb) / rho;
+  z = fmin(1., fmax(-1., z));
+  double eP, dP, eF, dF;
+  vwn_fit(0.0310907, 13.0720, 42.7198, -0.409286, rs, eP, dP);
+  vwn_fit(0.01554535, 20.1231, 101.578, -0.743294, rs, eF, dF);
+  const double den = 2. * cbrt(2.) - 2.;
+  const double op = cbrt(1. + z), om = cbrt(1. - z);
+  const double fz = (op * (1. + z) + om * (1. - z) - 2.) / den;
+  const double dfz = (4. / 3.) * (op - om) / den;
+  const double e = eP + (eF - eP) * fz;
+  const double common = e - (rs / 3.) * (dP + (dF - dP) * fz);
+  const double de_dz = (eF - eP) * dfz;
+  o.eps = e;
+  o.va = common + (1. - z) * de_dz;
+  o.vb = common - (1. + z) * de_dz;
+  return o;
+}
+
+// LDA kernels only (the reference's UKS GGA fixtures are BLYP, not restated here)
+GXB_HD XcOutPol eval_functional_pol_lda(const FunctionalDesc& f, double ra, double rb) {
+  XcOutPol t{0., 0., 0.};
+  for (int k = 0; k < f.nkern; ++k) {
+    XcOutPol o{0., 0., 0.};
+    if (f.kern[k] == K_SLATER_X) o = slater_x_pol(ra, rb);
+    else if (f.kern[k] == K_VWN5_C) o = vwn5_c_pol(ra, rb);
+    t.eps += f.coeff[k] * o.eps;
+    t.va += f.coeff[k] * o.va;
+    t.vb += f.coeff[k] * o.vb;
+  }
+  return t;
+}
+
 }  // namespace gxb

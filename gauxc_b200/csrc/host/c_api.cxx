@@ -400,12 +400,12 @@ void gauxc_integrator_eval_exc_vxc_rks(GauXCStatus* status, const GauXCIntegrato
   INTG(integrator)->eval_exc_vxc(m, n, P, ldp, vxc, vxc_ld, exc);
   C_CATCH(status)
 }
-void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrator, const int64_t,
-                                       const int64_t, const double*, const int64_t, const double*,
-                                       const int64_t, double*, double*, const int64_t, double*,
-                                       const int64_t) {
+void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                       const int64_t n, const double* Ps, const int64_t ldps, const double* Pz,
+                                       const int64_t ldpz, double* exc, double* vxc_s, const int64_t ldvs,
+                                       double* vxc_z, const int64_t ldvz) {
   C_TRY(status)
-  GAUXC_GENERIC_EXCEPTION("UKS NYI in B200 path");
+  INTG(integrator)->eval_exc_vxc_uks(m, n, Ps, ldps, Pz, ldpz, vxc_s, ldvs, vxc_z, ldvz, exc);
   C_CATCH(status)
 }
 void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator, const int64_t,

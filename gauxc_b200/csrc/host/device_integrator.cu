@@ -395,7 +395,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
-  sc->d_counters.alloc(std::max<size_t>(1, 2 * sc->batches.size()));  // fused + vxc queue heads
+  sc->d_counters.alloc(std::max<size_t>(1, 4 * sc->batches.size()));  // queue heads: fused, vxc (UKS: two each)
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
 }
@@ -458,7 +458,12 @@ XCFunctional functional_from_string(const std::string& spec_in, bool polarized) 
   else if (spec == "PBE") set(true, {{K_PBE_X, 1.}, {K_PBE_C, 1.}});
   else if (spec == "PBE0") { set(true, {{K_PBE_X, 0.75}, {K_PBE_C, 1.}}); f.hyb_exx = 0.25; }
   else GAUXC_GENERIC_EXCEPTION("Functional NYI in B200 path: " + spec_in);
-  if (polarized) GAUXC_GENERIC_EXCEPTION("Polarized (UKS/GKS) functionals NYI in B200 path");
+  if (polarized) {
+    // UKS is implemented for the LDA kernels with a restated spin-polarised form (Slater, VWN5)
+    bool ok = !f.desc.is_gga;
+    for (int k = 0; k < f.desc.nkern; ++k) ok = ok && (f.desc.kern[k] == K_SLATER_X || f.desc.kern[k] == K_VWN5_C);
+    if (!ok) GAUXC_GENERIC_EXCEPTION("Polarized (UKS) Functional NYI in B200 path: " + spec_in);
+  }
   return f;
 }
 
@@ -604,6 +609,7 @@ struct XCIntegrator::Impl {
   cudaEvent_t e_p_ready{};
   bool p_pending = false;  // set by the host-buffer entry points: wait for e_p_ready before P is read
   DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
+  DevBuf<double> dPz, dPtri_z, dVXCz, d_uks_den;  // UKS: z density / potential, rho_s per point
   gxb::TmapSet tmapA{};  // TMA views of d_ws: 16 rows x (32..128) points
   CUtensorMap tmapV{};   // 128 rows x 16 points
   int ncta = 0;
@@ -676,6 +682,7 @@ static size_t workspace_bytes(const LoadBalancer& lb) {
 
 void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d_out2, bool do_vxc) {
   auto& I = *impl_;
+  if (func_->polarized) GAUXC_GENERIC_EXCEPTION("RKS Evaluation Requires An Unpolarized Functional");
   if (!lb_->state().modified_weights_are_stored)
     GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
   {
@@ -772,7 +779,7 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     launches += 2;
     if (do_vxc) {
       gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                      sc.d_counters.p + sc.batches.size() + ib, sc.ncta, gga, dVXC, nbf, s);
+                      sc.d_counters.p + sc.batches.size() + ib, sc.ncta, gga ? 4 : 1, nmat, !gga, dVXC, nbf, s);
       ++launches;
     }
     if (ev) CUDA_CHECK(cudaEventRecord(ev[4], s));
@@ -874,6 +881,125 @@ void XCIntegrator::eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, 
   eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, false);
   CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  *EXC = I.h_out2[0];
+  stats_.n_el = I.h_out2[1];
+}
+
+// UKS, LDA functionals: Ps = P_alpha + P_beta, Pz = P_alpha - P_beta
+// (reference_replicated_xc_host_integrator_exc_vxc.hpp:107-601 with is_uks; device counterpart
+// incore_replicated_xc_device_integrator_exc_vxc.hpp:46-386).  Per batch: collocation, the fused kernel
+// over Ps (rho_s per point), the fused kernel over Pz (rho_z -> rho_+- -> polarised functional -> Z_s,
+// Z_z), the VXC rank update twice.
+void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz,
+                                    int64_t ldpz, double* VXCs, int64_t ldvxcs, double* VXCz,
+                                    int64_t ldvxcz, double* EXC) {
+  check_dims(*lb_, m, n, ldps, ldvxcs, true);
+  check_dims(*lb_, m, n, ldpz, ldvxcz, true);
+  if (!lb_->state().modified_weights_are_stored) GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
+  if (!func_->polarized) GAUXC_GENERIC_EXCEPTION("UKS Evaluation Requires A Polarized Functional");
+  if (func_->is_gga()) GAUXC_GENERIC_EXCEPTION("UKS GGA NYI in B200 path");
+  auto& I = *impl_;
+  cudaStream_t s = I.stream;
+  const size_t nbf = (size_t)m;
+  const size_t nn = nbf * nbf;
+  if (I.dP.n != nn) { I.dP.alloc(nn); I.dVXC.alloc(nn); I.d_out2.alloc(2); }
+  if (I.dPz.n != nn) { I.dPz.alloc(nn); I.dVXCz.alloc(nn); I.dPtri_z.alloc(nn); }
+  if (I.dPtri.n != nn) I.dPtri.alloc(nn);
+  CUDA_CHECK(cudaEventRecord(I.e_begin, s));
+  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), Ps, ldps * sizeof(double), nbf * sizeof(double),
+                               nbf, cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpy2DAsync(I.dPz.p, nbf * sizeof(double), Pz, ldpz * sizeof(double), nbf * sizeof(double),
+                               nbf, cudaMemcpyHostToDevice, s));
+  {
+    auto np = get_device_plan(*lb_);
+    if (np != I.plan) { I.plan = np; I.sched.reset(); }
+  }
+  auto& plan = *I.plan;
+  const int nmat = 3;  // B, Z_s, Z_z
+  if (!I.sched || I.sched_nmat != nmat) {
+    auto it = plan.schedules.find(nmat);
+    if (it == plan.schedules.end()) {
+      const size_t wsb = workspace_bytes(*lb_);
+      if (!I.ncta) {
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&I.ncta, cudaDevAttrMultiProcessorCount, dev));
+      }
+      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), 16, I.ncta, true);
+      it = plan.schedules.find(nmat);
+    }
+    I.sched = it->second;
+    I.sched_nmat = nmat;
+    I.d_ws.alloc(I.sched->ws_doubles);
+    if (I.sched->ws_doubles) {
+      CUDA_CHECK(cudaMemsetAsync(I.d_ws.p, 0, I.sched->ws_doubles * sizeof(double), s));
+      for (int w = 0; w < 4; ++w)
+        I.tmapA.m[w] = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 32 * (w + 1), 16);
+      I.tmapV = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 16, gxb::VXC_BLK);
+    }
+    I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
+    I.d_nel_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
+  }
+  if (I.d_uks_den.n < plan.npts) I.d_uks_den.alloc(std::max<size_t>(1, plan.npts));
+  auto& sc = *I.sched;
+  const gxb::PlanView pv = plan.view();
+  const int inbf = plan.nbf;
+  const size_t nb = sc.batches.size();
+
+  CUDA_CHECK(cudaMemsetAsync(I.dVXC.p, 0, sizeof(double) * nn, s));
+  CUDA_CHECK(cudaMemsetAsync(I.dVXCz.p, 0, sizeof(double) * nn, s));
+  CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
+  CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
+  gxb::launch_sym_half(I.dP.p, inbf, I.dPtri.p, inbf, s);
+  gxb::launch_sym_half(I.dPz.p, inbf, I.dPtri_z.p, inbf, s);
+  long long launches = 2;
+  size_t ib = 0;
+  for (auto& b : sc.batches) {
+    const int nt = b.tile_end - b.tile_begin;
+    const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
+    gxb::launch_collocation(pv, tl, nt, I.d_ws.p, false, s);
+    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, I.dPtri.p, inbf, func_->desc,
+                      I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 1, I.d_uks_den.p);
+    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + nb + ib, sc.ncta, I.d_ws.p, I.dPtri_z.p, inbf,
+                      func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 2, I.d_uks_den.p);
+    gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                    sc.d_counters.p + 2 * nb + ib, sc.ncta, 1, nmat, true, I.dVXC.p, inbf, s);
+    gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                    sc.d_counters.p + 3 * nb + ib, sc.ncta, 2, nmat, true, I.dVXCz.p, inbf, s);
+    launches += 5;
+    ++ib;
+  }
+  gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), I.d_out2.p, s);
+  gxb::launch_symmetrize(I.dVXC.p, inbf, inbf, s);
+  gxb::launch_symmetrize(I.dVXCz.p, inbf, inbf, s);
+  launches += 3;
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(I.e_lw1, s));
+  if (red_->comm_size() > 1) {
+    red_->allreduce_inplace(I.dVXC.p, nn, ReductionOp::Sum, s);
+    red_->allreduce_inplace(I.dVXCz.p, nn, ReductionOp::Sum, s);
+    red_->allreduce_inplace(I.d_out2.p, 2, ReductionOp::Sum, s);
+  }
+  CUDA_CHECK(cudaMemcpy2DAsync(VXCs, ldvxcs * sizeof(double), I.dVXC.p, nbf * sizeof(double), nbf * sizeof(double),
+                               nbf, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpy2DAsync(VXCz, ldvxcz * sizeof(double), I.dVXCz.p, nbf * sizeof(double), nbf * sizeof(double),
+                               nbf, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaEventRecord(I.e_end, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, I.e_lw0, I.e_lw1);
+  stats_.last_local_work_ms = ms;
+  cudaEventElapsedTime(&ms, I.e_begin, I.e_end);
+  stats_.last_total_ms = ms;
+  timer_.add("XCIntegrator.LocalWork_EXC_VXC_UKS", stats_.last_local_work_ms);
+  stats_.kernel_launches = launches;
+  stats_.f_dense = 2. * plan.f_dense;
+  stats_.sum_nbe_npts = plan.sum_nbe_npts;
+  stats_.npts = (long long)plan.npts;
+  stats_.ntiles = (long long)sc.tiles.size();
+  stats_.nbatches = (long long)sc.batches.size();
+  stats_.nitems = (long long)sc.items.size();
   *EXC = I.h_out2[0];
   stats_.n_el = I.h_out2[1];
 }

@@ -106,6 +106,9 @@ public:
   // RKS: P = P_alpha; VXC fully overwritten (column-major, ldvxc >= nbf)
   void eval_exc_vxc(int64_t m, int64_t n, const double* P, int64_t ldp, double* VXC,
                     int64_t ldvxc, double* EXC);
+  // UKS (LDA functionals): Ps = P_alpha + P_beta, Pz = P_alpha - P_beta; VXCs / VXCz fully overwritten
+  void eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
+                        double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC);
   void eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC);
   void integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL);
   // device-resident variant: dP (nbf x nbf, ld nbf) and dVXC live in HBM, out2 = {EXC, N_EL}

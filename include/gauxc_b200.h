@@ -216,8 +216,9 @@ void gauxc_integrator_eval_exc_vxc_rks(GauXCStatus* status, const GauXCIntegrato
                                        const int64_t m, const int64_t n, const double* density_matrix,
                                        const int64_t ldp, double* exc, double* vxc_matrix,
                                        const int64_t vxc_ld);
-/* UKS/GKS, gradients, EXX, FXC: declared for link compatibility, return status code 1 "NYI"
- * (out of scope). */
+/* UKS: implemented for LDA functionals built with polarized = true (SVWN5, LDA/SLATER, VWN5);
+ * density_matrix_s = P_alpha + P_beta, density_matrix_z = P_alpha - P_beta; GGA -> status 1 "NYI".
+ * Gradients: declared for link compatibility, status code 1 "NYI" (SURVEY.md section 8f). */
 void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrator integrator,
                                        const int64_t m, const int64_t n, const double* density_matrix_s,
                                        const int64_t ldp_s, const double* density_matrix_z,

@@ -423,6 +423,7 @@ public:
   using matrix_type = MatrixType;
   using value_type = typename MatrixType::value_type;
   using exc_vxc_type_rks = std::tuple<value_type, matrix_type>;
+  using exc_vxc_type_uks = std::tuple<value_type, matrix_type, matrix_type>;
 
 private:
   std::shared_ptr<GauXCIntegrator> h_;
@@ -441,6 +442,18 @@ public:
                                       &EXC, VXC.data(), (int64_t)VXC.rows());
     g.check();
     return std::make_tuple(EXC, std::move(VXC));
+  }
+  // UKS (include/gauxc/xc_integrator.hpp: eval_exc_vxc(Ps, Pz)): Ps = P_alpha + P_beta, Pz = P_alpha - P_beta;
+  // LDA functionals constructed with polarized = true
+  exc_vxc_type_uks eval_exc_vxc(const MatrixType& Ps, const MatrixType& Pz) {
+    matrix_type VXCs(Ps.rows(), Ps.cols()), VXCz(Pz.rows(), Pz.cols());
+    value_type EXC = 0;
+    detail::StatusGuard g;
+    gauxc_integrator_eval_exc_vxc_uks(&g.st, *h_, (int64_t)Ps.rows(), (int64_t)Ps.cols(), Ps.data(),
+                                      (int64_t)Ps.rows(), Pz.data(), (int64_t)Pz.rows(), &EXC, VXCs.data(),
+                                      (int64_t)VXCs.rows(), VXCz.data(), (int64_t)VXCz.rows());
+    g.check();
+    return std::make_tuple(EXC, std::move(VXCs), std::move(VXCz));
   }
   value_type eval_exc(const MatrixType& P) {
     value_type EXC = 0;

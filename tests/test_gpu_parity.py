@@ -258,6 +258,45 @@ def test_lda_triangular_density_matches_host_for_nonsymmetric_P(orc):
     assert abs(exc - ref["exc"]) <= TOL and np.abs(vxc - ref["vxc"]).max() <= TOL
 
 
+def test_uks_lda_golden_and_oracle(orc):
+    """UKS SVWN5 on the reference's cytosine fixture (tests/xc_integrator.cxx:455-459): Device result
+    against the oracle's UKS path on the same tasks (1e-10) and against the golden VXC_s / VXC_z with
+    the reference's own criterion |VXC - ref|_F / nbf < 1e-10; spin-unpolarised limit against RKS."""
+    d = systems.golden("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks")
+    atoms = [(int(Z), *xyz) for Z, xyz in zip(d["mol_Z"], d["mol_xyz"])]
+    shells = []
+    for i in range(len(d["sh_l"])):
+        n = int(d["sh_nprim"][i])
+        shells.append(dict(l=int(d["sh_l"][i]), pure=bool(d["sh_pure"][i]), exps=list(d["sh_alpha"][i, :n]),
+                           coefs=list(d["sh_coeff"][i, :n]), origin=tuple(d["sh_O"][i]), tol=np.finfo(float).eps))
+    _, basis, lb = make_lb(atoms, shells, "UltraFineGrid", "Robust", normalize=False, device=True)
+    gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(lb)
+    tasks = lb.export_tasks()
+    nbf = basis.nbf()
+    Ps, Pz = d["DENSITY_SCALAR"], d["DENSITY_Z"]
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional("SVWN5", polarized=True), lb)
+    exc, vs, vz = integ.eval_exc_vxc_uks(Ps, Pz)
+    ref = orc.exc_vxc_uks(basis.flat(), nbf, Ps, Pz, tasks, "SVWN5")
+    assert abs(exc - ref["exc"]) <= TOL
+    assert np.abs(vs - ref["vxc_s"]).max() <= TOL and np.abs(vz - ref["vxc_z"]).max() <= TOL
+    assert abs(integ.stats()["n_el"] - ref["nel"]) <= TOL
+    assert np.array_equal(vs, vs.T) and np.array_equal(vz, vz.T)
+    assert np.linalg.norm(vs - d["VXC_SCALAR"]) / nbf < 1e-10 and np.linalg.norm(vz - d["VXC_Z"]) / nbf < 1e-10
+    assert abs(exc - float(d["EXC"][0])) < 5e-9
+    # Pz = 0: UKS(Ps) == RKS(P_alpha = Ps / 2), VXC_z == 0
+    exc0, vs0, vz0 = integ.eval_exc_vxc_uks(Ps, np.zeros_like(Pz))
+    rks = gx.XCIntegratorFactory("Device").get_instance(gx.Functional("SVWN5"), lb)
+    exc_r, vxc_r = rks.eval_exc_vxc(0.5 * Ps)
+    assert abs(exc0 - exc_r) <= 1e-11 and np.abs(vs0 - vxc_r).max() <= 1e-11 and np.abs(vz0).max() <= 1e-13
+    # entry-point contracts
+    with pytest.raises(gx.GauXCError, match="Requires A Polarized Functional"):
+        rks.eval_exc_vxc_uks(Ps, Pz)
+    with pytest.raises(gx.GauXCError, match="Requires An Unpolarized Functional"):
+        integ.eval_exc_vxc(Ps)
+    with pytest.raises(gx.GauXCError, match="NYI"):
+        gx.Functional("PBE", polarized=True)
+
+
 def test_empty_task_list_gives_zero():
     atoms = systems.geometry("water")
     shells = systems.make_basis_shells(atoms, "cc-pvdz")
