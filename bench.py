@@ -159,8 +159,10 @@ def run_reference(args):
     vals = []
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
     base = None
+    # all host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its workers)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     for it in range(args.warmup + args.steps):
-        base = oracle_sample(s, tasks, per_step)
+        base = oracle_sample(s, tasks, per_step, threads=ncores)
         if it >= args.warmup:
             vals.append(base)
     v = float(np.mean([b["value"] for b in vals]))
@@ -187,14 +189,17 @@ def workload_config(s, ngpu, l2note):
 
 def main():
     args = parse()
+    # torchrun pins OMP_NUM_THREADS=1; the host-side setup (grid, screening, task merge -- outside the
+    # timed region) and the CPU reference arm are OpenMP code: give every working rank its share of the
+    # host cores instead (the reference arm runs on rank 0 alone, so it takes all of them)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if world_env > 1:
+        share = ncores if args.impl == "reference" else max(1, ncores // world_env)
+        os.environ["OMP_NUM_THREADS"] = str(share)
     if args.impl == "reference":
         run_reference(args)
         return
-    # torchrun pins OMP_NUM_THREADS=1; the host-side setup (grid, screening, task merge -- outside the
-    # timed region) is OpenMP code, so give every rank its share of the host cores instead
-    world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    if world_env > 1:
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world_env))
 
     import torch
     import torch.distributed as dist
