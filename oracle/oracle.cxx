@@ -194,7 +194,7 @@ void f_pbe_c(double rho, double sigma, double& e, double& v, double& vs) {
   vs = rho * dH_dt2 * t2 / sigma;
 }
 
-enum { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5 };
+enum { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5, K_B88_X = 6, K_LYP_C = 7 };
 
 struct Func {
   int nkern, is_gga;
@@ -294,6 +294,100 @@ void eval_func_pol_lda(const Func& f, int npts, const double* rho2, double* eps,
       E += f.coeff[k] * e; VA += f.coeff[k] * va; VB += f.coeff[k] * vb;
     }
     eps[i] = E; vrho2[2 * i] = VA; vrho2[2 * i + 1] = VB;
+  }
+}
+
+// ---- spin-polarised GGA by forward-mode differentiation (UKS GGA) ---------------
+// The oracle only needs to be right, not fast: the energy density E(rho_a, rho_b, sigma_aa, sigma_ab,
+// sigma_bb) of the published functional is written once on a 5-partial dual number and the
+// derivatives libxc / ExchCXX return (vrho[2], vsigma[3]) fall out.  B88 exchange (Becke 1988) and
+// LYP correlation (Miehlich et al. 1989 form) = the reference's UKS GGA fixture
+// cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks (tests/xc_integrator.cxx:468-472).
+struct D5 {
+  double v;
+  double d[5];
+  D5(double x = 0.) : v(x) { for (double& q : d) q = 0.; }
+  static D5 var(double x, int k) { D5 r(x); r.d[k] = 1.; return r; }
+};
+inline D5 lift(const D5& a, double f, double fp) {  // f(a), f'(a)
+  D5 r(f);
+  for (int k = 0; k < 5; ++k) r.d[k] = fp * a.d[k];
+  return r;
+}
+inline D5 operator+(const D5& a, const D5& b) { D5 r(a.v + b.v); for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] + b.d[k]; return r; }
+inline D5 operator-(const D5& a, const D5& b) { D5 r(a.v - b.v); for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] - b.d[k]; return r; }
+inline D5 operator-(const D5& a) { D5 r(-a.v); for (int k = 0; k < 5; ++k) r.d[k] = -a.d[k]; return r; }
+inline D5 operator*(const D5& a, const D5& b) { D5 r(a.v * b.v); for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k]; return r; }
+inline D5 operator/(const D5& a, const D5& b) { D5 r(a.v / b.v); for (int k = 0; k < 5; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) / b.v; return r; }
+inline D5 dpow(const D5& a, double p) { return lift(a, std::pow(a.v, p), p * std::pow(a.v, p - 1.)); }
+inline D5 dexp(const D5& a) { const double e = std::exp(a.v); return lift(a, e, e); }
+inline D5 dsqrt(const D5& a) { const double q = std::sqrt(a.v); return lift(a, q, 0.5 / q); }
+inline D5 dasinh(const D5& a) { return lift(a, std::asinh(a.v), 1. / std::sqrt(1. + a.v * a.v)); }
+
+// E_x^{B88} = sum_sigma -rho_s^{4/3} [ C + beta x^2 / (1 + 6 beta x asinh x) ],  x = |grad rho_s| / rho_s^{4/3}
+D5 b88_energy(const D5& ra, const D5& rb, const D5& saa, const D5& sbb) {
+  const double beta = 0.0042, C = 1.5 * std::cbrt(3. / (4. * PI));
+  auto spin = [&](const D5& r, const D5& s) {
+    if (r.v <= 1e-20) return D5(0.);
+    const D5 r43 = dpow(r, 4. / 3.);
+    if (s.v <= 1e-40) return -(r43 * D5(C));
+    const D5 x = dsqrt(s) / r43;
+    return -(r43 * (D5(C) + D5(beta) * x * x / (D5(1.) + D5(6. * beta) * x * dasinh(x))));
+  };
+  return spin(ra, saa) + spin(rb, sbb);
+}
+
+// LYP, Miehlich-Savin-Stoll-Preuss closed form (Chem. Phys. Lett. 157, 200 (1989), eq. 2)
+D5 lyp_energy(const D5& ra, const D5& rb, const D5& saa, const D5& sab, const D5& sbb) {
+  const double a = 0.04918, b = 0.132, c = 0.2533, d = 0.349;
+  const double CF = 0.3 * std::pow(3. * PI * PI, 2. / 3.);
+  const D5 rho = ra + rb;
+  if (rho.v <= 1e-20) return D5(0.);
+  const D5 rm13 = dpow(rho, -1. / 3.);
+  const D5 den = D5(1.) + D5(d) * rm13;
+  const D5 omega = dexp(-(D5(c) * rm13)) / den * dpow(rho, -11. / 3.);
+  const D5 delta = D5(c) * rm13 + D5(d) * rm13 / den;
+  const D5 sig = saa + D5(2.) * sab + sbb;
+  const D5 rab = ra * rb;
+  const D5 t1 = D5(std::pow(2., 11. / 3.) * CF) * (dpow(ra, 8. / 3.) + dpow(rb, 8. / 3.));
+  const D5 t2 = (D5(47. / 18.) - D5(7. / 18.) * delta) * sig;
+  const D5 t3 = (D5(2.5) - delta / D5(18.)) * (saa + sbb);
+  const D5 t4 = (delta - D5(11.)) / D5(9.) * (ra / rho * saa + rb / rho * sbb);
+  const D5 r2 = rho * rho;
+  const D5 brace = rab * (t1 + t2 - t3 - t4) - D5(2. / 3.) * r2 * sig + (D5(2. / 3.) * r2 - ra * ra) * sbb +
+                   (D5(2. / 3.) * r2 - rb * rb) * saa;
+  return -(D5(a) * D5(4.) / den * rab / rho) - D5(a * b) * omega * brace;
+}
+
+// gamma = (sigma_aa, sigma_ab, sigma_bb) interleaved per point like the reference (eval_uvvar_gga_uks)
+void eval_func_pol_gga(const Func& f, int npts, const double* rho2, const double* gamma3, double* eps,
+                       double* vrho2, double* vgamma3) {
+  for (int i = 0; i < npts; ++i) {
+    // densities are clipped away from zero so that rho^(negative power) stays finite; such points
+    // carry weights * rho ~ 0 anyway
+    const D5 ra = D5::var(std::max(rho2[2 * i], 1e-30), 0), rb = D5::var(std::max(rho2[2 * i + 1], 1e-30), 1);
+    const D5 saa = D5::var(std::max(gamma3[3 * i], 0.), 2), sab = D5::var(gamma3[3 * i + 1], 3),
+             sbb = D5::var(std::max(gamma3[3 * i + 2], 0.), 4);
+    D5 E(0.);
+    for (int k = 0; k < f.nkern; ++k) {
+      D5 e(0.);
+      switch (f.kern[k]) {
+        case K_B88_X: e = b88_energy(ra, rb, saa, sbb); break;
+        case K_LYP_C: e = lyp_energy(ra, rb, saa, sab, sbb); break;
+        default: e = D5(std::nan("")); break;  // not restated for UKS GGA
+      }
+      E = E + D5(f.coeff[k]) * e;
+    }
+    const double rho = rho2[2 * i] + rho2[2 * i + 1];
+    if (rho <= 1e-24) {
+      eps[i] = 0.;
+      vrho2[2 * i] = vrho2[2 * i + 1] = 0.;
+      vgamma3[3 * i] = vgamma3[3 * i + 1] = vgamma3[3 * i + 2] = 0.;
+      continue;
+    }
+    eps[i] = E.v / rho;
+    vrho2[2 * i] = E.d[0]; vrho2[2 * i + 1] = E.d[1];
+    vgamma3[3 * i] = E.d[2]; vgamma3[3 * i + 1] = E.d[3]; vgamma3[3 * i + 2] = E.d[4];
   }
 }
 
@@ -774,6 +868,136 @@ void oracle_exc_vxc_uks_lda(int nshells_total, const int32_t* l, const int32_t* 
   Acc E, N, F;
   for (int t = 0; t < ntasks; ++t) { E.add(exc_t[t]); N.add(nel_t[t]); F.add(flops_t[t]); }
   out3[0] = E.value(); out3[1] = N.value(); out3[2] = F.value();
+}
+
+// UKS, GGA: as oracle_exc_vxc_uks_lda plus eval_uvvar_gga_uks (driver.cxx:270-328: grad n, grad Mz with the
+// factor 2, gamma_{++,+-,--}), vgamma weights (:459-466) and eval_zmat_gga_vxc_uks (driver.cxx:715-773).
+void oracle_exc_vxc_uks_gga(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                            const double* alpha, const double* coeff, const double* origin, int nbf,
+                            const double* Ps, const double* Pz, int ldp, int ntasks, const int32_t* task_npts,
+                            const int32_t* task_nshells, const int32_t* shell_lists, const double* points,
+                            const double* weights, int nkern, const int* kern, const double* kcoeff,
+                            double* VXCs, double* VXCz, double* out3) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  Func func{};
+  func.nkern = nkern; func.is_gga = 1;
+  for (int k = 0; k < nkern; ++k) { func.kern[k] = kern[k]; func.coeff[k] = kcoeff[k]; }
+  std::vector<int> first_ao(nshells_total + 1, 0);
+  for (int s = 0; s < nshells_total; ++s) first_ao[s + 1] = first_ao[s] + B.size(s);
+  std::vector<size_t> poff(ntasks + 1, 0), soff(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) {
+    poff[t + 1] = poff[t] + task_npts[t];
+    soff[t + 1] = soff[t] + task_nshells[t];
+  }
+  std::fill(VXCs, VXCs + (size_t)nbf * nbf, 0.);
+  std::fill(VXCz, VXCz + (size_t)nbf * nbf, 0.);
+  std::vector<double> exc_t(ntasks, 0.), nel_t(ntasks, 0.), flops_t(ntasks, 0.);
+  sph_table(0);
+
+#pragma omp parallel
+  {
+    std::vector<double> ev, dxv, dyv, dzv, Xs, Xz, Zs, Zz, scr, Psub, den2, gam3, eps, vrho2, vgam3, dd[3];
+    std::vector<int> ao;
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; ++iT) {
+      const int npts = task_npts[iT];
+      const int nsh = task_nshells[iT];
+      const int32_t* sl = shell_lists + soff[iT];
+      const double* pts = points + 3 * poff[iT];
+      const double* w = weights + poff[iT];
+      ao.clear();
+      for (int q = 0; q < nsh; ++q)
+        for (int a = first_ao[sl[q]]; a < first_ao[sl[q] + 1]; ++a) ao.push_back(a);
+      const int nbe = (int)ao.size();
+      const size_t nn = (size_t)nbe * npts;
+      ev.resize(nn); dxv.resize(nn); dyv.resize(nn); dzv.resize(nn);
+      Xs.resize(nn); Xz.resize(nn); Zs.resize(nn); Zz.resize(nn);
+      scr.resize((size_t)nbe * nbe); Psub.resize((size_t)nbe * nbe);
+      den2.resize(2 * (size_t)npts); gam3.resize(3 * (size_t)npts); eps.resize(npts);
+      vrho2.resize(2 * (size_t)npts); vgam3.resize(3 * (size_t)npts);
+      for (auto& v : dd) v.resize(2 * (size_t)npts);
+      collocation(B, nsh, sl, npts, pts, nbe, true, ev.data(), dxv.data(), dyv.data(), dzv.data());
+      for (int pass = 0; pass < 2; ++pass) {
+        const double* P = pass == 0 ? Ps : Pz;
+        for (int j = 0; j < nbe; ++j)
+          for (int i = 0; i < nbe; ++i) Psub[i + (size_t)j * nbe] = P[ao[i] + (size_t)ao[j] * ldp];
+        gemm_nn(nbe, npts, nbe, 1.0, Psub.data(), nbe, ev.data(), nbe, (pass == 0 ? Xs : Xz).data(), nbe);
+      }
+      const double* dB[3] = {dxv.data(), dyv.data(), dzv.data()};
+      for (int i = 0; i < npts; ++i) {
+        const size_t o = (size_t)i * nbe;
+        const double *bi = ev.data() + o, *xs = Xs.data() + o, *xz = Xz.data() + o;
+        double rs = 0, rz = 0;
+        for (int m = 0; m < nbe; ++m) { rs += bi[m] * xs[m]; rz += bi[m] * xz[m]; }
+        den2[2 * i] = 0.5 * (rs + rz);
+        den2[2 * i + 1] = 0.5 * (rs - rz);
+        double dn[3], dm[3];
+        for (int c = 0; c < 3; ++c) {
+          double a = 0, b = 0;
+          for (int m = 0; m < nbe; ++m) { a += dB[c][o + m] * xs[m]; b += dB[c][o + m] * xz[m]; }
+          dn[c] = 2. * a; dm[c] = 2. * b;
+          dd[c][2 * i] = dn[c]; dd[c][2 * i + 1] = dm[c];
+        }
+        const double dn_sq = dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2];
+        const double dm_sq = dm[0] * dm[0] + dm[1] * dm[1] + dm[2] * dm[2];
+        const double dn_dm = dn[0] * dm[0] + dn[1] * dm[1] + dn[2] * dm[2];
+        gam3[3 * i] = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm;
+        gam3[3 * i + 1] = 0.25 * (dn_sq - dm_sq);
+        gam3[3 * i + 2] = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
+      }
+      eval_func_pol_gga(func, npts, den2.data(), gam3.data(), eps.data(), vrho2.data(), vgam3.data());
+      Acc e_acc, n_acc;
+      for (int i = 0; i < npts; ++i) {
+        eps[i] *= w[i];
+        vrho2[2 * i] *= w[i]; vrho2[2 * i + 1] *= w[i];
+        vgam3[3 * i] *= w[i]; vgam3[3 * i + 1] *= w[i]; vgam3[3 * i + 2] *= w[i];
+        const double den = den2[2 * i] + den2[2 * i + 1];
+        n_acc.add(w[i] * den);
+        e_acc.add(eps[i] * den);
+      }
+      exc_t[iT] = e_acc.value();
+      nel_t[iT] = n_acc.value();
+      for (int i = 0; i < npts; ++i) {
+        const size_t o = (size_t)i * nbe;
+        const double* bi = ev.data() + o;
+        double *zs = Zs.data() + o, *zz = Zz.data() + o;
+        const double factp = 0.5 * vrho2[2 * i], factm = 0.5 * vrho2[2 * i + 1];
+        const double fs = 0.5 * (factp + factm), fz = 0.5 * (factp - factm);
+        const double gpp = vgam3[3 * i], gpm = vgam3[3 * i + 1], gmm = vgam3[3 * i + 2];
+        const double g1 = 0.5 * (gpp + gpm + gmm), g2 = 0.5 * (gpp - gmm), g3 = 0.5 * (gpp - gpm + gmm);
+        for (int m = 0; m < nbe; ++m) { zs[m] = fs * bi[m]; zz[m] = fz * bi[m]; }
+        for (int c = 0; c < 3; ++c) {
+          const double f_s = g1 * dd[c][2 * i] + g2 * dd[c][2 * i + 1];
+          const double f_z = g3 * dd[c][2 * i + 1] + g2 * dd[c][2 * i];
+          for (int m = 0; m < nbe; ++m) { zs[m] += f_s * dB[c][o + m]; zz[m] += f_z * dB[c][o + m]; }
+        }
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        double* V = pass == 0 ? VXCs : VXCz;
+        syr2k_ln(nbe, npts, ev.data(), nbe, (pass == 0 ? Zs : Zz).data(), nbe, scr.data(), nbe);
+        for (int j = 0; j < nbe; ++j)
+          for (int i = j; i < nbe; ++i) {
+#pragma omp atomic
+            V[ao[i] + (size_t)ao[j] * nbf] += scr[i + (size_t)j * nbe];
+          }
+      }
+      flops_t[iT] = 8. * double(nbe) * double(nbe) * double(npts);
+    }
+  }
+  for (double* V : {VXCs, VXCz})
+    for (int j = 0; j < nbf; ++j)
+      for (int i = j + 1; i < nbf; ++i) V[j + (size_t)i * nbf] = V[i + (size_t)j * nbf];
+  Acc E, N, F;
+  for (int t = 0; t < ntasks; ++t) { E.add(exc_t[t]); N.add(nel_t[t]); F.add(flops_t[t]); }
+  out3[0] = E.value(); out3[1] = N.value(); out3[2] = F.value();
+}
+
+void oracle_functional_pol_gga(int nkern, const int* kern, const double* coeff, int npts, const double* rho2,
+                               const double* gamma3, double* eps, double* vrho2, double* vgamma3) {
+  Func f{};
+  f.nkern = nkern; f.is_gga = 1;
+  for (int k = 0; k < nkern; ++k) { f.kern[k] = kern[k]; f.coeff[k] = coeff[k]; }
+  eval_func_pol_gga(f, npts, rho2, gamma3, eps, vrho2, vgamma3);
 }
 
 // polarised LDA functional on its own (unit tests: spin-unpolarised limit, finite differences)

@@ -16,7 +16,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lib = None
 
-KERN = dict(SLATER_X=0, VWN5_C=1, PBE_X=2, PBE_C=3, PW92_C=5)
+KERN = dict(SLATER_X=0, VWN5_C=1, PBE_X=2, PBE_C=3, PW92_C=5, B88_X=6, LYP_C=7)
 FUNCTIONALS = {
     "SVWN5": (False, [("SLATER_X", 1.0), ("VWN5_C", 1.0)]),
     "LDA": (False, [("SLATER_X", 1.0)]),
@@ -24,6 +24,7 @@ FUNCTIONALS = {
     "SPW92": (False, [("SLATER_X", 1.0), ("PW92_C", 1.0)]),
     "PBE": (True, [("PBE_X", 1.0), ("PBE_C", 1.0)]),
     "PBE0": (True, [("PBE_X", 0.75), ("PBE_C", 1.0)]),
+    "BLYP": (True, [("B88_X", 1.0), ("LYP_C", 1.0)]),  # UKS oracle only (forward-mode differentiation)
 }
 
 
@@ -137,8 +138,6 @@ def exc_vxc_uks(flat_basis, nbf, Ps, Pz, tasks, func_name):
     """UKS, LDA functionals (SVWN5, LDA, VWN5): (Ps, Pz) = (P_alpha + P_beta, P_alpha - P_beta)."""
     l, pure, nprim, alpha, coeff, origin = flat_basis
     gga, nk, kern, coef = _func(func_name)
-    if gga:
-        raise NotImplementedError("the UKS oracle covers LDA functionals (the reference's UKS GGA fixture is BLYP)")
     Psf = np.asfortranarray(np.asarray(Ps, np.float64))
     Pzf = np.asfortranarray(np.asarray(Pz, np.float64))
     tn = np.ascontiguousarray(tasks["npts"], np.int32)
@@ -148,10 +147,21 @@ def exc_vxc_uks(flat_basis, nbf, Ps, Pz, tasks, func_name):
     w = np.ascontiguousarray(tasks["weights"], np.float64)
     vs, vz = np.zeros((nbf, nbf), order="F"), np.zeros((nbf, nbf), order="F")
     out3 = np.zeros(3)
-    lib().oracle_exc_vxc_uks_lda(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), nbf, _d(Psf),
-                                 _d(Pzf), Psf.shape[0], len(tn), _i(tn), _i(ts), _i(sl), _d(pts), _d(w), nk, kern,
-                                 coef, _d(vs), _d(vz), _d(out3))
+    fn = lib().oracle_exc_vxc_uks_gga if gga else lib().oracle_exc_vxc_uks_lda
+    fn(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), nbf, _d(Psf), _d(Pzf), Psf.shape[0],
+       len(tn), _i(tn), _i(ts), _i(sl), _d(pts), _d(w), nk, kern, coef, _d(vs), _d(vz), _d(out3))
     return dict(exc=out3[0], nel=out3[1], flops=out3[2], vxc_s=vs, vxc_z=vz)
+
+
+def functional_pol_gga(func_name, rho_a, rho_b, s_aa, s_ab, s_bb):
+    """Spin-polarised GGA (B88, LYP): eps, (vrho_a, vrho_b), (vsigma_aa, vsigma_ab, vsigma_bb)."""
+    gga, nk, kern, coef = _func(func_name)
+    n = len(rho_a)
+    r2 = np.ascontiguousarray(np.stack([rho_a, rho_b], 1).ravel(), np.float64)
+    g3 = np.ascontiguousarray(np.stack([s_aa, s_ab, s_bb], 1).ravel(), np.float64)
+    eps, v2, v3 = np.zeros(n), np.zeros(2 * n), np.zeros(3 * n)
+    lib().oracle_functional_pol_gga(nk, kern, coef, n, _d(r2), _d(g3), _d(eps), _d(v2), _d(v3))
+    return eps, (v2[0::2].copy(), v2[1::2].copy()), (v3[0::3].copy(), v3[1::3].copy(), v3[2::3].copy())
 
 
 def functional_pol_lda(func_name, rho_a, rho_b):

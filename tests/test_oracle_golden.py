@@ -93,6 +93,59 @@ def test_exc_vxc_golden(orc, benzene_golden, name, func, pruning):
     assert abs(r["nel"] - 42.0) < 1e-5
 
 
+def _cytosine_uks(orc, name):
+    from gauxc_b200 import systems
+    d = systems.golden(name)
+    atoms = [(int(Z), *xyz) for Z, xyz in zip(d["mol_Z"], d["mol_xyz"])]
+    shells = []
+    for i in range(len(d["sh_l"])):
+        n = int(d["sh_nprim"][i])
+        shells.append(dict(l=int(d["sh_l"][i]), pure=bool(d["sh_pure"][i]), exps=list(d["sh_alpha"][i, :n]),
+                           coefs=list(d["sh_coeff"][i, :n]), origin=tuple(d["sh_O"][i]), tol=np.finfo(float).eps))
+    mol, basis, lb = make_lb(atoms, shells, "UltraFineGrid", "Robust", normalize=False)
+    tasks = lb.export_tasks()
+    coords = np.array([a[1:] for a in atoms])
+    tasks["weights"] = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"],
+                                       tasks["points"], tasks["weights"])
+    return d, basis, tasks
+
+
+def test_uks_gga_golden(orc):
+    """UKS BLYP on cytosine (reference: tests/xc_integrator.cxx:468-472 over
+    cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks.hdf5): pins the oracle's UKS GGA path -- grad n / grad Mz,
+    gamma_{++,+-,--}, B88 + LYP by forward-mode differentiation, Z_s / Z_z with the three vgamma
+    combinations -- ahead of a Device UKS GGA path.  Same acceptance as the LDA fixture; the scalar
+    channel shows the same 1.4e-9 EXC offset as SVWN5 (fixture, not functional)."""
+    d, basis, tasks = _cytosine_uks(orc, "cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks")
+    nbf = basis.nbf()
+    r = orc.exc_vxc_uks(basis.flat(), nbf, d["DENSITY_SCALAR"], d["DENSITY_Z"], tasks, "BLYP")
+    assert abs(r["exc"] - float(d["EXC"][0])) < 5e-9
+    assert np.linalg.norm(r["vxc_s"] - d["VXC_SCALAR"]) / nbf < 1e-10
+    assert np.linalg.norm(r["vxc_z"] - d["VXC_Z"]) / nbf < 1e-10
+    assert np.abs(r["vxc_s"] - d["VXC_SCALAR"]).max() < 2e-9 and np.abs(r["vxc_z"] - d["VXC_Z"]).max() < 1e-11
+
+
+def test_polarised_gga_symmetry_and_fd(orc):
+    rng = np.random.default_rng(5)
+    n = 500
+    ra, rb = 10 ** rng.uniform(-3, 1, n), 10 ** rng.uniform(-3, 1, n)
+    ga, gb = rng.standard_normal((n, 3)) * ra[:, None], rng.standard_normal((n, 3)) * rb[:, None]
+    saa, sab, sbb = (ga * ga).sum(1), (ga * gb).sum(1), (gb * gb).sum(1)
+    e, (va, vb), (vaa, vab, vbb) = orc.functional_pol_gga("BLYP", ra, rb, saa, sab, sbb)
+    e2, (va2, vb2), (vaa2, vab2, vbb2) = orc.functional_pol_gga("BLYP", rb, ra, sbb, sab, saa)
+    assert np.abs(e - e2).max() < 1e-13 and np.abs(va - vb2).max() < 1e-12 and np.abs(vaa - vbb2).max() < 1e-12
+    h = 1e-6 * ra
+    ep = orc.functional_pol_gga("BLYP", ra + h, rb, saa, sab, sbb)[0]
+    em = orc.functional_pol_gga("BLYP", ra - h, rb, saa, sab, sbb)[0]
+    fd = ((ra + h + rb) * ep - (ra - h + rb) * em) / (2 * h)
+    assert (np.abs(fd - va) / (np.abs(va) + 1e-6)).max() < 1e-5
+    hs = 1e-2 * (np.abs(sab) + 1e-2)  # LYP is linear in sigma_ab: a wide step only reduces cancellation noise
+    ep = orc.functional_pol_gga("BLYP", ra, rb, saa, sab + hs, sbb)[0]
+    em = orc.functional_pol_gga("BLYP", ra, rb, saa, sab - hs, sbb)[0]
+    fd = (ra + rb) * (ep - em) / (2 * hs)
+    assert (np.abs(fd - vab) / (np.abs(vab) + 1e-6)).max() < 1e-6
+
+
 def test_uks_lda_golden(orc):
     """UKS SVWN5 on cytosine (reference: tests/xc_integrator.cxx:455-459 over
     cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks.hdf5): pins the oracle's UKS path -- X_s / X_z, rho_+-,

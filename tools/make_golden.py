@@ -191,6 +191,7 @@ if __name__ == "__main__":
               "benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "benzene_svwn5_cc-pvdz_ufg_ssf_treutler_prune"):
         conv_xc(n)
     conv_xc_uks("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks")
+    conv_xc_uks("cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks")
     conv_basis_only("benzene_m062x_def2-svp_ufg_ssf", "benzene_def2-svp_basis")
     conv_collocation()
     conv_weights()
