@@ -1,5 +1,9 @@
 #include "load_balancer.hpp"
 #include <algorithm>
+#include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace GauXC {
@@ -76,8 +80,32 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     }
   }
 
+  const bool dbg_t = std::getenv("GAUXC_B200_LB_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_scr = 0, t_deal = 0; const double t_begin = tnow();
   std::vector<XCTask> local_work;
   std::vector<size_t> global_workload(world_size, 0);
+
+  // Uniform cell list over the shell centres: a batch only tests the centres whose cell can reach its
+  // box (the reference tests every shell against every batch, O(natoms) per batch -- 2.5e9 tests for
+  // the 2499-atom water cluster).  Candidates are visited in ascending centre index, so the shell
+  // lists come out exactly as before.
+  double cmin[3] = {1e300, 1e300, 1e300}, cmax[3] = {-1e300, -1e300, -1e300}, rmax_all = 0.;
+  for (size_t c = 0; c < natoms; ++c) {
+    const double cen[3] = {mol[c].x, mol[c].y, mol[c].z};
+    for (int d = 0; d < 3; ++d) { cmin[d] = std::min(cmin[d], cen[d]); cmax[d] = std::max(cmax[d], cen[d]); }
+    rmax_all = std::max(rmax_all, center_maxrad[c]);
+  }
+  const double cell = std::max(4.0, 0.5 * rmax_all);
+  int ncell[3] = {1, 1, 1};
+  for (int d = 0; d < 3; ++d) ncell[d] = natoms ? std::max(1, (int)std::floor((cmax[d] - cmin[d]) / cell) + 1) : 1;
+  std::vector<std::vector<int32_t>> cells((size_t)ncell[0] * ncell[1] * ncell[2]);
+  auto cell_of = [&](double v, int d) {
+    return std::min(ncell[d] - 1, std::max(0, (int)std::floor((v - cmin[d]) / cell)));
+  };
+  for (size_t c = 0; c < natoms; ++c)
+    cells[((size_t)cell_of(mol[c].x, 0) * ncell[1] + cell_of(mol[c].y, 1)) * ncell[2] + cell_of(mol[c].z, 2)]
+        .push_back((int32_t)c);
 
   for (size_t iAtom = 0; iAtom < natoms; ++iAtom) {
     const auto& atom = mol[iAtom];
@@ -86,6 +114,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     std::vector<XCTask> temp(nb);
     std::vector<char> keep(nb, 0);
 
+    const double t_a = tnow();
 #pragma omp parallel for schedule(dynamic, 4)
     for (size_t ib = 0; ib < nb; ++ib) {
       const GridBatch& gb = grid.batch(ib);
@@ -94,7 +123,22 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       const double up[3] = {gb.up[0] + atom.x, gb.up[1] + atom.y, gb.up[2] + atom.z};
 
       std::vector<int32_t> shell_list;
-      for (size_t c = 0; c < natoms; ++c) {
+      std::vector<int32_t> cand;
+      {
+        int c0[3], c1[3];
+        for (int d = 0; d < 3; ++d) {
+          c0[d] = cell_of(lo[d] - rmax_all, d);
+          c1[d] = cell_of(up[d] + rmax_all, d);
+        }
+        for (int ix = c0[0]; ix <= c1[0]; ++ix)
+          for (int iy = c0[1]; iy <= c1[1]; ++iy)
+            for (int iz = c0[2]; iz <= c1[2]; ++iz) {
+              const auto& cl = cells[((size_t)ix * ncell[1] + iy) * ncell[2] + iz];
+              cand.insert(cand.end(), cl.begin(), cl.end());
+            }
+        std::sort(cand.begin(), cand.end());
+      }
+      for (int32_t c : cand) {
         if (center_shells[c].empty()) continue;
         const double cen[3] = {mol[c].x, mol[c].y, mol[c].z};
         if (!cube_sphere_intersect(lo, up, cen, center_maxrad[c])) continue;
@@ -125,6 +169,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       keep[ib] = 1;
     }
 
+    const double t_b = tnow(); t_scr += t_b - t_a;
     // deterministic greedy deal in batch order
     for (size_t ib = 0; ib < nb; ++ib) {
       if (!keep[ib]) continue;
@@ -133,21 +178,56 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       global_workload[min_rank] += temp[ib].cost(n_deriv, natoms);
       if (world_rank == min_rank) local_work.push_back(std::move(temp[ib]));
     }
+    t_deal += tnow() - t_b;
   }
+  const double t_loop = tnow();
 
-  auto task_order = [](const XCTask& a, const XCTask& b) {
-    if (a.iParent < b.iParent) return true;
-    if (a.iParent > b.iParent) return false;
-    return a.bfn_screening.shell_list < b.bfn_screening.shell_list;
-  };
-  std::stable_sort(local_work.begin(), local_work.end(), task_order);
-
-  // merge runs of equivalent tasks
+  // Sort by (iParent, shell_list), stable, then merge runs of equivalent tasks (same parent, same shell
+  // list).  Tasks are created parent by parent, so both steps act inside each parent's stretch of the
+  // list: the stretches are processed independently and in parallel, then concatenated in order.
   std::vector<XCTask> merged;
-  for (auto& t : local_work) {
-    if (!merged.empty() && merged.back().equiv_with(t)) merged.back().merge_with(t);
-    else merged.push_back(std::move(t));
+  {
+    std::vector<size_t> run_begin;
+    for (size_t i = 0; i < local_work.size(); ++i)
+      if (i == 0 || local_work[i].iParent != local_work[i - 1].iParent) run_begin.push_back(i);
+    run_begin.push_back(local_work.size());
+    bool ascending = true;
+    for (size_t r = 0; r + 2 < run_begin.size(); ++r)
+      ascending = ascending && local_work[run_begin[r]].iParent < local_work[run_begin[r + 1]].iParent;
+    auto merge_range = [](std::vector<XCTask>& out, std::vector<XCTask>::iterator b, std::vector<XCTask>::iterator e) {
+      for (auto it = b; it != e; ++it) {
+        if (!out.empty() && out.back().equiv_with(*it)) out.back().merge_with(*it);
+        else out.push_back(std::move(*it));
+      }
+    };
+    if (ascending && !local_work.empty()) {
+      auto by_list = [](const XCTask& a, const XCTask& b) {
+        return a.bfn_screening.shell_list < b.bfn_screening.shell_list;
+      };
+      const long nruns = (long)run_begin.size() - 1;
+      std::vector<std::vector<XCTask>> per_run(nruns);
+#pragma omp parallel for schedule(dynamic, 1)
+      for (long r = 0; r < nruns; ++r) {
+        std::stable_sort(local_work.begin() + run_begin[r], local_work.begin() + run_begin[r + 1], by_list);
+        merge_range(per_run[r], local_work.begin() + run_begin[r], local_work.begin() + run_begin[r + 1]);
+      }
+      size_t total = 0;
+      for (auto& v : per_run) total += v.size();
+      merged.reserve(total);
+      for (auto& v : per_run)
+        for (auto& t : v) merged.push_back(std::move(t));
+    } else {
+      auto task_order = [](const XCTask& a, const XCTask& b) {
+        if (a.iParent < b.iParent) return true;
+        if (a.iParent > b.iParent) return false;
+        return a.bfn_screening.shell_list < b.bfn_screening.shell_list;
+      };
+      std::stable_sort(local_work.begin(), local_work.end(), task_order);
+      merge_range(merged, local_work.begin(), local_work.end());
+    }
   }
+  const double t_sort = tnow();
+  if (dbg_t) std::fprintf(stderr, "[lb] screen %.2f deal %.2f (loop %.2f) sort+merge %.2f s\n", t_scr, t_deal, t_loop - t_begin, t_sort - t_loop);
   return merged;
 }
 
