@@ -129,6 +129,7 @@ def lib():
         "gauxc_b200_radial": (None, [S, C.c_int, C.c_int, C.c_double, _dp, _dp]),
         "gauxc_b200_eval_collocation": (None, [S, _Handle, C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
+        "gauxc_b200_functional_eval_host_pol": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_probe_peak": (C.c_double, [S, C.c_int]),
         "gauxc_b200_device_count": (C.c_int, []),
         "gauxc_b200_set_device": (None, [S, C.c_int]),
@@ -400,6 +401,16 @@ class Functional(_Obj):
         eps, vr, vs = np.zeros(n), np.zeros(n), np.zeros(n)
         _call("gauxc_b200_functional_eval_host", self.h, n, _d(rho), _d(sg), _d(eps), _d(vr), _d(vs))
         return eps, vr, vs
+
+
+    def eval_host_pol(self, rho_a, rho_b):
+        """Spin-polarised LDA kernels (UKS) on the host: eps, d(rho eps)/d rho_a, d(rho eps)/d rho_b."""
+        ra = np.ascontiguousarray(rho_a, np.float64)
+        rb = np.ascontiguousarray(rho_b, np.float64)
+        n = len(ra)
+        eps, va, vb = np.zeros(n), np.zeros(n), np.zeros(n)
+        _call("gauxc_b200_functional_eval_host_pol", self.h, n, _d(ra), _d(rb), _d(eps), _d(va), _d(vb))
+        return eps, va, vb
 
 
 class XCIntegrator(_Obj):

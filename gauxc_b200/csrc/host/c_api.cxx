@@ -367,6 +367,21 @@ void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional 
   C_CATCH(status)
 }
 
+void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
+                                         const double* rho_a, const double* rho_b, double* eps, double* vrho_a,
+                                         double* vrho_b) {
+  C_TRY(status)
+  const auto& f = **FN(functional);
+  if (f.is_gga()) GAUXC_GENERIC_EXCEPTION("Polarized GGA NYI in B200 path");
+  for (int64_t i = 0; i < npts; ++i) {
+    const auto o = gxb::eval_functional_pol_lda(f.desc, rho_a[i], rho_b[i]);
+    eps[i] = o.eps;
+    vrho_a[i] = o.va;
+    vrho_b[i] = o.vb;
+  }
+  C_CATCH(status)
+}
+
 // ---- integrator ----------------------------------------------------------------------------------
 GauXCIntegrator gauxc_integrator_new(GauXCStatus* status, const GauXCFunctional functional,
                                      const GauXCLoadBalancer lb, enum GauXC_ExecutionSpace ex,

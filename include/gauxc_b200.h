@@ -294,6 +294,10 @@ void gauxc_b200_eval_collocation(GauXCStatus* status, const GauXCBasisSet basis,
 void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
                                      const double* rho, const double* sigma, double* eps, double* vrho,
                                      double* vsigma);
+/* same for the spin-polarised LDA kernels of the UKS path: out = {eps, vrho_a, vrho_b} per point */
+void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
+                                         const double* rho_a, const double* rho_b, double* eps, double* vrho_a,
+                                         double* vrho_b);
 /* FP64 machine-peak probes (roofline denominators): which = 0 DMMA TF/s, 1 DFMA TF/s, 2 HBM copy GB/s */
 double gauxc_b200_probe_peak(GauXCStatus* status, int which);
 int gauxc_b200_device_count(void);

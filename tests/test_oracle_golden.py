@@ -176,6 +176,22 @@ def test_uks_lda_golden(orc):
     assert abs(r["nel"] - 57.0) < 1e-4  # the fixture is the radical cation (58 protons)
 
 
+def test_polarised_lda_product_vs_oracle(orc):
+    """The product's spin-polarised LDA kernels (the __host__ __device__ source the fused kernel's UKS
+    pass compiles) against the oracle's on random (rho_a, rho_b), including fully polarised points."""
+    import gauxc_b200 as gx
+    rng = np.random.default_rng(9)
+    rho = 10 ** rng.uniform(-9, 2, 4000)
+    zeta = np.r_[rng.uniform(-1, 1, 3990), [1.0, -1.0, 0.0, 0.999999, -0.999999, 1.0, -1.0, 0.0, 0.5, -0.5]]
+    ra, rb = 0.5 * rho * (1 + zeta), 0.5 * rho * (1 - zeta)
+    for fn in ("SVWN5", "LDA", "VWN5"):
+        e1, a1, b1 = gx.Functional(fn, polarized=True).eval_host_pol(ra, rb)
+        e2, a2, b2 = orc.functional_pol_lda(fn, ra, rb)
+        for x, y in ((e1, e2), (a1, a2), (b1, b2)):
+            assert np.all(np.isfinite(x))
+            assert (np.abs(x - y) / (np.abs(y) + 1e-13)).max() < 1e-8, fn
+
+
 def test_polarised_lda_limits_and_fd(orc):
     rng = np.random.default_rng(3)
     rho = 10 ** rng.uniform(-6, 1.5, 2000)
