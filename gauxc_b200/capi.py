@@ -130,6 +130,8 @@ def lib():
         "gauxc_b200_eval_collocation": (None, [S, _Handle, C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host_pol": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
+        "gauxc_b200_functional_eval_host_pol_gga": (None, [S, C.c_int, C.POINTER(C.c_int), _dp, C.c_int64, _dp, _dp,
+                                                           _dp, _dp, _dp]),
         "gauxc_b200_probe_peak": (C.c_double, [S, C.c_int]),
         "gauxc_b200_device_count": (C.c_int, []),
         "gauxc_b200_set_device": (None, [S, C.c_int]),
@@ -411,6 +413,20 @@ class Functional(_Obj):
         eps, va, vb = np.zeros(n), np.zeros(n), np.zeros(n)
         _call("gauxc_b200_functional_eval_host_pol", self.h, n, _d(ra), _d(rb), _d(eps), _d(va), _d(vb))
         return eps, va, vb
+
+
+def eval_host_pol_gga(kernels, rho_a, rho_b, s_aa, s_ab, s_bb):
+    """Spin-polarised GGA kernels prepared for UKS GGA, on the host: kernels = [("B88_X", c), ("LYP_C", c)]."""
+    ids = dict(B88_X=0, LYP_C=1)
+    kern = (C.c_int * len(kernels))(*[ids[k] for k, _ in kernels])
+    coef = np.array([c for _, c in kernels], np.float64)
+    n = len(rho_a)
+    r2 = np.ascontiguousarray(np.stack([rho_a, rho_b], 1).ravel(), np.float64)
+    g3 = np.ascontiguousarray(np.stack([s_aa, s_ab, s_bb], 1).ravel(), np.float64)
+    eps, v2, v3 = np.zeros(n), np.zeros(2 * n), np.zeros(3 * n)
+    _call("gauxc_b200_functional_eval_host_pol_gga", len(kernels), kern, _d(coef), n, _d(r2), _d(g3), _d(eps),
+          _d(v2), _d(v3))
+    return eps, (v2[0::2].copy(), v2[1::2].copy()), (v3[0::3].copy(), v3[1::3].copy(), v3[2::3].copy())
 
 
 class XCIntegrator(_Obj):

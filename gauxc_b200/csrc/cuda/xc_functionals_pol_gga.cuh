@@ -1,0 +1,128 @@
+// Spin-polarised GGA kernels for the UKS GGA path (B88 exchange, LYP correlation, PBE exchange and
+// correlation to follow), evaluated with 5-partial forward-mode dual numbers: the energy density
+// E(rho_a, rho_b, sigma_aa, sigma_ab, sigma_bb) of the published functional is written once and
+// vrho[2] / vsigma[3] (the libxc / ExchCXX polarised GGA outputs the reference consumes in
+// eval_zmat_gga_vxc_uks, reference_local_host_work_driver.cxx:715-773) fall out.  The functional is
+// evaluated once per grid point (~10^3 flop against ~10^5 of the contractions), so the 6x arithmetic
+// of the dual numbers is invisible next to the DMMA work.
+//
+// STATUS: host-verified against the oracle (tests/test_oracle_golden.py); not yet included by a
+// kernel -- the Device UKS GGA path is the next step.
+#pragma once
+#include "xc_functionals.cuh"
+
+namespace gxb {
+
+struct Dual5 {
+  double v;
+  double d[5];
+  GXB_HD Dual5(double x = 0.) : v(x) {
+    for (int k = 0; k < 5; ++k) d[k] = 0.;
+  }
+};
+GXB_HD Dual5 dual_var(double x, int k) {
+  Dual5 r(x);
+  r.d[k] = 1.;
+  return r;
+}
+GXB_HD Dual5 dual_lift(const Dual5& a, double f, double fp) {
+  Dual5 r(f);
+  for (int k = 0; k < 5; ++k) r.d[k] = fp * a.d[k];
+  return r;
+}
+GXB_HD Dual5 operator+(const Dual5& a, const Dual5& b) {
+  Dual5 r(a.v + b.v);
+  for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] + b.d[k];
+  return r;
+}
+GXB_HD Dual5 operator-(const Dual5& a, const Dual5& b) {
+  Dual5 r(a.v - b.v);
+  for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] - b.d[k];
+  return r;
+}
+GXB_HD Dual5 operator-(const Dual5& a) {
+  Dual5 r(-a.v);
+  for (int k = 0; k < 5; ++k) r.d[k] = -a.d[k];
+  return r;
+}
+GXB_HD Dual5 operator*(const Dual5& a, const Dual5& b) {
+  Dual5 r(a.v * b.v);
+  for (int k = 0; k < 5; ++k) r.d[k] = a.d[k] * b.v + a.v * b.d[k];
+  return r;
+}
+GXB_HD Dual5 operator/(const Dual5& a, const Dual5& b) {
+  Dual5 r(a.v / b.v);
+  for (int k = 0; k < 5; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) / b.v;
+  return r;
+}
+GXB_HD Dual5 dual_pow(const Dual5& a, double p) { return dual_lift(a, pow(a.v, p), p * pow(a.v, p - 1.)); }
+GXB_HD Dual5 dual_exp(const Dual5& a) {
+  const double e = exp(a.v);
+  return dual_lift(a, e, e);
+}
+GXB_HD Dual5 dual_sqrt(const Dual5& a) {
+  const double q = sqrt(a.v);
+  return dual_lift(a, q, 0.5 / q);
+}
+GXB_HD Dual5 dual_asinh(const Dual5& a) { return dual_lift(a, asinh(a.v), 1. / sqrt(1. + a.v * a.v)); }
+
+// Becke 1988: E_x = sum_s -rho_s^{4/3} [ C + beta x^2 / (1 + 6 beta x asinh x) ],  x = |grad rho_s| / rho_s^{4/3}
+GXB_HD Dual5 b88_x_spin(const Dual5& r, const Dual5& s) {
+  const double beta = 0.0042, C = 0.93052573634910002500;  // (3/2) (3 / (4 pi))^(1/3)
+  if (r.v <= 1e-20) return Dual5(0.);
+  const Dual5 r43 = dual_pow(r, 4. / 3.);
+  if (s.v <= 1e-40) return -(r43 * Dual5(C));
+  const Dual5 x = dual_sqrt(s) / r43;
+  return -(r43 * (Dual5(C) + Dual5(beta) * x * x / (Dual5(1.) + Dual5(6. * beta) * x * dual_asinh(x))));
+}
+
+// Lee-Yang-Parr in the closed form of Miehlich, Savin, Stoll, Preuss, Chem. Phys. Lett. 157, 200 (1989)
+GXB_HD Dual5 lyp_c_energy(const Dual5& ra, const Dual5& rb, const Dual5& saa, const Dual5& sab, const Dual5& sbb) {
+  const double a = 0.04918, b = 0.132, c = 0.2533, d = 0.349;
+  const double CF = 2.87123400018819181594;  // (3/10) (3 pi^2)^(2/3)
+  const Dual5 rho = ra + rb;
+  if (rho.v <= 1e-20) return Dual5(0.);
+  const Dual5 rm13 = dual_pow(rho, -1. / 3.);
+  const Dual5 den = Dual5(1.) + Dual5(d) * rm13;
+  const Dual5 omega = dual_exp(-(Dual5(c) * rm13)) / den * dual_pow(rho, -11. / 3.);
+  const Dual5 delta = Dual5(c) * rm13 + Dual5(d) * rm13 / den;
+  const Dual5 sig = saa + Dual5(2.) * sab + sbb;
+  const Dual5 rab = ra * rb;
+  const Dual5 t1 = Dual5(12.69920841574560865 * CF) * (dual_pow(ra, 8. / 3.) + dual_pow(rb, 8. / 3.));  // 2^(11/3)
+  const Dual5 t2 = (Dual5(47. / 18.) - Dual5(7. / 18.) * delta) * sig;
+  const Dual5 t3 = (Dual5(2.5) - delta / Dual5(18.)) * (saa + sbb);
+  const Dual5 t4 = (delta - Dual5(11.)) / Dual5(9.) * (ra / rho * saa + rb / rho * sbb);
+  const Dual5 r2 = rho * rho;
+  const Dual5 brace = rab * (t1 + t2 - t3 - t4) - Dual5(2. / 3.) * r2 * sig + (Dual5(2. / 3.) * r2 - ra * ra) * sbb +
+                      (Dual5(2. / 3.) * r2 - rb * rb) * saa;
+  return -(Dual5(a) * Dual5(4.) / den * rab / rho) - Dual5(a * b) * omega * brace;
+}
+
+enum PolGgaKernelId : int { PK_B88_X = 0, PK_LYP_C = 1 };
+
+struct XcOutPolGga {
+  double eps, va, vb, vaa, vab, vbb;
+};
+
+// sum_k coeff_k kernel_k at one point; gamma = (sigma_aa, sigma_ab, sigma_bb)
+GXB_HD XcOutPolGga eval_pol_gga(int nkern, const int* kern, const double* coeff, double rho_a, double rho_b,
+                                double s_aa, double s_ab, double s_bb) {
+  XcOutPolGga o{0., 0., 0., 0., 0., 0.};
+  const double rho = rho_a + rho_b;
+  if (rho <= 1e-24) return o;
+  const Dual5 ra = dual_var(fmax(rho_a, 1e-30), 0), rb = dual_var(fmax(rho_b, 1e-30), 1);
+  const Dual5 saa = dual_var(fmax(s_aa, 0.), 2), sab = dual_var(s_ab, 3), sbb = dual_var(fmax(s_bb, 0.), 4);
+  Dual5 E(0.);
+  for (int k = 0; k < nkern; ++k) {
+    Dual5 e(0.);
+    if (kern[k] == PK_B88_X) e = b88_x_spin(ra, saa) + b88_x_spin(rb, sbb);
+    else if (kern[k] == PK_LYP_C) e = lyp_c_energy(ra, rb, saa, sab, sbb);
+    E = E + Dual5(coeff[k]) * e;
+  }
+  o.eps = E.v / rho;
+  o.va = E.d[0]; o.vb = E.d[1];
+  o.vaa = E.d[2]; o.vab = E.d[3]; o.vbb = E.d[4];
+  return o;
+}
+
+}  // namespace gxb

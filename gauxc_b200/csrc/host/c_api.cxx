@@ -3,6 +3,7 @@
 // src/c-api/c_status.hpp:23-43, src/c-api/c_xc_integrator.cxx:86-147).
 #include "../../../include/gauxc_b200.h"
 #include "../cuda/xc_functionals.cuh"
+#include "../cuda/xc_functionals_pol_gga.cuh"
 #include "xc_integrator.hpp"
 #include <cstdlib>
 #include <cstring>
@@ -378,6 +379,20 @@ void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctio
     eps[i] = o.eps;
     vrho_a[i] = o.va;
     vrho_b[i] = o.vb;
+  }
+  C_CATCH(status)
+}
+
+void gauxc_b200_functional_eval_host_pol_gga(GauXCStatus* status, int nkern, const int* kern, const double* coeff,
+                                             int64_t npts, const double* rho2, const double* gamma3, double* eps,
+                                             double* vrho2, double* vgamma3) {
+  C_TRY(status)
+  for (int64_t i = 0; i < npts; ++i) {
+    const auto o = gxb::eval_pol_gga(nkern, kern, coeff, rho2[2 * i], rho2[2 * i + 1], gamma3[3 * i],
+                                     gamma3[3 * i + 1], gamma3[3 * i + 2]);
+    eps[i] = o.eps;
+    vrho2[2 * i] = o.va; vrho2[2 * i + 1] = o.vb;
+    vgamma3[3 * i] = o.vaa; vgamma3[3 * i + 1] = o.vab; vgamma3[3 * i + 2] = o.vbb;
   }
   C_CATCH(status)
 }

@@ -298,6 +298,11 @@ void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional 
 void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
                                          const double* rho_a, const double* rho_b, double* eps, double* vrho_a,
                                          double* vrho_b);
+/* spin-polarised GGA kernels prepared for the UKS GGA path (host evaluation for unit tests; kern: 0 = B88
+ * exchange, 1 = LYP correlation; rho2 = {rho_a, rho_b}, gamma3 = {sigma_aa, sigma_ab, sigma_bb} per point) */
+void gauxc_b200_functional_eval_host_pol_gga(GauXCStatus* status, int nkern, const int* kern, const double* coeff,
+                                             int64_t npts, const double* rho2, const double* gamma3, double* eps,
+                                             double* vrho2, double* vgamma3);
 /* FP64 machine-peak probes (roofline denominators): which = 0 DMMA TF/s, 1 DFMA TF/s, 2 HBM copy GB/s */
 double gauxc_b200_probe_peak(GauXCStatus* status, int which);
 int gauxc_b200_device_count(void);

@@ -176,6 +176,23 @@ def test_uks_lda_golden(orc):
     assert abs(r["nel"] - 57.0) < 1e-4  # the fixture is the radical cation (58 protons)
 
 
+def test_polarised_gga_product_kernels_vs_oracle(orc):
+    """The product's B88 / LYP kernels for the coming UKS GGA path (xc_functionals_pol_gga.cuh, dual numbers)
+    against the oracle's, which is pinned to the reference's BLYP UKS fixture."""
+    from gauxc_b200 import capi
+    rng = np.random.default_rng(13)
+    n = 3000
+    ra, rb = 10 ** rng.uniform(-7, 1.5, n), 10 ** rng.uniform(-7, 1.5, n)
+    ga, gb = rng.standard_normal((n, 3)) * ra[:, None] ** (4 / 3), rng.standard_normal((n, 3)) * rb[:, None] ** (4 / 3)
+    saa, sab, sbb = (ga * ga).sum(1), (ga * gb).sum(1), (gb * gb).sum(1)
+    got = capi.eval_host_pol_gga([("B88_X", 1.0), ("LYP_C", 1.0)], ra, rb, saa, sab, sbb)
+    ref = orc.functional_pol_gga("BLYP", ra, rb, saa, sab, sbb)
+    flat = lambda r: [r[0], *r[1], *r[2]]  # noqa: E731
+    for x, y in zip(flat(got), flat(ref)):
+        assert np.all(np.isfinite(x))
+        assert (np.abs(x - y) / (np.abs(y) + 1e-12)).max() < 1e-9
+
+
 def test_polarised_lda_product_vs_oracle(orc):
     """The product's spin-polarised LDA kernels (the __host__ __device__ source the fused kernel's UKS
     pass compiles) against the oracle's on random (rho_a, rho_b), including fully polarised points."""
