@@ -5,6 +5,9 @@ A "step" is one full XCIntegrator::eval_exc_vxc over the whole molecular grid of
 (all local grid batches: collocation -> X = P_sub B (DMMA) -> rho/grad rho -> functional -> Z ->
 VXC += B^T Z (DMMA) -> scatter -> symmetrise -> allreduce over ranks).
 
+  parity  : EXC / N_el / max|dVXC| of the Device path -- through the NCCL reduction at N > 1 -- against the
+            oracle on a fixed sample of the real task list (every k-th task of every rank), at every N.
+  others  : the other multi-GPU BASELINE configurations (short runs) in the same JSON line.
   value   : grid points/s, whole job, inputs (P, tasks, weights) resident in HBM, device-resident
             entry point (gauxc_b200_integrator_eval_exc_vxc_rks_device), CUDA events on the
             integrator's stream, max over ranks.
@@ -40,8 +43,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("GAUXC_B200_WORKLOAD", "taxol"),
+    # headline = the largest BASELINE configuration that fits one GPU ((H2O)833: nbf 19 992, 146 M points)
+    ap.add_argument("--workload", default=os.environ.get("GAUXC_B200_WORKLOAD", "water833"),
                     choices=["water", "benzene", "taxol", "ubiquitin", "water833"])
+    ap.add_argument("--others", default=os.environ.get("GAUXC_B200_BENCH_OTHERS", "taxol,ubiquitin"),
+                    help="comma separated workloads reported under `others` (short runs: 3 steps); '' = none")
+    ap.add_argument("--parity-seconds", type=float, default=25.0,
+                    help="CPU time the oracle may spend on the parity sample of each workload")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
@@ -170,7 +178,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(s, 1, "host cores; bounded task sample per step"),
+            "config": workload_config(s, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": "port",
                              "sample": base["sample"], "blas": base["blas"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,13 +186,242 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(s, ngpu, l2note):
+def workload_config(s, ngpu, l2note=None):
+    """Identical in the b200 and the reference arm for the same --workload / --gpus."""
     return {"workload": f"{s.workload} {s.basis_name} {s.func_name} {s.grid} unpruned SSF RKS EXC+VXC",
             "natoms": len(s.atoms), "nbf": int(s.nbf), "basis_tol": 1e-10, "batch_size": 512,
             "density": "SCF density of the reference fixture" if s.workload == "benzene" else
                        "synthetic SAD-like + seeded perturbation (SURVEY 8d)",
-            "parallelism": f"grid batches dealt over {ngpu} GPU(s), NCCL allreduce of VXC/EXC",
-            "l2": l2note}
+            "parallelism": f"grid batches dealt over {ngpu} GPU(s), one NCCL allreduce of [tril(VXC) | EXC | N_EL]",
+            "l2": "inputs larger than L2: the per-step working set (B / dB workspace, GBs) streams through the "
+                  "126 MB L2, no flush needed"}
+
+
+def gather_tasks(local, world, rank):
+    """Concatenate per-rank task dicts on rank 0 (pickled through torch.distributed)."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(local, out, dst=0)
+    if rank != 0:
+        return None
+    keys = ["npts", "iParent", "dist_nearest", "nshells", "nbe", "points", "weights", "shell_lists"]
+    return {k: np.concatenate([o[k] for o in out]) for k in keys if k in out[0]}
+
+
+def parity_block(s, world, rank, seconds, dmma_rate_hint=None):
+    """Device (+ NCCL reduction over `world` ranks) vs the oracle on a fixed sample of the real task list:
+    every k-th local task of every rank, k chosen so that the oracle needs ~`seconds` of CPU.  The sample runs
+    through the same public entry point (gauxc_integrator_eval_exc_vxc_rks), a LoadBalancer holding the sampled
+    tasks with their Device SSF weights, and the integrator's reduction driver."""
+    import gauxc_b200 as gx
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    info = s.lb.task_info()
+    nt = len(info["npts"])
+    cost = float((info["nbe"].astype(float) ** 2 * info["npts"] * 4).sum()) * world  # ~ whole-job dense flops
+    rate = 2.5e11 if dmma_rate_hint is None else dmma_rate_hint  # oracle dense flop/s (measured 2-4e11 on 16+ cores)
+    stride = int(max(1, np.ceil(cost / (rate * seconds))))
+    pick = np.arange(rank % stride, nt, stride) if nt else np.zeros(0, int)
+    poff = np.r_[0, np.cumsum(info["npts"])]
+    npts_s, ip_s, dn_s, nsh_s = info["npts"][pick], info["iParent"][pick], info["dist_nearest"][pick], info["nshells"][pick]
+    pts, w, sl = [], [], []
+    for t in pick:
+        p_, w_, s_ = s.lb.get_task(int(t), info)
+        pts.append(p_); w.append(w_); sl.append(s_)
+    pts = np.concatenate(pts) if pts else np.zeros((0, 3))
+    w = np.concatenate(w) if w else np.zeros(0)
+    sl = np.concatenate(sl) if sl else np.zeros(0, np.int32)
+    lb2 = gx.LoadBalancerFactory("Host", "Replicated").get_instance(s.rt, s.mol, s.mg, s.basis)
+    lb2.set_tasks(npts_s, ip_s, dn_s, pts, w, nsh_s, sl, True)
+    integ2 = gx.XCIntegratorFactory("Device", "Replicated", "Default", "Default", "Default") \
+        .get_instance(gx.Functional(s.func_name), lb2)
+    exc, vxc = integ2.eval_exc_vxc(s.P)
+    nel = integ2.stats()["n_el"]
+    local = dict(npts=npts_s.astype(np.int32), iParent=ip_s.astype(np.int32), dist_nearest=dn_s,
+                 nshells=nsh_s.astype(np.int32), points=pts, weights=w, shell_lists=sl.astype(np.int32))
+    allt = gather_tasks(local, world, rank)
+    out = None
+    if rank == 0:
+        orc.init_blas()
+        t0 = time.time()
+        ref = orc.exc_vxc(s.basis.flat(), s.nbf, s.P, allt, s.func_name)
+        dt = time.time() - t0
+        dvxc = float(np.abs(vxc - ref["vxc"]).max())
+        out = {"dexc": abs(exc - ref["exc"]), "dvxc": dvxc, "dnel": abs(nel - ref["nel"]),
+               "vxc_checksum": float(np.abs(vxc).sum()), "vxc_symmetric": bool(np.array_equal(vxc, vxc.T)),
+               "exc_sample": exc, "ntasks": int(len(allt["npts"])), "npts": int(allt["npts"].sum()),
+               "sample": f"every {stride}th task of every rank's list ({len(allt['npts'])} tasks, "
+                         f"{int(allt['npts'].sum())} points), oracle {dt:.1f} s",
+               "tolerance": 1e-10, "through": "gauxc_integrator_eval_exc_vxc_rks" + (" + NCCL allreduce" if world > 1 else "")}
+        out["ok"] = bool(out["dexc"] <= 1e-10 and out["dvxc"] <= 1e-10 and out["dnel"] <= 1e-10)
+    del integ2, lb2
+    return out
+
+
+def run_workload(args, workload, steps, warmup, full, rank, local_rank, world, barrier):
+    """One workload through both arms.  full: headline run (e2e, CPU baseline, clocks); else short `others` run."""
+    import torch
+    import torch.distributed as dist
+    from gauxc_b200 import capi
+    from gauxc_b200.driver import System
+
+    t_setup0 = time.time()
+    s = System(workload, rank=rank, size=world, device=True, verbose=args.verbose and rank == 0)
+    ssf_ms = s.modify_weights()
+    integ = s.make_integrator("Default")
+    nbf = s.nbf
+    info = s.lb.task_info()
+    npts_local = int(info["npts"].sum())
+    npts_t = torch.tensor([float(npts_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(npts_t)
+    npts_total = int(npts_t.item())
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    dP = torch.from_numpy(np.ascontiguousarray(s.P.T)).cuda()  # symmetric: layout agnostic
+    dV = torch.zeros((nbf, nbf), dtype=torch.float64, device="cuda")
+    dout = torch.zeros(2, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.ExternalStream(integ.stream())
+    torch.cuda.synchronize()
+    setup_s = time.time() - t_setup0
+
+    def step_dev():
+        integ.eval_exc_vxc_device(dP.data_ptr(), dV.data_ptr(), dout.data_ptr())
+
+    for _ in range(warmup):
+        step_dev()
+    integ.set_profile(True)  # per-kernel CUDA events on the launching stream, read after the sync
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = np.zeros(4)
+    launches = 0
+    e0.record(stream)
+    t0 = time.time()
+    for _ in range(steps):
+        step_dev()
+        st = integ.stats()
+        kms += [st["k_colloc_ms"], st["k_xmat_ms"], st["k_zmat_ms"], st["k_vxc_ms"]]
+        launches += int(st["launches"])
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.time() - t0) * 1e3
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    tt = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(tt[0]), float(tt[1])
+    ms_per_step = dev_ms / steps
+    value = npts_total / (ms_per_step * 1e-3)
+    exc_dev, nel_dev = [float(x) for x in dout.cpu()]
+    st = integ.stats()
+    integ.set_profile(False)
+
+    # ---- end-to-end arm: the reference-facing C-ABI call with host buffers -----------------------
+    e2e = None
+    if full or world > 1:
+        Ph = torch.empty((nbf, nbf), dtype=torch.float64).pin_memory()
+        Ph.copy_(torch.from_numpy(np.ascontiguousarray(s.P.T)))
+        Vh = torch.empty((nbf, nbf), dtype=torch.float64).pin_memory()
+        Pn, Vn = Ph.numpy(), Vh.numpy()
+        for _ in range(max(1, min(warmup, 2))):
+            integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
+        barrier()
+        t0 = time.time()
+        e2e_dev_ms = 0.0
+        for _ in range(steps):
+            integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
+            e2e_dev_ms += integ.stats()["total_ms"]
+        barrier()
+        e2e_wall_ms = (time.time() - t0) * 1e3
+        tt = torch.tensor([e2e_wall_ms, e2e_dev_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt[0]) / steps  # wall clock of the blocking host call, max over ranks
+        slab = world > 1 and (nbf * nbf * 8 // world) >= (4 << 20)
+        e2e = {"value": npts_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "device_ms_per_step": float(tt[1]) / steps,
+               "h2d_bytes_per_step": int(nbf * nbf * 8 // (world if slab else 1)),
+               "d2h_bytes_per_step": int(nbf * nbf * 8 + 16),
+               "api": "gauxc_integrator_eval_exc_vxc_rks(host P, host VXC), pinned host buffers; per rank" +
+                      ("; P uploaded as 1/N column slabs + NCCL all-gather" if slab else "")}
+        del Ph, Vh
+
+    # ---- parity against the oracle, through the reduction, at this N ---------------------------------
+    parity = parity_block(s, world, rank, args.parity_seconds)
+
+    # ---- roofline of the dominant kernel class (local rank 0 numbers) ------------------------------
+    peaks, peak_src = measured_peaks()
+    dmma_peak = capi.probe_peak("dmma")  # FP64 tensor peak is not in MEASURED_PEAKS.json: probe
+    f_dense = st["f_dense"]
+    k_names = ["collocation", "xmat_density(DMMA)", "func_zmat", "vxc(DMMA)"]
+    k_ms = (kms / steps).tolist()
+    nb = max(1, int(st["nbatches"]))
+    gga = s.func_name.upper() not in ("SVWN5", "LDA", "SLATER", "VWN5", "SPW92")
+    hbm_peak = peaks.get("hbm_gbs")
+    # per-kernel rooflines (SURVEY 8d): algorithmic work per step / CUDA-event time of that kernel.
+    # The contractions are charged 2 nbe^2 npts flops each for LDA and GGA alike; the LDA kernels EXECUTE
+    # half of that (triangular quadratic form for rho, SYRK for VXC): `frac_executed` is the honest pipe figure.
+    colloc_bytes = st["sum_nbe_npts"] * 8 * (4 if gga else 1) + 32.0 * st["npts"]
+
+    def tensor_entry(name, ms):
+        a = 0.5 * f_dense / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": name, "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": a / dmma_peak, "frac_executed": a / dmma_peak * (1.0 if gga else 0.5),
+                "ms_per_step": ms, "launches_per_step": nb,
+                "avg_launch_ms": ms / nb, "flops_per_launch": 0.5 * f_dense / nb}
+
+    per_kernel = [
+        {"kernel": "collocation_kernel", "bound": "hbm", "achieved": colloc_bytes / (k_ms[0] * 1e-3) / 1e9
+         if k_ms[0] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+         "frac": (colloc_bytes / (k_ms[0] * 1e-3) / 1e9 / hbm_peak) if k_ms[0] > 0 and hbm_peak else None,
+         "ms_per_step": k_ms[0], "launches_per_step": nb, "avg_launch_ms": k_ms[0] / nb,
+         "bytes_per_launch": colloc_bytes / nb},
+        tensor_entry("fused_xmat_den_zmat_kernel (X = P_sub B on DMMA + rho/grad rho + functional + Z factors)", k_ms[1]),
+        tensor_entry("vxc_kernel (Z on the fly, VXC_sub = B^T Z + Z^T B on DMMA + scatter-add)", k_ms[3]),
+    ]
+    dom = max(per_kernel[1:], key=lambda e: e["ms_per_step"])  # the dominant kernel of the step
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(workload, {}).get(dom["kernel"].split(" ")[0])
+    except Exception:
+        pass
+    dense_ms = k_ms[1] + k_ms[3]
+    roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dmma_peak,
+                "unit": "TFLOP/s", "frac": dom["frac"], "frac_executed": dom["frac_executed"],
+                "peak_source": "FP64 DMMA (mma.sync m8n8k4) register-resident probe run in this process "
+                               "(builder-probed peak; MEASURED_PEAKS.json holds HBM/bf16 only, tcgen05 has no FP64 kind)",
+                "flops_per_launch": dom["flops_per_launch"], "launches_per_step": nb,
+                "avg_launch_ms": dom["avg_launch_ms"], "traffic": traffic,
+                "both_contractions_tflops": f_dense / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0,
+                "kernel_ms_per_step": dict(zip(k_names, k_ms)),
+                "whole_path_fp64_frac": f_dense / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
+                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "per_kernel": per_kernel}
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
+    cpu = None
+    if full and world == 1 and not args.no_cpu_baseline:
+        tasks = s.lb.export_tasks()
+        cpu = oracle_sample(s, tasks, args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "blas", "gflops")}
+        del tasks
+
+    res = {"workload": workload, "value": value, "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / steps,
+           "grid_points": npts_total, "exc": exc_dev, "n_el": nel_dev, "ssf_weights_ms": ssf_ms, "setup_s": setup_s,
+           "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+           "parity": parity, "steps": steps, "warmup": warmup,
+           "config": workload_config(s, world),
+           "streamed_gb_per_step": st["sum_nbe_npts"] * 8 * (12 if gga else 4) / 1e9}
+    del integ, dP, dV, s
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -204,7 +441,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gauxc_b200 import capi
-    from gauxc_b200.driver import System, init_nccl_from_torch
+    from gauxc_b200.driver import init_nccl_from_torch
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -223,148 +460,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    s = System(args.workload, rank=rank, size=world, device=True, verbose=args.verbose and rank == 0)
-    ssf_ms = s.modify_weights()
-    integ = s.make_integrator("Default")
-    nbf = s.nbf
-    info = s.lb.task_info()
-    npts_local = int(info["npts"].sum())
-    npts_t = torch.tensor([float(npts_local)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(npts_t)
-    npts_total = int(npts_t.item())
-
-    # ---- device-resident arm -------------------------------------------------------------------
-    dP = torch.from_numpy(np.ascontiguousarray(s.P.T)).cuda()  # symmetric: layout agnostic
-    dV = torch.zeros((nbf, nbf), dtype=torch.float64, device="cuda")
-    dout = torch.zeros(2, dtype=torch.float64, device="cuda")
-    stream = torch.cuda.ExternalStream(integ.stream())
-    torch.cuda.synchronize()
-
-    def step_dev():
-        integ.eval_exc_vxc_device(dP.data_ptr(), dV.data_ptr(), dout.data_ptr())
-
-    for _ in range(args.warmup):
-        step_dev()
-    integ.set_profile(True)  # per-kernel CUDA events on the launching stream, read after the sync
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = np.zeros(4)
-    launches = 0
-    e0.record(stream)
-    t0 = time.time()
-    for _ in range(args.steps):
-        step_dev()
-        st = integ.stats()
-        kms += [st["k_colloc_ms"], st["k_xmat_ms"], st["k_zmat_ms"], st["k_vxc_ms"]]
-        launches += int(st["launches"])
-    e1.record(stream)
-    barrier()
-    wall_ms = (time.time() - t0) * 1e3
-    clocks = sampler.stop()
-    dev_ms = e0.elapsed_time(e1)
-    tt = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = float(tt[0]), float(tt[1])
-    ms_per_step = dev_ms / args.steps
-    value = npts_total / (ms_per_step * 1e-3)
-    exc_dev, nel_dev = [float(x) for x in dout.cpu()]
-    st = integ.stats()
-    integ.set_profile(False)
-
-    # ---- end-to-end arm: the reference-facing C-ABI call with host buffers -----------------------
-    Ph = torch.empty((nbf, nbf), dtype=torch.float64).pin_memory()
-    Ph.copy_(torch.from_numpy(np.ascontiguousarray(s.P.T)))
-    Vh = torch.empty((nbf, nbf), dtype=torch.float64).pin_memory()
-    Pn, Vn = Ph.numpy(), Vh.numpy()
-    for _ in range(max(1, min(args.warmup, 2))):
-        integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
-    barrier()
-    t0 = time.time()
-    e2e_dev_ms = 0.0
-    for _ in range(args.steps):
-        exc_h = integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
-        e2e_dev_ms += integ.stats()["total_ms"]
-    barrier()
-    e2e_wall_ms = (time.time() - t0) * 1e3
-    tt = torch.tensor([e2e_wall_ms, e2e_dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_ms = float(tt[0]) / args.steps  # wall clock of the blocking host call, max over ranks
-    e2e = {"value": npts_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "device_ms_per_step": float(tt[1]) / args.steps,
-           "h2d_bytes_per_step": int(nbf * nbf * 8), "d2h_bytes_per_step": int(nbf * nbf * 8 + 16),
-           "api": "gauxc_integrator_eval_exc_vxc_rks(host P, host VXC), pinned host buffers"}
-
-    # ---- roofline of the dominant kernel class (local rank 0 numbers) ------------------------------
-    peaks, peak_src = measured_peaks()
-    dmma_peak = capi.probe_peak("dmma")  # FP64 tensor peak is not in MEASURED_PEAKS.json: probe
-    f_dense = st["f_dense"]
-    k_names = ["collocation", "xmat_density(DMMA)", "func_zmat", "vxc(DMMA)"]
-    k_ms = (kms / args.steps).tolist()
-    nb = max(1, int(st["nbatches"]))
-    gga = s.func_name.upper().startswith("PBE")
-    hbm_peak = peaks.get("hbm_gbs")
-    # per-kernel rooflines: algorithmic work per step / CUDA-event time of that kernel.
-    # The contractions are charged 2 nbe^2 npts flops each for LDA and GGA alike (the LDA kernels
-    # execute about half of that: triangular quadratic form for rho, SYRK for VXC).
-    colloc_bytes = st["sum_nbe_npts"] * 8 * (4 if gga else 1) + 32.0 * st["npts"]
-
-    def tensor_entry(name, ms):
-        a = 0.5 * f_dense / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        return {"kernel": name, "bound": "tensor", "achieved": a, "peak": dmma_peak, "unit": "TFLOP/s",
-                "frac": a / dmma_peak, "ms_per_step": ms, "launches_per_step": nb,
-                "avg_launch_ms": ms / nb, "flops_per_launch": 0.5 * f_dense / nb}
-
-    per_kernel = [
-        {"kernel": "collocation_kernel", "bound": "hbm", "achieved": colloc_bytes / (k_ms[0] * 1e-3) / 1e9
-         if k_ms[0] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-         "frac": (colloc_bytes / (k_ms[0] * 1e-3) / 1e9 / hbm_peak) if k_ms[0] > 0 and hbm_peak else None,
-         "ms_per_step": k_ms[0], "launches_per_step": nb, "avg_launch_ms": k_ms[0] / nb,
-         "bytes_per_launch": colloc_bytes / nb},
-        tensor_entry("fused_xmat_den_zmat_kernel (X = P_sub B on DMMA + rho/grad rho + functional + Z)", k_ms[1]),
-        tensor_entry("vxc_kernel (VXC_sub = B^T Z + Z^T B on DMMA + scatter-add)", k_ms[3]),
-    ]
-    dom = max(per_kernel[1:], key=lambda e: e["ms_per_step"])  # the dominant kernel of the step
-    traffic = None
-    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = tj.get(args.workload, {}).get(dom["kernel"].split(" ")[0])
-    except Exception:
-        pass
-    dense_ms = k_ms[1] + k_ms[3]
-    roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dmma_peak,
-                "unit": "TFLOP/s", "frac": dom["frac"],
-                "peak_source": "FP64 DMMA (mma.sync m8n8k4) register-resident probe run in this process; "
-                               "MEASURED_PEAKS.json holds HBM/bf16 only (tcgen05 has no FP64 kind)",
-                "flops_per_launch": dom["flops_per_launch"], "launches_per_step": nb,
-                "avg_launch_ms": dom["avg_launch_ms"], "traffic": traffic,
-                "both_contractions_tflops": f_dense / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0,
-                "kernel_ms_per_step": dict(zip(k_names, k_ms)),
-                "whole_path_fp64_frac": f_dense / (ms_per_step * 1e-3) / 1e12 / dmma_peak,
-                "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "per_kernel": per_kernel}
-
-    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        tasks = s.lb.export_tasks()
-        cpu = oracle_sample(s, tasks, args.cpu_seconds)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "blas", "gflops")}
+    t_all = time.time()
+    head = run_workload(args, args.workload, args.steps, args.warmup, True, rank, local_rank, world, barrier)
+    others = {}
+    for w in [x for x in args.others.split(",") if x and x != args.workload]:
+        if time.time() - t_all > 420:  # keep the whole default run within minutes
+            others[w] = {"skipped": "time budget of the bench run"}
+            continue
+        r = run_workload(args, w, 3, 3, False, rank, local_rank, world, barrier)
+        others[w] = {"ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT, "grid_points": r["grid_points"],
+                     "nbf": r["config"]["nbf"], "workload": r["config"]["workload"],
+                     "e2e_ms_per_step": r["e2e"]["ms_per_step"] if r["e2e"] else None,
+                     "ssf_weights_ms": r["ssf_weights_ms"], "steps": r["steps"], "warmup": r["warmup"],
+                     "kernel_ms_per_step": r["roofline"]["kernel_ms_per_step"],
+                     "frac": {k["kernel"].split(" ")[0]: k["frac"] for k in r["roofline"]["per_kernel"]},
+                     "frac_executed": {k["kernel"].split(" ")[0]: k.get("frac_executed") for k in
+                                       r["roofline"]["per_kernel"][1:]},
+                     "whole_path_fp64_frac": r["roofline"]["whole_path_fp64_frac"], "parity": r["parity"],
+                     "exc": r["exc"], "n_el": r["n_el"]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(s, world, "per-step working set (B/dB/Z workspace, %.1f GB streamed) "
-                                          "far exceeds the 126 MB L2; no flush needed" %
-                                          (st["sum_nbe_npts"] * 8 * (6 if s.func_name.startswith("PBE") else 3) / 1e9)),
-                "grid_points": npts_total, "wall_ms_per_step": wall_ms / args.steps,
-                "exc": exc_dev, "n_el": nel_dev, "ssf_weights_ms": ssf_ms,
-                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "clocks": clocks}
+                "config": head["config"], "grid_points": head["grid_points"],
+                "wall_ms_per_step": head["wall_ms_per_step"], "exc": head["exc"], "n_el": head["n_el"],
+                "ssf_weights_ms": head["ssf_weights_ms"], "setup_s": head["setup_s"],
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+                "cpu_baseline": head["cpu_baseline"], "parity": head["parity"], "others": others,
+                "clocks": head["clocks"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

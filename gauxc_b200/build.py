@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-Wall,
           "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 SOURCES = [
-    "host/core.cxx", "host/grid.cxx", "host/load_balancer.cxx", "host/c_api.cxx",
+    "host/core.cxx", "host/grid.cxx", "host/load_balancer.cxx", "host/hdf5_io.cxx", "host/c_api.cxx",
     "host/device_integrator.cu",
     "cuda/collocation.cu", "cuda/fused.cu", "cuda/vxc.cu", "cuda/ssf_weights.cu", "cuda/probe.cu",
 ]

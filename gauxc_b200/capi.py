@@ -98,6 +98,7 @@ def lib():
         "gauxc_molecular_weights_modify_weights": (None, [S, _Handle, _Handle]),
         "gauxc_molecular_weights_delete": (None, [S, C.POINTER(_Handle)]),
         "gauxc_functional_from_string": (_Handle, [S, C.c_char_p, C.c_bool]),
+        "gauxc_functional_from_enum": (_Handle, [S, C.c_int, C.c_bool]),
         "gauxc_functional_delete": (None, [S, C.POINTER(_Handle)]),
         "gauxc_integrator_new": (_Handle, [S, _Handle, _Handle, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
         "gauxc_integrator_delete": (None, [S, C.POINTER(_Handle)]),
@@ -107,6 +108,10 @@ def lib():
         "gauxc_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
         "gauxc_integrator_eval_exc_vxc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
                                                      _dp, _dp, C.c_int64, _dp, C.c_int64]),
+        "gauxc_integrator_eval_exc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp]),
+        "gauxc_integrator_eval_exc_grad_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
+                                                      _dp]),
+        "gauxc_integrator_eval_exx_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64]),
         "gauxc_b200_nccl_get_unique_id": (None, [S, C.c_char_p]),
         "gauxc_b200_nccl_init": (None, [S, C.c_char_p, C.c_int, C.c_int]),
         "gauxc_b200_nccl_finalize": (None, [S]),
@@ -389,12 +394,26 @@ class MolecularWeightsFactory(_Obj):
         return MolecularWeights(_call("gauxc_molecular_weights_factory_get_instance", self.h))
 
 
+# include/gauxc/c/functional.h: enum GauXC_Functional (the members this build constructs)
+FunctionalEnum = dict(SVWN3=0, SVWN5=1, BLYP=2, B3LYP=3, PBE=4, revPBE=5, PBE0=6, SCAN=7, LDA=19, SPW92=22,
+                      VWN3=26, VWN5=27, revPBE0=34)
+
+
 class Functional(_Obj):
     _deleter = "gauxc_functional_delete"
 
     def __init__(self, spec, polarized=False):
         self.spec = spec
         super().__init__(_call("gauxc_functional_from_string", spec.encode(), polarized))
+
+    @classmethod
+    def from_enum(cls, value, polarized=False):
+        """gauxc_functional_from_enum (value: a FunctionalEnum name or the integer enumerator)."""
+        f = cls.__new__(cls)
+        f.spec = str(value)
+        v = FunctionalEnum[value] if isinstance(value, str) else int(value)
+        _Obj.__init__(f, _call("gauxc_functional_from_enum", v, polarized))
+        return f
 
     def eval_host(self, rho, sigma=None):
         rho = np.ascontiguousarray(rho, np.float64)
@@ -454,6 +473,22 @@ class XCIntegrator(_Obj):
         _call("gauxc_integrator_eval_exc_vxc_uks", self.h, m, n, _d(Psf), max(m, 1), _d(Pzf), max(m, 1),
               C.byref(exc), _d(vs), max(n, 1), _d(vz), max(n, 1))
         return exc.value, vs, vz
+
+    def eval_exc_uks(self, Ps, Pz):
+        Psf = np.asfortranarray(np.asarray(Ps, dtype=np.float64))
+        Pzf = np.asfortranarray(np.asarray(Pz, dtype=np.float64))
+        m, n = Psf.shape
+        exc = C.c_double(0.)
+        _call("gauxc_integrator_eval_exc_uks", self.h, m, n, _d(Psf), max(m, 1), _d(Pzf), max(m, 1), C.byref(exc))
+        return exc.value
+
+    def eval_exc_grad(self, P, natoms):
+        """RKS EXC gradient (3 * natoms)."""
+        Pf = np.asfortranarray(np.asarray(P, dtype=np.float64))
+        m, n = Pf.shape
+        g = np.zeros(3 * natoms)
+        _call("gauxc_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g))
+        return g
 
     def eval_exc_vxc_raw(self, m, n, P, ldp, vxc, ldv):
         exc = C.c_double(0.)

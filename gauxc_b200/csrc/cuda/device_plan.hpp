@@ -7,12 +7,15 @@
 //      incore_replicated_xc_device_integrator_exc_vxc.hpp:254-257).  Resident across calls.
 //   * a task is cut into TILES of <= TP consecutive points that share the task's shell list.
 //   * per batch of tiles a workspace holds, per tile, NMAT matrices [nbp][TP] (nbp = nbe
-//     rounded up to 16 rows, pad rows are zero): B, (dBx,dBy,dBz for GGA), Z.  Rows are 1 KB
-//     (point index fastest) and XOR-swizzled: element (row, i) lives at column
-//     i ^ ((row & 3) << 2).  With that one permutation a TMA box of 16 rows x 128 points (the
-//     A operand of X = B P) and a TMA box of 128 rows x 16 points (both operands of B^T Z)
-//     land in shared memory dense AND conflict-free for the m8n8k4 DMMA fragment loads,
-//     while every global row access stays fully coalesced.
+//     rounded up to 16 rows, pad rows are zero): B, (dBx,dBy,dBz for GGA), followed by FAC_ROWS
+//     rows of per-point factors (a, fx, fy, fz | the same for the z channel of UKS) written by
+//     the fused kernel: Z = a B + fx dBx + fy dBy + fz dBz is never stored, the VXC kernel forms
+//     it on the fly.  Matrix rows are 1 KB (point index fastest) and XOR-swizzled: element
+//     (row, i) lives at column i ^ ((row & 3) << 2).  With that one permutation a TMA box of
+//     16 rows x 128 points (the A operand of X = B P) and a box of 128 rows x 16 points (the
+//     B^T operand of B^T Z) land in shared memory dense AND conflict-free for the m8n8k4 DMMA
+//     fragment loads, while every global row access stays fully coalesced.  Factor rows are
+//     not swizzled.
 #pragma once
 #include <cstdint>
 
@@ -25,11 +28,14 @@
 namespace gxb {
 
 constexpr int TP = 128;  // points per tile
+constexpr int FAC_ROWS = 16;  // factor rows appended to a tile's matrices (8 used, 16 keeps row alignment)
 
 GXB_HOST_DEVICE inline int pad16(int nbe) { return (nbe + 15) & ~15; }
 // columns of a tile that are ever written / read: npts rounded up to 32
 GXB_HOST_DEVICE inline int tile_width(int npts) { return (npts + 31) & ~31; }
 GXB_HOST_DEVICE inline int swz(int row, int i) { return i ^ ((row & 3) << 2); }
+// workspace rows of one tile: nmat matrices of pad16(nbe) rows + the factor rows
+GXB_HOST_DEVICE inline int tile_rows(int nmat, int nbe) { return nmat * pad16(nbe) + FAC_ROWS; }
 
 struct DevShell {
   double x, y, z;
@@ -55,15 +61,17 @@ struct DevTile {
   int pad;
 };
 
-// one unit of the VXC rank update: output block (mblk,nblk) of one task, accumulated over a run of
-// `ntiles` consecutive tiles of that task in the current batch.  Self-contained (32 bytes, one
-// load): the tiles of a task lie back to back in the workspace (row stride nmat * pad16(nbe)),
-// all full (TP points = TP/16 K steps) except possibly the last one (nks_last K steps).
+// one unit of the VXC rank update: output block (mblk, nblk) of VXC_BLK x VXC_BLN of one task,
+// accumulated over a run of `ntiles` consecutive tiles of that task in the current batch.
+// Self-contained (32 bytes, one load): the tiles of a task lie back to back in the workspace (row
+// stride tile_rows(nmat, nbe)), all full (TP points = TP/16 K steps) except possibly the last one
+// (nks_last K steps).
 struct VxcItem {
   int nbe, ao_off, mblk, nblk;
   int row0, ntiles, nks_last, pad;  // row0: workspace row (ws_off / TP) of the first tile
 };
-constexpr int VXC_BLK = 128;  // output block edge of the VXC rank update
+constexpr int VXC_BLK = 128;  // output block rows (mu) of the VXC rank update
+constexpr int VXC_BLN = 64;   // output block columns (nu)
 
 struct PlanView {
   // static
@@ -82,7 +90,10 @@ struct PlanView {
 enum XcKind : int { XC_LDA = 0, XC_GGA = 1 };
 
 // functional = sum_k coeff_k * kernel_k  (ExchCXX XCFunctional semantics)
-enum KernelId : int { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5 };
+enum KernelId : int {
+  K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5,
+  K_B88_X = 6, K_LYP_C = 7, K_REVPBE_X = 8
+};
 struct FunctionalDesc {
   int nkern;
   int is_gga;

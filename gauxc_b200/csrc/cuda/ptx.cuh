@@ -44,11 +44,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps instead of hanging the GPU.
+// Spin on try_wait (which itself suspends the thread for a hardware time slice).  A protocol bug must not
+// hang the GPU for ever, but a legitimate wait can be long under preemption / MPS / profiler replay, so the
+// bound is generous: 2^26 failed probes (a minute or more), where a healthy wait takes a handful.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 20)) __trap();
+    if (++spins > (1u << 26)) __trap();
   }
 }
 // all prior cp.async of this thread arrive on the barrier when they complete
@@ -94,6 +96,9 @@ __device__ __forceinline__ void ldg256_stream(double (&v)[4], const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n"
                : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
                : "l"(p));
+}
+__device__ __forceinline__ void ldg128_stream(double (&v)[2], const double* p) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];\n" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
 }
 __device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]),

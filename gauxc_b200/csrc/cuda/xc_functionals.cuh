@@ -150,13 +150,27 @@ GXB_HD XcOut pbe_c(double rho, double sigma) {
   return o;
 }
 
+#ifndef GXB_VIA_POL_INLINE
+#define GXB_VIA_POL_INLINE __forceinline__
+#endif
+// B88 exchange / LYP correlation at zeta = 0 through the spin-resolved dual-number kernels
+// (xc_functionals_pol_gga.cuh); out of line: evaluated once per grid point, must not weigh on the
+// register allocation of the streaming loops around it
+#ifdef __CUDACC__
+__host__ __device__ GXB_VIA_POL_INLINE
+#endif
+XcOut eval_kernel_via_pol(int id, double rho, double sigma);
+
 GXB_HD XcOut eval_kernel(int id, double rho, double sigma) {
   switch (id) {
     case K_SLATER_X: return slater_x(rho);
     case K_VWN5_C: return vwn5_c(rho);
     case K_PW92_C: return pw92_c(rho);
     case K_PBE_X: return pbe_x(rho, sigma, 0.8040, 0.2195149727645171);
+    case K_REVPBE_X: return pbe_x(rho, sigma, 1.245, 0.2195149727645171);  // libxc gga_x_pbe_r
     case K_PBE_C: return pbe_c(rho, sigma);
+    case K_B88_X:
+    case K_LYP_C: return eval_kernel_via_pol(id, rho, sigma);
     default: return XcOut{0., 0., 0.};
   }
 }

@@ -6,8 +6,7 @@
 // evaluated once per grid point (~10^3 flop against ~10^5 of the contractions), so the 6x arithmetic
 // of the dual numbers is invisible next to the DMMA work.
 //
-// STATUS: host-verified against the oracle (tests/test_oracle_golden.py); not yet included by a
-// kernel -- the Device UKS GGA path is the next step.
+// Used by the fused kernel for the UKS GGA path and, at zeta = 0, for the unpolarised BLYP / B3LYP kernels.
 #pragma once
 #include "xc_functionals.cuh"
 
@@ -99,6 +98,28 @@ GXB_HD Dual5 lyp_c_energy(const Dual5& ra, const Dual5& rb, const Dual5& saa, co
 }
 
 enum PolGgaKernelId : int { PK_B88_X = 0, PK_LYP_C = 1 };
+
+// unpolarised limit: E(rho, sigma) = E_pol(rho/2, rho/2, sigma/4, sigma/4, sigma/4), so
+// vrho = dE/d rho_a and vsigma = (vaa + vab + vbb) / 4
+#ifdef __CUDACC__
+__host__ __device__ GXB_VIA_POL_INLINE
+#else
+inline
+#endif
+XcOut eval_kernel_via_pol(int id, double rho, double sigma) {
+  XcOut o{0., 0., 0.};
+  if (rho <= 1e-24) return o;
+  const Dual5 ra = dual_var(fmax(0.5 * rho, 1e-30), 0), rb = dual_var(fmax(0.5 * rho, 1e-30), 1);
+  const double q = 0.25 * fmax(sigma, 0.);
+  const Dual5 saa = dual_var(q, 2), sab = dual_var(q, 3), sbb = dual_var(q, 4);
+  Dual5 E(0.);
+  if (id == K_B88_X) E = b88_x_spin(ra, saa) + b88_x_spin(rb, sbb);
+  else if (id == K_LYP_C) E = lyp_c_energy(ra, rb, saa, sab, sbb);
+  o.eps = E.v / rho;
+  o.vrho = E.d[0];
+  o.vsigma = 0.25 * (E.d[2] + E.d[3] + E.d[4]);
+  return o;
+}
 
 struct XcOutPolGga {
   double eps, va, vb, vaa, vab, vbb;

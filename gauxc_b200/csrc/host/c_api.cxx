@@ -4,6 +4,7 @@
 #include "../../../include/gauxc_b200.h"
 #include "../cuda/xc_functionals.cuh"
 #include "../cuda/xc_functionals_pol_gga.cuh"
+#include "hdf5_io.hpp"
 #include "xc_integrator.hpp"
 #include <cstdlib>
 #include <cstring>
@@ -300,8 +301,8 @@ GauXCLoadBalancer gauxc_load_balancer_factory_get_instance(GauXCStatus* status,
                                                            const GauXCBasisSet basis) {
   GauXCLoadBalancer lb{{GauXC_Type_LoadBalancer}, nullptr};
   C_TRY(status)
-  checked<LBFactory>(factory.ptr, factory.hdr, GauXC_Type_LoadBalancerFactory, "LoadBalancerFactory");
-  lb.ptr = new LBPtr(std::make_shared<LoadBalancer>(*RT(env), *MOL(mol), *MG(mg), *BAS(basis)));
+  auto* f = checked<LBFactory>(factory.ptr, factory.hdr, GauXC_Type_LoadBalancerFactory, "LoadBalancerFactory");
+  lb.ptr = new LBPtr(std::make_shared<LoadBalancer>(*RT(env), *MOL(mol), *MG(mg), *BAS(basis), f->kernel));
   C_CATCH(status)
   return lb;
 }
@@ -351,6 +352,29 @@ GauXCFunctional gauxc_functional_from_string(GauXCStatus* status, const char* sp
   GauXCFunctional f{{GauXC_Type_Functional}, nullptr};
   C_TRY(status)
   f.ptr = new FuncPtr(std::make_shared<XCFunctional>(functional_from_string(spec ? spec : "", polarized)));
+  C_CATCH(status)
+  return f;
+}
+GauXCFunctional gauxc_functional_from_enum(GauXCStatus* status, enum GauXC_Functional functional_type,
+                                           bool polarized) {
+  // src/c-api/c_functional.cxx:96-114 (ExchCXX::Functional enumerators in the same order)
+  GauXCFunctional f{{GauXC_Type_Functional}, nullptr};
+  C_TRY(status)
+  const char* name = nullptr;
+  switch (functional_type) {
+    case GauXC_Functional_SVWN5: name = "SVWN5"; break;
+    case GauXC_Functional_BLYP: name = "BLYP"; break;
+    case GauXC_Functional_B3LYP: name = "B3LYP"; break;
+    case GauXC_Functional_PBE: name = "PBE"; break;
+    case GauXC_Functional_revPBE: name = "REVPBE"; break;
+    case GauXC_Functional_PBE0: name = "PBE0"; break;
+    case GauXC_Functional_LDA: name = "LDA"; break;
+    case GauXC_Functional_SPW92: name = "SPW92"; break;
+    case GauXC_Functional_VWN5: name = "VWN5"; break;
+    case GauXC_Functional_revPBE0: name = "REVPBE0"; break;
+    default: GAUXC_GENERIC_EXCEPTION("Functional NYI in B200 path: enum " + std::to_string((int)functional_type));
+  }
+  f.ptr = new FuncPtr(std::make_shared<XCFunctional>(functional_from_string(name, polarized)));
   C_CATCH(status)
   return f;
 }
@@ -438,11 +462,54 @@ void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrato
   INTG(integrator)->eval_exc_vxc_uks(m, n, Ps, ldps, Pz, ldpz, vxc_s, ldvs, vxc_z, ldvz, exc);
   C_CATCH(status)
 }
-void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator, const int64_t,
-                                        const int64_t, const double*, const int64_t, double*) {
+void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                        const int64_t n, const double* P, const int64_t ldp, double* exc_grad) {
   C_TRY(status)
-  GAUXC_GENERIC_EXCEPTION("EXC Gradient NYI in B200 path");
+  INTG(integrator)->eval_exc_grad(m, n, P, ldp, exc_grad);
   C_CATCH(status)
+}
+void gauxc_integrator_eval_exc_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                   const int64_t n, const double* Ps, const int64_t ldps, const double* Pz,
+                                   const int64_t ldpz, double* exc) {
+  C_TRY(status)
+  INTG(integrator)->eval_exc_uks(m, n, Ps, ldps, Pz, ldpz, exc);
+  C_CATCH(status)
+}
+// Entry points of include/gauxc/c/xc_integrator.h that lie outside the LDA/GGA RKS/UKS EXC/VXC path
+// (SURVEY.md section 8f): exported for link compatibility, status code 1 with a "NYI" message.
+#define GAUXC_B200_NYI(what)                                          \
+  C_TRY(status)                                                       \
+  GAUXC_GENERIC_EXCEPTION(what " NYI in B200 path");                  \
+  C_CATCH(status)
+void gauxc_integrator_eval_exc_gks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
+                                   const double*, const int64_t, const double*, const int64_t, const double*,
+                                   const int64_t, const double*, const int64_t, double*) {
+  GAUXC_B200_NYI("GKS EXC")
+}
+void gauxc_integrator_eval_exc_vxc_gks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
+                                       const double*, const int64_t, const double*, const int64_t, const double*,
+                                       const int64_t, const double*, const int64_t, double*, double*, const int64_t,
+                                       double*, const int64_t, double*, const int64_t, double*, const int64_t) {
+  GAUXC_B200_NYI("GKS EXC/VXC")
+}
+void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
+                                        const double*, const int64_t, const double*, const int64_t, double*) {
+  GAUXC_B200_NYI("UKS EXC Gradient")
+}
+void gauxc_integrator_eval_exx_rks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
+                                   const double*, const int64_t, double*, const int64_t) {
+  GAUXC_B200_NYI("EXX")
+}
+void gauxc_integrator_eval_fxc_contraction_rks(GauXCStatus* status, const GauXCIntegrator, const int64_t,
+                                               const int64_t, const double*, const int64_t, const double*,
+                                               const int64_t, double*, const int64_t) {
+  GAUXC_B200_NYI("FXC Contraction")
+}
+void gauxc_integrator_eval_fxc_contraction_uks(GauXCStatus* status, const GauXCIntegrator, const int64_t,
+                                               const int64_t, const double*, const int64_t, const double*,
+                                               const int64_t, const double*, const int64_t, const double*,
+                                               const int64_t, double*, const int64_t, double*, const int64_t) {
+  GAUXC_B200_NYI("FXC Contraction")
 }
 void gauxc_b200_integrator_eval_exc_vxc_rks_device(GauXCStatus* status, const GauXCIntegrator integrator,
                                                    const double* dP, double* dVXC, double* d_out2) {
@@ -463,6 +530,28 @@ void gauxc_b200_integrator_stats(GauXCStatus* status, const GauXCIntegrator inte
 void gauxc_b200_integrator_set_profile(GauXCStatus* status, const GauXCIntegrator integrator, int on) {
   C_TRY(status)
   INTG(integrator)->set_profile(on != 0);
+  C_CATCH(status)
+}
+
+// ---- include/gauxc/c/hdf5.h ----------------------------------------------------------------------------
+void gauxc_molecule_write_hdf5_record(GauXCStatus* status, GauXCMolecule mol, const char* fname, const char* dset) {
+  C_TRY(status)
+  write_hdf5_record(*MOL(mol), fname ? fname : "", dset ? dset : "");
+  C_CATCH(status)
+}
+void gauxc_basisset_write_hdf5_record(GauXCStatus* status, GauXCBasisSet basis, const char* fname, const char* dset) {
+  C_TRY(status)
+  write_hdf5_record(*BAS(basis), fname ? fname : "", dset ? dset : "");
+  C_CATCH(status)
+}
+void gauxc_molecule_read_hdf5_record(GauXCStatus* status, GauXCMolecule mol, const char* fname, const char* dset) {
+  C_TRY(status)
+  read_hdf5_record(*MOL(mol), fname ? fname : "", dset ? dset : "");
+  C_CATCH(status)
+}
+void gauxc_basisset_read_hdf5_record(GauXCStatus* status, GauXCBasisSet basis, const char* fname, const char* dset) {
+  C_TRY(status)
+  read_hdf5_record(*BAS(basis), fname ? fname : "", dset ? dset : "");
   C_CATCH(status)
 }
 
@@ -572,10 +661,14 @@ void gauxc_b200_load_balancer_set_tasks(GauXCStatus* status, GauXCLoadBalancer l
                                         int weights_are_modified) {
   C_TRY(status)
   auto& l = **LB(lb);
-  auto& tasks = l.get_tasks();
-  tasks.clear();
+  std::vector<XCTask> tasks;
+  tasks.reserve((size_t)ntasks);
+  const int32_t nsh_total = (int32_t)l.basis().size();
+  const int32_t natoms = (int32_t)l.molecule().size();
   size_t po = 0, so = 0;
   for (int64_t i = 0; i < ntasks; ++i) {
+    if (npts[i] < 0 || nshells[i] < 0) GAUXC_GENERIC_EXCEPTION("Invalid Task: negative size");
+    if (iParent[i] < 0 || iParent[i] >= natoms) GAUXC_GENERIC_EXCEPTION("Invalid Task: iParent out of range");
     XCTask t;
     t.iParent = iParent[i];
     t.npts = npts[i];
@@ -586,15 +679,23 @@ void gauxc_b200_load_balancer_set_tasks(GauXCStatus* status, GauXCLoadBalancer l
       t.points[p] = {points[3 * (po + p)], points[3 * (po + p) + 1], points[3 * (po + p) + 2]};
     t.bfn_screening.shell_list.assign(shell_lists + so, shell_lists + so + nshells[i]);
     int nbe = 0;
-    for (int s : t.bfn_screening.shell_list) nbe += l.basis().at(s).size();
+    int32_t prev = -1;
+    for (int s : t.bfn_screening.shell_list) {
+      // the kernels gather the lower triangle of P' / scatter distinct AO pairs: the list must be
+      // strictly ascending, as every list the LoadBalancer produces is
+      if (s <= prev || s >= nsh_total)
+        GAUXC_GENERIC_EXCEPTION("Invalid Task: shell_list must be strictly ascending and within the basis");
+      prev = s;
+      nbe += l.basis().at(s).size();
+    }
     t.bfn_screening.nbe = nbe;
     po += npts[i];
     so += nshells[i];
     tasks.push_back(std::move(t));
   }
+  l.replace_tasks(std::move(tasks));
   l.state().modified_weights_are_stored = weights_are_modified != 0;
   l.state().weight_alg = weights_are_modified ? XCWeightAlg::SSF : XCWeightAlg::NOTPARTITIONED;
-  l.touch();
   C_CATCH(status)
 }
 

@@ -91,6 +91,7 @@ struct Schedule {
 };
 
 struct DevicePlan {
+  int device = -1;  // the CUDA device the buffers live on
   int nbf = 0, natoms = 0;
   size_t npts = 0;
   std::vector<gxb::DevTask> tasks;
@@ -128,6 +129,7 @@ struct DevicePlan {
 static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
   require_device();
   auto plan = std::make_shared<DevicePlan>();
+  CUDA_CHECK(cudaGetDevice(&plan->device));
   auto& tasks = lb.get_tasks();
   const auto& basis = lb.basis();
   const auto& bmap = lb.basis_map();
@@ -308,6 +310,10 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
 
 std::shared_ptr<DevicePlan> get_device_plan(LoadBalancer& lb) {
   lb.get_tasks();
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  if (lb.device_cache && std::static_pointer_cast<DevicePlan>(lb.device_cache)->device != dev)
+    lb.device_cache.reset();  // the calling thread moved to another device: rebuild there
   if (!lb.device_cache || lb.device_cache_version != lb.version()) {
     lb.device_cache = build_plan(lb);
     lb.device_cache_version = lb.version();
@@ -332,8 +338,9 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
       int e = q;
       while (e < b.tile_end && sc->tiles[e].task == sc->tiles[q].task) ++e;
       const int nbe = plan.tasks[sc->tiles[q].task].nbe;
-      const int nb = (nbe + gxb::VXC_BLK - 1) / gxb::VXC_BLK;
-      const size_t need = (size_t)nmat * gxb::pad16(nbe) * gxb::TP;
+      const int nbm = (nbe + gxb::VXC_BLK - 1) / gxb::VXC_BLK;
+      const int nbn = (nbe + gxb::VXC_BLN - 1) / gxb::VXC_BLN;
+      const size_t need = (size_t)gxb::tile_rows(nmat, nbe) * gxb::TP;
       for (int c = q; c < e; c += tiles_per_item) {
         const int ce = std::min(e, c + tiles_per_item);
         for (int t = c; t < ce; ++t) {
@@ -342,8 +349,10 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
               (t + 1 < ce && sc->tiles[t].npts != gxb::TP))
             GAUXC_GENERIC_EXCEPTION("Inconsistent Tile Layout In VXC Item");
         }
-        for (int im = 0; im < nb; ++im)
-          for (int in = 0; in < (sym ? im + 1 : nb); ++in) {
+        for (int im = 0; im < nbm; ++im)
+          for (int in = 0; in < nbn; ++in) {
+            // symmetric M (LDA): only blocks that reach the lower triangle
+            if (sym && in * gxb::VXC_BLN > im * gxb::VXC_BLK + gxb::VXC_BLK - 1) continue;
             gxb::VxcItem it{};
             it.nbe = nbe;
             it.ao_off = plan.tasks[sc->tiles[q].task].ao_off;
@@ -364,7 +373,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
     // batches keep the task order (VXC regions stay L2-resident) -- their tail is negligible.
     auto cost = [](const gxb::VxcItem& x) {
       const long long rows = std::min(gxb::VXC_BLK, x.nbe - x.mblk * gxb::VXC_BLK);
-      const long long cols = std::min(gxb::VXC_BLK, x.nbe - x.nblk * gxb::VXC_BLK);
+      const long long cols = std::min(gxb::VXC_BLN, x.nbe - x.nblk * gxb::VXC_BLN);
       const long long nks = (long long)(x.ntiles - 1) * (gxb::TP / 16) + x.nks_last;
       return rows * cols * nks;
     };
@@ -381,7 +390,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
     ws_max = std::max(ws_max, cur);
   };
   for (int i = 0; i < (int)sc->tiles.size(); ++i) {
-    const size_t need = (size_t)nmat * gxb::pad16(plan.tasks[sc->tiles[i].task].nbe) * gxb::TP;
+    const size_t need = (size_t)gxb::tile_rows(nmat, plan.tasks[sc->tiles[i].task].nbe) * gxb::TP;
     if (need > ws_doubles) GAUXC_GENERIC_EXCEPTION("Device Workspace Too Small For One Tile");
     if (cur + need > ws_doubles) {
       close_batch(i);
@@ -395,7 +404,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
-  sc->d_counters.alloc(std::max<size_t>(1, 4 * sc->batches.size()));  // queue heads: fused, vxc (UKS: two each)
+  sc->d_counters.alloc(std::max<size_t>(1, 8 * sc->batches.size()));  // queue heads: fused, vxc (UKS: several each)
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
 }
@@ -457,11 +466,16 @@ XCFunctional functional_from_string(const std::string& spec_in, bool polarized) 
   else if (spec == "SPW92") set(false, {{K_SLATER_X, 1.}, {K_PW92_C, 1.}});
   else if (spec == "PBE") set(true, {{K_PBE_X, 1.}, {K_PBE_C, 1.}});
   else if (spec == "PBE0") { set(true, {{K_PBE_X, 0.75}, {K_PBE_C, 1.}}); f.hyb_exx = 0.25; }
+  else if (spec == "REVPBE") set(true, {{K_REVPBE_X, 1.}, {K_PBE_C, 1.}});
+  else if (spec == "REVPBE0") { set(true, {{K_REVPBE_X, 0.75}, {K_PBE_C, 1.}}); f.hyb_exx = 0.25; }
+  else if (spec == "BLYP") set(true, {{K_B88_X, 1.}, {K_LYP_C, 1.}});
+  // libxc hyb_gga_xc_b3lyp: 0.08 LDA_X + 0.72 B88 + 0.19 VWN_RPA + 0.81 LYP (+ 0.20 exact exchange, the caller's)
+  else if (spec == "B3LYP") { set(true, {{K_SLATER_X, 0.08}, {K_B88_X, 0.72}, {K_VWN5_C, 0.19}, {K_LYP_C, 0.81}}); f.hyb_exx = 0.20; }
   else GAUXC_GENERIC_EXCEPTION("Functional NYI in B200 path: " + spec_in);
   if (polarized) {
-    // UKS is implemented for the LDA kernels with a restated spin-polarised form (Slater, VWN5)
-    bool ok = !f.desc.is_gga;
-    for (int k = 0; k < f.desc.nkern; ++k) ok = ok && (f.desc.kern[k] == K_SLATER_X || f.desc.kern[k] == K_VWN5_C);
+    // spin-polarised forms exist for Slater, VWN (RPA set), B88, LYP, PBE exchange (spin scaling) and PBE correlation
+    bool ok = true;
+    for (int k = 0; k < f.desc.nkern; ++k) ok = ok && f.desc.kern[k] != K_PW92_C && f.desc.kern[k] != K_VWN3_C;
     if (!ok) GAUXC_GENERIC_EXCEPTION("Polarized (UKS) Functional NYI in B200 path: " + spec_in);
   }
   return f;
@@ -477,6 +491,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   void load() {
@@ -487,6 +502,7 @@ struct NcclApi {
     GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy)
@@ -510,6 +526,13 @@ struct NCCLReductionDriver : ReductionDriver {
   void allreduce_inplace(double* data, size_t n, ReductionOp, void* stream) override {
     if (!g_comm) GAUXC_GENERIC_EXCEPTION("NCCL FAILED: communicator not initialised");
     auto r = g_nccl.AllReduce(data, data, n, ncclDouble, ncclSum, g_comm, (cudaStream_t)stream);
+    if (r != ncclSuccess) GAUXC_GENERIC_EXCEPTION("NCCL FAILED");
+  }
+  bool can_allgather() const override { return g_nccl.AllGather != nullptr; }
+  void allgather_inplace(double* data, size_t count_per_rank, void* stream) override {
+    if (!g_comm) GAUXC_GENERIC_EXCEPTION("NCCL FAILED: communicator not initialised");
+    auto r = g_nccl.AllGather(data + (size_t)g_comm_rank * count_per_rank, data, count_per_rank, ncclDouble, g_comm,
+                              (cudaStream_t)stream);
     if (r != ncclSuccess) GAUXC_GENERIC_EXCEPTION("NCCL FAILED");
   }
 };
@@ -608,8 +631,8 @@ struct XCIntegrator::Impl {
   cudaStream_t copy_stream = nullptr;  // H2D of P overlaps the collocation of the first batch
   cudaEvent_t e_p_ready{};
   bool p_pending = false;  // set by the host-buffer entry points: wait for e_p_ready before P is read
-  DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2;
-  DevBuf<double> dPz, dPtri_z, dVXCz, d_uks_den;  // UKS: z density / potential, rho_s per point
+  DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2, d_pack;
+  DevBuf<double> dPz, dPtri_z, dVXCz, d_uks_den;  // UKS: z density / potential, densities per point
   gxb::TmapSet tmapA{};  // TMA views of d_ws: 16 rows x (32..128) points
   CUtensorMap tmapV{};   // 128 rows x 16 points
   int ncta = 0;
@@ -620,17 +643,84 @@ struct XCIntegrator::Impl {
   std::vector<cudaEvent_t> ev;  // profile mode: 5 events per batch, read after the final sync
   cudaEvent_t e_begin{}, e_lw0{}, e_lw1{}, e_end{};
   double* h_out2 = nullptr;  // pinned
-  double* h_pin = nullptr;   // pinned staging for P / VXC
-  size_t h_pin_n = 0;
   ~Impl() {
     for (auto e : ev) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (e_p_ready) cudaEventDestroy(e_p_ready);
     if (h_out2) cudaFreeHost(h_out2);
-    if (h_pin) cudaFreeHost(h_pin);
   }
+
+  // plan + schedule + workspace + TMA views for tiles of `nmat` matrices (1: B; 4: B, dBx, dBy, dBz)
+  void prepare(LoadBalancer& lb, int nmat, bool sym);
+  // P (nbf x nbf, ld = nbf) and VXC buffers of the host-buffer entry points; P is padded so that an
+  // all-gather of per-rank column slabs fits
+  void ensure_matrices(size_t nbf, int nranks, bool uks);
 };
+
+static size_t workspace_bytes(const LoadBalancer& lb) {
+  if (const char* e = std::getenv("GAUXC_B200_WORKSPACE_MB")) return (size_t)std::atoll(e) << 20;
+  size_t free_b = 0, tot_b = 0;
+  cudaMemGetInfo(&free_b, &tot_b);
+  double frac = 0.9;
+  if (auto* d = dynamic_cast<const DeviceRuntimeEnvironment*>(&lb.runtime()))
+    if (d->fill_fraction() > 0.) frac = d->fill_fraction();
+  size_t cap = (size_t)16 << 30;  // default: 16 GiB of B / dB workspace per batch
+  if (const char* e = std::getenv("GAUXC_DEVICE_MEMORY_CAP")) cap = (size_t)std::atoll(e);
+  return std::min<size_t>(cap, (size_t)(frac * free_b * 0.8));
+}
+
+void XCIntegrator::Impl::prepare(LoadBalancer& lb, int nmat, bool sym) {
+  {
+    auto np = get_device_plan(lb);
+    if (np != plan) {
+      plan = np;
+      sched.reset();
+    }
+  }
+  if (plan->nbf && (size_t)plan->nbf * plan->nbf > (size_t)std::numeric_limits<int>::max() * 64)
+    GAUXC_GENERIC_EXCEPTION("Basis Too Large");
+  if (sched && sched_nmat == nmat) return;
+  auto it = plan->schedules.find(nmat);
+  if (it == plan->schedules.end()) {
+    const size_t wsb = workspace_bytes(lb);
+    int tpi = 16;
+    if (const char* e = std::getenv("GAUXC_B200_TILES_PER_ITEM")) tpi = std::max(1, std::atoi(e));
+    if (!ncta) {
+      int dev = 0;
+      CUDA_CHECK(cudaGetDevice(&dev));
+      CUDA_CHECK(cudaDeviceGetAttribute(&ncta, cudaDevAttrMultiProcessorCount, dev));
+    }
+    plan->schedules[nmat] = build_schedule(*plan, nmat, wsb / sizeof(double), tpi, ncta, sym);
+    plan->schedule_ws_bytes = wsb;
+    it = plan->schedules.find(nmat);
+  }
+  sched = it->second;
+  sched_nmat = nmat;
+  d_ws.alloc(sched->ws_doubles);
+  if (sched->ws_doubles) {
+    // TMA may read (never use) rows of a neighbouring matrix: keep every byte finite
+    CUDA_CHECK(cudaMemsetAsync(d_ws.p, 0, sched->ws_doubles * sizeof(double), stream));
+    for (int w = 0; w < 4; ++w) tmapA.m[w] = make_ws_tensor_map(d_ws.p, sched->ws_doubles, 32 * (w + 1), 16);
+    tmapV = make_ws_tensor_map(d_ws.p, sched->ws_doubles, 16, gxb::VXC_BLK);
+  }
+  d_exc_part.alloc(std::max<size_t>(1, sched->tiles.size()));
+  d_nel_part.alloc(std::max<size_t>(1, sched->tiles.size()));
+}
+
+void XCIntegrator::Impl::ensure_matrices(size_t nbf, int nranks, bool uks) {
+  const size_t cpr = (nbf + nranks - 1) / std::max(1, nranks);  // columns per rank slab
+  const size_t np = std::max(nbf * nbf, cpr * nranks * nbf);
+  if (dP.n != np) {
+    dP.alloc(np);
+    dVXC.alloc(nbf * nbf);
+    d_out2.alloc(2);
+  }
+  if (uks && dPz.n != np) {
+    dPz.alloc(np);
+    dVXCz.alloc(nbf * nbf);
+  }
+}
 
 XCIntegrator::XCIntegrator(ExecutionSpace ex, const std::string& input_type,
                            const std::string& integrator_kernel, const std::string& lwd_kernel,
@@ -668,16 +758,29 @@ XCIntegrator::~XCIntegrator() = default;
 void XCIntegrator::set_profile(bool on) { impl_->profile = on; }
 void* XCIntegrator::stream() const { return impl_->stream; }
 
-static size_t workspace_bytes(const LoadBalancer& lb) {
-  if (const char* e = std::getenv("GAUXC_B200_WORKSPACE_MB")) return (size_t)std::atoll(e) << 20;
-  size_t free_b = 0, tot_b = 0;
-  cudaMemGetInfo(&free_b, &tot_b);
-  double frac = 0.9;
-  if (auto* d = dynamic_cast<const DeviceRuntimeEnvironment*>(&lb.runtime()))
-    if (d->fill_fraction() > 0.) frac = d->fill_fraction();
-  size_t cap = (size_t)16 << 30;  // default: 16 GiB of B/Z workspace per batch
-  if (const char* e = std::getenv("GAUXC_DEVICE_MEMORY_CAP")) cap = (size_t)std::atoll(e);
-  return std::min<size_t>(cap, (size_t)(frac * free_b * 0.8));
+// Sum over the ranks of the lower triangle(s) of VXC and of {EXC, N_EL} in ONE collective
+// (incore_replicated_xc_device_integrator_exc_vxc.hpp:158-162 reduces VXC, EXC and N_EL one by one, full
+// matrices): pack [tril(VXC) | (tril(VXCz)) | EXC | N_EL] -> allreduce -> unpack + mirror.  Single rank:
+// symmetrise in place.
+void XCIntegrator::reduce_and_symmetrize_(double* dV, double* dVz, double* d_out2, int nbf, bool do_vxc) {
+  auto& I = *impl_;
+  cudaStream_t s = I.stream;
+  const int nmatv = do_vxc ? (dVz ? 2 : 1) : 0;
+  if (red_->comm_size() <= 1) {
+    if (nmatv >= 1) gxb::launch_symmetrize(dV, nbf, nbf, s);
+    if (nmatv == 2) gxb::launch_symmetrize(dVz, nbf, nbf, s);
+    return;
+  }
+  const size_t ntri = (size_t)nbf * (nbf + 1) / 2;
+  const size_t total = nmatv * ntri + 2;
+  if (I.d_pack.n < total) I.d_pack.alloc(total);
+  if (nmatv >= 1) gxb::launch_pack_tril(dV, nbf, nbf, I.d_pack.p, s);
+  if (nmatv == 2) gxb::launch_pack_tril(dVz, nbf, nbf, I.d_pack.p + ntri, s);
+  CUDA_CHECK(cudaMemcpyAsync(I.d_pack.p + nmatv * ntri, d_out2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  red_->allreduce_inplace(I.d_pack.p, total, ReductionOp::Sum, s);
+  if (nmatv >= 1) gxb::launch_unpack_tril_sym(I.d_pack.p, dV, nbf, nbf, s);
+  if (nmatv == 2) gxb::launch_unpack_tril_sym(I.d_pack.p + ntri, dVz, nbf, nbf, s);
+  CUDA_CHECK(cudaMemcpyAsync(d_out2, I.d_pack.p + nmatv * ntri, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
 void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d_out2, bool do_vxc) {
@@ -685,48 +788,11 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   if (func_->polarized) GAUXC_GENERIC_EXCEPTION("RKS Evaluation Requires An Unpolarized Functional");
   if (!lb_->state().modified_weights_are_stored)
     GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
-  {
-    auto np = get_device_plan(*lb_);
-    if (np != I.plan) {
-      I.plan = np;
-      I.sched.reset();
-    }
-  }
-  auto& plan = *I.plan;
   const bool gga = func_->is_gga();
-  const int nmat = gga ? 5 : 2;
+  const int nmat = gga ? 4 : 1;
+  I.prepare(*lb_, nmat, !gga);
+  auto& plan = *I.plan;
   cudaStream_t s = I.stream;
-  if (plan.nbf && (size_t)plan.nbf * plan.nbf > (size_t)std::numeric_limits<int>::max() * 64)
-    GAUXC_GENERIC_EXCEPTION("Basis Too Large");
-
-  if (!I.sched || I.sched_nmat != nmat) {
-    auto it = plan.schedules.find(nmat);
-    if (it == plan.schedules.end()) {
-      const size_t wsb = workspace_bytes(*lb_);
-      int tpi = 16;
-      if (const char* e = std::getenv("GAUXC_B200_TILES_PER_ITEM")) tpi = std::max(1, std::atoi(e));
-      if (!I.ncta) {
-        int dev = 0;
-        CUDA_CHECK(cudaGetDevice(&dev));
-        CUDA_CHECK(cudaDeviceGetAttribute(&I.ncta, cudaDevAttrMultiProcessorCount, dev));
-      }
-      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), tpi, I.ncta, !gga);
-      plan.schedule_ws_bytes = wsb;
-      it = plan.schedules.find(nmat);
-    }
-    I.sched = it->second;
-    I.sched_nmat = nmat;
-    I.d_ws.alloc(I.sched->ws_doubles);
-    if (I.sched->ws_doubles) {
-      // TMA may read (never use) rows of a neighbouring matrix: keep every byte finite
-      CUDA_CHECK(cudaMemsetAsync(I.d_ws.p, 0, I.sched->ws_doubles * sizeof(double), s));
-      for (int w = 0; w < 4; ++w)
-        I.tmapA.m[w] = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 32 * (w + 1), 16);
-      I.tmapV = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 16, gxb::VXC_BLK);
-    }
-    I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
-    I.d_nel_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
-  }
   auto& sc = *I.sched;
   const gxb::PlanView pv = plan.view();
   const int nbf = plan.nbf;
@@ -772,14 +838,15 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
     if (ev) CUDA_CHECK(cudaEventRecord(ev[1], s));
     if (ib == 0) first_use_of_P();
-    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, dP, nbf,
-                      func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s);
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, dP, nbf,
+                                 func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s));
     if (ev) CUDA_CHECK(cudaEventRecord(ev[2], s));
     if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
     launches += 2;
     if (do_vxc) {
-      gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                      sc.d_counters.p + sc.batches.size() + ib, sc.ncta, gga ? 4 : 1, nmat, !gga, dVXC, nbf, s);
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + sc.batches.size() + ib, sc.ncta, I.d_ws.p, gga, 0, !gga,
+                                 dVXC, nbf, s));
       ++launches;
     }
     if (ev) CUDA_CHECK(cudaEventRecord(ev[4], s));
@@ -788,18 +855,13 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   if (sc.batches.empty()) first_use_of_P();  // nothing consumed P: still retire the pending upload
   gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), d_out2, s);
   ++launches;
-  if (do_vxc) {
-    gxb::launch_symmetrize(dVXC, nbf, nbf, s);
-    ++launches;
-  }
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(I.e_lw1, s));
 
-  // replicated-data reduction over the ranks (…exc_vxc.hpp:158-162)
-  if (red_->comm_size() > 1) {
-    if (do_vxc) red_->allreduce_inplace(dVXC, (size_t)nbf * nbf, ReductionOp::Sum, s);
-    red_->allreduce_inplace(d_out2, 2, ReductionOp::Sum, s);
-  }
+  // replicated-data reduction over the ranks + upper <- lower
+  reduce_and_symmetrize_(dVXC, nullptr, d_out2, nbf, do_vxc);
+  launches += do_vxc ? (red_->comm_size() > 1 ? 2 : 1) : 0;
+  CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaStreamSynchronize(s));
   if (I.profile)
     for (size_t q = 0; q < sc.batches.size(); ++q)
@@ -832,6 +894,43 @@ static void check_dims(const LoadBalancer& lb, int64_t m, int64_t n, int64_t ldp
   if (vxc && ldv < nbf) GAUXC_GENERIC_EXCEPTION("Invalid LDVXC");
 }
 
+// Host P -> device, on the copy stream.  One rank: one copy.  Several ranks of one box (the contract
+// replicates P in every rank's host memory): every rank uploads only its slab of columns over its own
+// PCIe link and the slabs are all-gathered over NVLink -- the host links carry nbf^2 * 8 bytes per box
+// instead of per GPU (the reference uploads the full matrix on every rank,
+// xc_device_stack_data.cxx:350-384).
+void XCIntegrator::upload_density_(const double* P, int64_t ldp, double* dP, size_t nbf) {
+  auto& I = *impl_;
+  const int nr = red_->comm_size();
+  auto copy_cols = [&](size_t c0, size_t c1) {
+    if (c1 <= c0) return;
+    if ((size_t)ldp == nbf)
+      CUDA_CHECK(cudaMemcpyAsync(dP + c0 * nbf, P + c0 * nbf, (c1 - c0) * nbf * sizeof(double),
+                                 cudaMemcpyHostToDevice, I.copy_stream));
+    else
+      CUDA_CHECK(cudaMemcpy2DAsync(dP + c0 * nbf, nbf * sizeof(double), P + c0 * ldp, ldp * sizeof(double),
+                                   nbf * sizeof(double), c1 - c0, cudaMemcpyHostToDevice, I.copy_stream));
+  };
+  size_t min_slab = (size_t)4 << 20;  // below 4 MB per slab the collective costs more than it saves
+  if (const char* e = std::getenv("GAUXC_B200_SLAB_UPLOAD_MIN_BYTES")) min_slab = (size_t)std::atoll(e);
+  const size_t cpr = (nbf + nr - 1) / nr;
+  if (nr > 1 && red_->can_allgather() && cpr * nbf * sizeof(double) >= min_slab) {
+    const size_t r = (size_t)lb_->runtime().comm_rank();
+    copy_cols(std::min(nbf, r * cpr), std::min(nbf, (r + 1) * cpr));
+    red_->allgather_inplace(dP, cpr * nbf, I.copy_stream);
+  } else {
+    copy_cols(0, nbf);
+  }
+}
+
+static void download_matrix(double* H, int64_t ldh, const double* D, size_t nbf, cudaStream_t s) {
+  if ((size_t)ldh == nbf)
+    CUDA_CHECK(cudaMemcpyAsync(H, D, nbf * nbf * sizeof(double), cudaMemcpyDeviceToHost, s));
+  else
+    CUDA_CHECK(cudaMemcpy2DAsync(H, ldh * sizeof(double), D, nbf * sizeof(double), nbf * sizeof(double), nbf,
+                                 cudaMemcpyDeviceToHost, s));
+}
+
 void XCIntegrator::eval_exc_vxc(int64_t m, int64_t n, const double* P, int64_t ldp, double* VXC,
                                 int64_t ldvxc, double* EXC) {
   check_dims(*lb_, m, n, ldp, ldvxc, true);
@@ -840,20 +939,14 @@ void XCIntegrator::eval_exc_vxc(int64_t m, int64_t n, const double* P, int64_t l
   auto& I = *impl_;
   const size_t nbf = (size_t)m;
   cudaStream_t s = I.stream;
-  if (I.dP.n != nbf * nbf) {
-    I.dP.alloc(nbf * nbf);
-    I.dVXC.alloc(nbf * nbf);
-    I.d_out2.alloc(2);
-  }
+  I.ensure_matrices(nbf, red_->comm_size(), false);
   CUDA_CHECK(cudaEventRecord(I.e_begin, s));
   CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
-  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), P, ldp * sizeof(double),
-                               nbf * sizeof(double), nbf, cudaMemcpyHostToDevice, I.copy_stream));
+  upload_density_(P, ldp, I.dP.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   I.p_pending = true;
   eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, true);
-  CUDA_CHECK(cudaMemcpy2DAsync(VXC, ldvxc * sizeof(double), I.dVXC.p, nbf * sizeof(double),
-                               nbf * sizeof(double), nbf, cudaMemcpyDeviceToHost, s));
+  download_matrix(VXC, ldvxc, I.dVXC.p, nbf, s);
   CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaEventRecord(I.e_end, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -869,32 +962,77 @@ void XCIntegrator::eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, 
   auto& I = *impl_;
   const size_t nbf = (size_t)m;
   cudaStream_t s = I.stream;
-  if (I.dP.n != nbf * nbf) {
-    I.dP.alloc(nbf * nbf);
-    I.dVXC.alloc(nbf * nbf);
-    I.d_out2.alloc(2);
-  }
-  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), P, ldp * sizeof(double),
-                               nbf * sizeof(double), nbf, cudaMemcpyHostToDevice, I.copy_stream));
+  I.ensure_matrices(nbf, red_->comm_size(), false);
+  CUDA_CHECK(cudaEventRecord(I.e_begin, s));
+  CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
+  upload_density_(P, ldp, I.dP.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   I.p_pending = true;
-  eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, false);
+  eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, false);  // reduces {EXC, N_EL} over the ranks
   CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   *EXC = I.h_out2[0];
   stats_.n_el = I.h_out2[1];
 }
 
-// UKS, LDA functionals: Ps = P_alpha + P_beta, Pz = P_alpha - P_beta
+// integrate_den (incore_replicated_xc_device_integrator_integrate_den.hpp): N = sum_i w_i B_i^T P B_i with
+// X = 1.0 * P * B -- collocation + the density half of the fused kernel only; no functional, no Z factors
+// that anything reads, no VXC kernel.  The fused kernel carries the RKS factor 2, so halve.
+void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL) {
+  check_dims(*lb_, m, n, ldp, 0, false);
+  auto& I = *impl_;
+  const size_t nbf = (size_t)m;
+  cudaStream_t s = I.stream;
+  I.ensure_matrices(nbf, red_->comm_size(), false);
+  CUDA_CHECK(cudaEventRecord(I.e_begin, s));
+  CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
+  upload_density_(P, ldp, I.dP.p, nbf);
+  CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
+  I.prepare(*lb_, 1, true);
+  auto& plan = *I.plan;
+  auto& sc = *I.sched;
+  const gxb::PlanView pv = plan.view();
+  const int inbf = plan.nbf;
+  if (I.dPtri.n != nbf * nbf) {
+    I.dPtri.alloc(nbf * nbf);
+    CUDA_CHECK(cudaMemsetAsync(I.dPtri.p, 0, sizeof(double) * nbf * nbf, s));
+  }
+  CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
+  gxb::launch_sym_half(I.dP.p, inbf, I.dPtri.p, inbf, s);
+  gxb::FunctionalDesc none{};  // nkern = 0: eps = vrho = 0, only N_EL is accumulated
+  long long launches = 1;
+  size_t ib = 0;
+  for (auto& b : sc.batches) {
+    const int nt = b.tile_end - b.tile_begin;
+    const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
+    gxb::launch_collocation(pv, tl, nt, I.d_ws.p, false, s);
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, I.dPtri.p, inbf,
+                                 none, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s));
+    launches += 2;
+    ++ib;
+  }
+  gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), I.d_out2.p, s);
+  ++launches;
+  CUDA_CHECK(cudaGetLastError());
+  if (red_->comm_size() > 1) red_->allreduce_inplace(I.d_out2.p, 2, ReductionOp::Sum, s);
+  CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  stats_.kernel_launches = launches;
+  stats_.n_el = I.h_out2[1];
+  *N_EL = 0.5 * I.h_out2[1];
+}
+
+// UKS: Ps = P_alpha + P_beta, Pz = P_alpha - P_beta
 // (reference_replicated_xc_host_integrator_exc_vxc.hpp:107-601 with is_uks; device counterpart
-// incore_replicated_xc_device_integrator_exc_vxc.hpp:46-386).  Per batch: collocation, the fused kernel
-// over Ps (rho_s per point), the fused kernel over Pz (rho_z -> rho_+- -> polarised functional -> Z_s,
-// Z_z), the VXC rank update twice.
-void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz,
-                                    int64_t ldpz, double* VXCs, int64_t ldvxcs, double* VXCz,
-                                    int64_t ldvxcz, double* EXC) {
-  check_dims(*lb_, m, n, ldps, ldvxcs, true);
-  check_dims(*lb_, m, n, ldpz, ldvxcz, true);
+// incore_replicated_xc_device_integrator_exc_vxc.hpp:46-386).  LDA, per batch: collocation, the fused kernel
+// over Ps (rho_s per point), the fused kernel over Pz (rho_z -> rho_+- -> polarised functional -> factors of
+// Z_s and Z_z), the VXC rank update twice (factor rows 0 and 4).
+void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
+                             double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC,
+                             bool do_vxc) {
+  check_dims(*lb_, m, n, ldps, ldvxcs, do_vxc);
+  check_dims(*lb_, m, n, ldpz, ldvxcz, do_vxc);
   if (!lb_->state().modified_weights_are_stored) GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
   if (!func_->polarized) GAUXC_GENERIC_EXCEPTION("UKS Evaluation Requires A Polarized Functional");
   if (func_->is_gga()) GAUXC_GENERIC_EXCEPTION("UKS GGA NYI in B200 path");
@@ -902,52 +1040,33 @@ void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int6
   cudaStream_t s = I.stream;
   const size_t nbf = (size_t)m;
   const size_t nn = nbf * nbf;
-  if (I.dP.n != nn) { I.dP.alloc(nn); I.dVXC.alloc(nn); I.d_out2.alloc(2); }
-  if (I.dPz.n != nn) { I.dPz.alloc(nn); I.dVXCz.alloc(nn); I.dPtri_z.alloc(nn); }
-  if (I.dPtri.n != nn) I.dPtri.alloc(nn);
+  I.ensure_matrices(nbf, red_->comm_size(), true);
+  if (I.dPtri.n != nn) {
+    I.dPtri.alloc(nn);
+    CUDA_CHECK(cudaMemsetAsync(I.dPtri.p, 0, sizeof(double) * nn, s));
+  }
+  if (I.dPtri_z.n != nn) {
+    I.dPtri_z.alloc(nn);
+    CUDA_CHECK(cudaMemsetAsync(I.dPtri_z.p, 0, sizeof(double) * nn, s));
+  }
   CUDA_CHECK(cudaEventRecord(I.e_begin, s));
-  CUDA_CHECK(cudaMemcpy2DAsync(I.dP.p, nbf * sizeof(double), Ps, ldps * sizeof(double), nbf * sizeof(double),
-                               nbf, cudaMemcpyHostToDevice, s));
-  CUDA_CHECK(cudaMemcpy2DAsync(I.dPz.p, nbf * sizeof(double), Pz, ldpz * sizeof(double), nbf * sizeof(double),
-                               nbf, cudaMemcpyHostToDevice, s));
-  {
-    auto np = get_device_plan(*lb_);
-    if (np != I.plan) { I.plan = np; I.sched.reset(); }
-  }
+  CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
+  upload_density_(Ps, ldps, I.dP.p, nbf);
+  upload_density_(Pz, ldpz, I.dPz.p, nbf);
+  CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
+  I.prepare(*lb_, 1, true);
   auto& plan = *I.plan;
-  const int nmat = 3;  // B, Z_s, Z_z
-  if (!I.sched || I.sched_nmat != nmat) {
-    auto it = plan.schedules.find(nmat);
-    if (it == plan.schedules.end()) {
-      const size_t wsb = workspace_bytes(*lb_);
-      if (!I.ncta) {
-        int dev = 0;
-        CUDA_CHECK(cudaGetDevice(&dev));
-        CUDA_CHECK(cudaDeviceGetAttribute(&I.ncta, cudaDevAttrMultiProcessorCount, dev));
-      }
-      plan.schedules[nmat] = build_schedule(plan, nmat, wsb / sizeof(double), 16, I.ncta, true);
-      it = plan.schedules.find(nmat);
-    }
-    I.sched = it->second;
-    I.sched_nmat = nmat;
-    I.d_ws.alloc(I.sched->ws_doubles);
-    if (I.sched->ws_doubles) {
-      CUDA_CHECK(cudaMemsetAsync(I.d_ws.p, 0, I.sched->ws_doubles * sizeof(double), s));
-      for (int w = 0; w < 4; ++w)
-        I.tmapA.m[w] = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 32 * (w + 1), 16);
-      I.tmapV = make_ws_tensor_map(I.d_ws.p, I.sched->ws_doubles, 16, gxb::VXC_BLK);
-    }
-    I.d_exc_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
-    I.d_nel_part.alloc(std::max<size_t>(1, I.sched->tiles.size()));
-  }
   if (I.d_uks_den.n < plan.npts) I.d_uks_den.alloc(std::max<size_t>(1, plan.npts));
   auto& sc = *I.sched;
   const gxb::PlanView pv = plan.view();
   const int inbf = plan.nbf;
   const size_t nb = sc.batches.size();
 
-  CUDA_CHECK(cudaMemsetAsync(I.dVXC.p, 0, sizeof(double) * nn, s));
-  CUDA_CHECK(cudaMemsetAsync(I.dVXCz.p, 0, sizeof(double) * nn, s));
+  if (do_vxc) {
+    CUDA_CHECK(cudaMemsetAsync(I.dVXC.p, 0, sizeof(double) * nn, s));
+    CUDA_CHECK(cudaMemsetAsync(I.dVXCz.p, 0, sizeof(double) * nn, s));
+  }
   CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
   CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
   gxb::launch_sym_half(I.dP.p, inbf, I.dPtri.p, inbf, s);
@@ -958,32 +1077,35 @@ void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int6
     const int nt = b.tile_end - b.tile_begin;
     const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
     gxb::launch_collocation(pv, tl, nt, I.d_ws.p, false, s);
-    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, I.dPtri.p, inbf, func_->desc,
-                      I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 1, I.d_uks_den.p);
-    gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + nb + ib, sc.ncta, I.d_ws.p, I.dPtri_z.p, inbf,
-                      func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 2, I.d_uks_den.p);
-    gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                    sc.d_counters.p + 2 * nb + ib, sc.ncta, 1, nmat, true, I.dVXC.p, inbf, s);
-    gxb::launch_vxc(I.tmapV, pv, tl, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                    sc.d_counters.p + 3 * nb + ib, sc.ncta, 2, nmat, true, I.dVXCz.p, inbf, s);
-    launches += 5;
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, I.dPtri.p, inbf,
+                                 func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 1, I.d_uks_den.p));
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + nb + ib, sc.ncta, I.d_ws.p, I.dPtri_z.p,
+                                 inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 2,
+                                 I.d_uks_den.p));
+    launches += 3;
+    if (do_vxc) {
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + 2 * nb + ib, sc.ncta, I.d_ws.p, false, 0, true, I.dVXC.p, inbf,
+                                 s));
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + 3 * nb + ib, sc.ncta, I.d_ws.p, false, 4, true, I.dVXCz.p,
+                                 inbf, s));
+      launches += 2;
+    }
     ++ib;
   }
   gxb::launch_reduce_partials(I.d_exc_part.p, I.d_nel_part.p, (int)sc.tiles.size(), I.d_out2.p, s);
-  gxb::launch_symmetrize(I.dVXC.p, inbf, inbf, s);
-  gxb::launch_symmetrize(I.dVXCz.p, inbf, inbf, s);
-  launches += 3;
+  ++launches;
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(I.e_lw1, s));
-  if (red_->comm_size() > 1) {
-    red_->allreduce_inplace(I.dVXC.p, nn, ReductionOp::Sum, s);
-    red_->allreduce_inplace(I.dVXCz.p, nn, ReductionOp::Sum, s);
+  if (do_vxc) {
+    reduce_and_symmetrize_(I.dVXC.p, I.dVXCz.p, I.d_out2.p, inbf, true);
+    launches += 2;
+    download_matrix(VXCs, ldvxcs, I.dVXC.p, nbf, s);
+    download_matrix(VXCz, ldvxcz, I.dVXCz.p, nbf, s);
+  } else if (red_->comm_size() > 1) {
     red_->allreduce_inplace(I.d_out2.p, 2, ReductionOp::Sum, s);
   }
-  CUDA_CHECK(cudaMemcpy2DAsync(VXCs, ldvxcs * sizeof(double), I.dVXC.p, nbf * sizeof(double), nbf * sizeof(double),
-                               nbf, cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpy2DAsync(VXCz, ldvxcz * sizeof(double), I.dVXCz.p, nbf * sizeof(double), nbf * sizeof(double),
-                               nbf, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaEventRecord(I.e_end, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1004,12 +1126,18 @@ void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int6
   stats_.n_el = I.h_out2[1];
 }
 
-void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL) {
-  // the reference integrates with X = 1.0 * P * B (…integrate_den.hpp); N_EL of the EXC path
-  // carries the RKS factor 2, so halve it (integrate_den(P) == N_el / 2)
-  double exc;
-  eval_exc(m, n, P, ldp, &exc);
-  *N_EL = 0.5 * stats_.n_el;
+void XCIntegrator::eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz,
+                                    int64_t ldpz, double* VXCs, int64_t ldvxcs, double* VXCz,
+                                    int64_t ldvxcz, double* EXC) {
+  eval_uks_(m, n, Ps, ldps, Pz, ldpz, VXCs, ldvxcs, VXCz, ldvxcz, EXC, true);
+}
+void XCIntegrator::eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz,
+                                int64_t ldpz, double* EXC) {
+  eval_uks_(m, n, Ps, ldps, Pz, ldpz, nullptr, 0, nullptr, 0, EXC, false);
+}
+
+void XCIntegrator::eval_exc_grad(int64_t, int64_t, const double*, int64_t, double*) {
+  GAUXC_GENERIC_EXCEPTION("EXC Gradient NYI in B200 path");
 }
 
 }  // namespace GauXC

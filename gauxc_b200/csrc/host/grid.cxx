@@ -109,9 +109,21 @@ int lebedev_next_algebraic_order(int order) {
 // ---------------------------------------------------------------------------
 // Defaults (src/molgrid_defaults.cxx:52-71, 145-199)
 // ---------------------------------------------------------------------------
+// Slater-64 radii (J. Chem. Phys. 41, 3199) with the Clementi-67 values for the noble gases the
+// Slater table lacks, in pm (src/atomic_radii.cxx:16-36: Slater first, Clementi to fill gaps)
+static double default_atomic_radius(int64_t Z) {
+  static const double pm[37] = {0,   25,  31,  145, 105, 85,  70,  65,  60,  50,  38,  180, 150,
+                                125, 110, 100, 100, 100, 71,  220, 180, 160, 140, 135, 140, 140,
+                                140, 135, 135, 135, 135, 130, 125, 115, 115, 115, 88};
+  if (Z < 1 || Z > 36) GAUXC_GENERIC_EXCEPTION("Default Atomic Radius NYI in B200 path for Z > 36");
+  return pm[Z] * 0.0188973000000929 / 1.00000205057;  // pm_to_bohr of the reference
+}
+
 double default_radial_scaling_factor(RadialQuad rq, int64_t Z) {
-  if (rq != RadialQuad::MuraKnowles && rq != RadialQuad::MurrayHandyLaming)
-    GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path (MuraKnowles only)");
+  // src/molgrid_defaults.cxx:52-71 (MuraKnowles), :118-122 (MurrayHandyLaming)
+  if (rq == RadialQuad::MurrayHandyLaming) return default_atomic_radius(Z) * (Z != 1 ? 0.5 : 1.0);
+  if (rq != RadialQuad::MuraKnowles)
+    GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path (MuraKnowles, MurrayHandyLaming)");
   switch (Z) {
     case 3: case 4: case 11: case 12: case 19: case 20:
     case 37: case 38: case 55: case 56: case 87: case 88:

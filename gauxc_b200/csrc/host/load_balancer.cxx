@@ -21,13 +21,24 @@ bool cube_sphere_intersect(const double* lo, const double* up, const double* cen
 }
 
 LoadBalancer::LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecule& mol,
-                           const MolGrid& mg, const BasisSet& basis)
+                           const MolGrid& mg, const BasisSet& basis, const std::string& kernel)
     : runtime_(std::move(rt)),
       mol_(std::make_shared<Molecule>(mol)),
       mg_(std::make_shared<MolGrid>(mg)),
       basis_(std::make_shared<BasisSet>(basis)),
       molmeta_(std::make_shared<MolMeta>(mol)),
-      basis_map_(std::make_shared<BasisSetMap>(basis, mol)) {}
+      basis_map_(std::make_shared<BasisSetMap>(basis, mol)) {
+  // src/load_balancer/host/load_balancer_host_factory.cxx:28-40
+  if (kernel == "REPLICATED-FILLIN") fill_in_ = true;
+  else if (kernel != "DEFAULT" && kernel != "REPLICATED" && kernel != "REPLICATED-PETITE")
+    GAUXC_GENERIC_EXCEPTION("LoadBalancer Kernel Not Recognized: " + kernel);
+}
+
+void LoadBalancer::replace_tasks(std::vector<XCTask> tasks) {
+  local_tasks_ = std::move(tasks);
+  tasks_created_ = true;
+  ++version_;
+}
 
 std::vector<XCTask>& LoadBalancer::get_tasks() {
   if (!tasks_created_) {
@@ -96,9 +107,20 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     for (int d = 0; d < 3; ++d) { cmin[d] = std::min(cmin[d], cen[d]); cmax[d] = std::max(cmax[d], cen[d]); }
     rmax_all = std::max(rmax_all, center_maxrad[c]);
   }
-  const double cell = std::max(4.0, 0.5 * rmax_all);
+  // cell edge: at least half the largest cutoff; enlarged until the grid holds at most ~8 cells per atom,
+  // so far-apart fragments (dissociation scans) cannot blow the cell array up
+  double cell = std::max(4.0, 0.5 * rmax_all);
   int ncell[3] = {1, 1, 1};
-  for (int d = 0; d < 3; ++d) ncell[d] = natoms ? std::max(1, (int)std::floor((cmax[d] - cmin[d]) / cell) + 1) : 1;
+  for (;;) {
+    double total = 1.;
+    for (int d = 0; d < 3; ++d) {
+      const double nd = natoms ? std::max(1., std::floor((cmax[d] - cmin[d]) / cell) + 1.) : 1.;
+      total *= nd;
+      ncell[d] = (int)std::min(nd, 1e6);
+    }
+    if (total <= 8. * double(natoms) + 64.) break;
+    cell *= 1.5;
+  }
   std::vector<std::vector<int32_t>> cells((size_t)ncell[0] * ncell[1] * ncell[2]);
   auto cell_of = [&](double v, int d) {
     return std::min(ncell[d] - 1, std::max(0, (int)std::floor((v - cmin[d]) / cell)));
@@ -151,6 +173,12 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
           shell_list.push_back(s);
       if (shell_list.empty()) continue;
       std::sort(shell_list.begin(), shell_list.end());
+      if (fill_in_) {
+        // fillin_replicated_load_balancer.cxx: every shell between the first and the last hit
+        const int32_t first = shell_list.front(), last = shell_list.back();
+        shell_list.resize((size_t)(last - first + 1));
+        std::iota(shell_list.begin(), shell_list.end(), first);
+      }
 
       size_t nbe = 0;
       for (auto s : shell_list) nbe += basis[s].size();

@@ -7,6 +7,7 @@
 #include "grid.hpp"
 #include "types.hpp"
 #include <memory>
+#include <string>
 
 namespace GauXC {
 
@@ -59,13 +60,20 @@ class LoadBalancer {
   LoadBalancerState state_;
   uint64_t version_ = 0;  // bumped whenever tasks / weights change (device caches key on it)
 
+  bool fill_in_ = false;  // REPLICATED-FILLIN: contiguous shell range first..last instead of the exact list
+
   std::vector<XCTask> create_local_tasks_() const;
 
 public:
+  // kernel: "DEFAULT" / "REPLICATED" / "REPLICATED-PETITE" (exact shell lists,
+  // petite_replicated_load_balancer.cxx:31-65) or "REPLICATED-FILLIN" (fillin_replicated_load_balancer.cxx)
   LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecule& mol, const MolGrid& mg,
-               const BasisSet& basis);
+               const BasisSet& basis, const std::string& kernel = "DEFAULT");
 
   std::vector<XCTask>& get_tasks();
+  // install a user supplied task list without generating the default one first
+  void replace_tasks(std::vector<XCTask> tasks);
+  bool tasks_created() const { return tasks_created_; }
   const Molecule& molecule() const { return *mol_; }
   const MolGrid& molgrid() const { return *mg_; }
   const BasisSet& basis() const { return *basis_; }

@@ -44,6 +44,11 @@ public:
   // stream: cudaStream_t passed as void* (the reference passes std::any queue)
   virtual void allreduce_inplace(double* data, size_t n, ReductionOp op, void* stream) = 0;
   virtual int comm_size() const = 0;
+  // extension used for the replicated density upload: rank r contributes data[r * count .. (r+1) * count)
+  virtual bool can_allgather() const { return false; }
+  virtual void allgather_inplace(double*, size_t /*count_per_rank*/, void* /*stream*/) {
+    GAUXC_GENERIC_EXCEPTION("allgather NYI for this ReductionDriver");
+  }
 };
 // "Default"/"NCCL": NCCL over NVLink when comm_size > 1, a no-op driver for a single rank.
 // "BasicMPI" is rejected (no MPI in this build).
@@ -97,6 +102,11 @@ class XCIntegrator {
   Timer timer_;
   XCIntegratorStats stats_;
 
+  void reduce_and_symmetrize_(double* dV, double* dVz, double* d_out2, int nbf, bool do_vxc);
+  void upload_density_(const double* P, int64_t ldp, double* dP, size_t nbf);
+  void eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
+                 double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC, bool do_vxc);
+
 public:
   XCIntegrator(ExecutionSpace ex, const std::string& input_type, const std::string& integrator_kernel,
                const std::string& lwd_kernel, const std::string& reduction_kernel,
@@ -109,7 +119,11 @@ public:
   // UKS (LDA functionals): Ps = P_alpha + P_beta, Pz = P_alpha - P_beta; VXCs / VXCz fully overwritten
   void eval_exc_vxc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
                         double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC);
+  void eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
+                    double* EXC);
   void eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC);
+  // EXC gradient w.r.t. the nuclear coordinates (3 * natoms), RKS
+  void eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD);
   void integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL);
   // device-resident variant: dP (nbf x nbf, ld nbf) and dVXC live in HBM, out2 = {EXC, N_EL}
   // device scalars; no host<->device traffic in the call.

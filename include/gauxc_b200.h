@@ -194,6 +194,32 @@ typedef struct GauXCFunctional {
   void* ptr;
 } GauXCFunctional;
 GauXCFunctional gauxc_functional_from_string(GauXCStatus* status, const char* functional_spec, bool polarized);
+/* include/gauxc/c/functional.h:22-330 (same enumerators, same order as ExchCXX::Functional); LDA/GGA members
+ * SVWN5, BLYP, B3LYP, PBE, revPBE, PBE0, LDA, SPW92, VWN5, revPBE0 are built, the rest -> status 1 "NYI" */
+enum GauXC_Functional {
+  GauXC_Functional_SVWN3, GauXC_Functional_SVWN5, GauXC_Functional_BLYP, GauXC_Functional_B3LYP,
+  GauXC_Functional_PBE, GauXC_Functional_revPBE, GauXC_Functional_PBE0, GauXC_Functional_SCAN,
+  GauXC_Functional_R2SCAN, GauXC_Functional_R2SCANL, GauXC_Functional_M062X, GauXC_Functional_PKZB,
+  GauXC_Functional_EPC17_1, GauXC_Functional_EPC17_2, GauXC_Functional_EPC18_1, GauXC_Functional_EPC18_2,
+  GauXC_Functional_B97D, GauXC_Functional_B97D3ZERO, GauXC_Functional_CAMB3LYP, GauXC_Functional_LDA,
+  GauXC_Functional_M06L, GauXC_Functional_SCAN0, GauXC_Functional_SPW92, GauXC_Functional_TPSS,
+  GauXC_Functional_TPSSh, GauXC_Functional_TPSS0, GauXC_Functional_VWN3, GauXC_Functional_VWN5,
+  GauXC_Functional_LRCwPBE, GauXC_Functional_LRCwPBEh, GauXC_Functional_BP86, GauXC_Functional_HSE03,
+  GauXC_Functional_HSE06, GauXC_Functional_revB3LYP, GauXC_Functional_revPBE0, GauXC_Functional_revTPSS,
+  GauXC_Functional_revTPSSh, GauXC_Functional_PW91, GauXC_Functional_mBEEF, GauXC_Functional_B3PW91,
+  GauXC_Functional_O3LYP, GauXC_Functional_OLYP, GauXC_Functional_OPBE, GauXC_Functional_MPW1K,
+  GauXC_Functional_RPBE, GauXC_Functional_B88, GauXC_Functional_MPW91, GauXC_Functional_RSCAN,
+  GauXC_Functional_TUNEDCAMB3LYP, GauXC_Functional_wB97, GauXC_Functional_wB97X, GauXC_Functional_wB97XD,
+  GauXC_Functional_wB97XD3, GauXC_Functional_LCwPBE, GauXC_Functional_X3LYP, GauXC_Functional_XLYP,
+  GauXC_Functional_BHANDH, GauXC_Functional_BMK, GauXC_Functional_BP86VWN, GauXC_Functional_PW86B95,
+  GauXC_Functional_PW86PBE, GauXC_Functional_R2SCAN0, GauXC_Functional_R2SCANh, GauXC_Functional_R2SCAN50,
+  GauXC_Functional_M05, GauXC_Functional_M06, GauXC_Functional_M08HX, GauXC_Functional_M08SO,
+  GauXC_Functional_M052X, GauXC_Functional_M06SX, GauXC_Functional_CF22D, GauXC_Functional_SOGGA11X,
+  GauXC_Functional_M06HF, GauXC_Functional_M11, GauXC_Functional_MN12L, GauXC_Functional_MN12SX,
+  GauXC_Functional_MN15, GauXC_Functional_MN15L, GauXC_Functional_revM06L
+};
+GauXCFunctional gauxc_functional_from_enum(GauXCStatus* status, enum GauXC_Functional functional_type,
+                                           bool polarized);
 void gauxc_functional_delete(GauXCStatus* status, GauXCFunctional* functional);
 
 /* ---- include/gauxc/c/xc_integrator.h:34-190 -------------------------------------------------- */
@@ -216,9 +242,8 @@ void gauxc_integrator_eval_exc_vxc_rks(GauXCStatus* status, const GauXCIntegrato
                                        const int64_t m, const int64_t n, const double* density_matrix,
                                        const int64_t ldp, double* exc, double* vxc_matrix,
                                        const int64_t vxc_ld);
-/* UKS: implemented for LDA functionals built with polarized = true (SVWN5, LDA/SLATER, VWN5);
- * density_matrix_s = P_alpha + P_beta, density_matrix_z = P_alpha - P_beta; GGA -> status 1 "NYI".
- * Gradients: declared for link compatibility, status code 1 "NYI" (SURVEY.md section 8f). */
+/* UKS: functionals built with polarized = true; density_matrix_s = P_alpha + P_beta,
+ * density_matrix_z = P_alpha - P_beta. */
 void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrator integrator,
                                        const int64_t m, const int64_t n, const double* density_matrix_s,
                                        const int64_t ldp_s, const double* density_matrix_z,
@@ -227,6 +252,49 @@ void gauxc_integrator_eval_exc_vxc_uks(GauXCStatus* status, const GauXCIntegrato
 void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator integrator,
                                         const int64_t m, const int64_t n, const double* density_matrix,
                                         const int64_t ldp, double* exc_grad);
+void gauxc_integrator_eval_exc_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                   const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                   const double* density_matrix_z, const int64_t ldp_z, double* exc);
+/* include/gauxc/c/xc_integrator.h:124-365, outside the LDA/GGA RKS/UKS path: exported for link
+ * compatibility, every call returns status code 1 with a "... NYI in B200 path" message. */
+void gauxc_integrator_eval_exc_gks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                   const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                   const double* density_matrix_z, const int64_t ldp_z,
+                                   const double* density_matrix_y, const int64_t ldp_y,
+                                   const double* density_matrix_x, const int64_t ldp_x, double* exc);
+void gauxc_integrator_eval_exc_vxc_gks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                       const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                       const double* density_matrix_z, const int64_t ldp_z,
+                                       const double* density_matrix_y, const int64_t ldp_y,
+                                       const double* density_matrix_x, const int64_t ldp_x, double* exc,
+                                       double* vxc_matrix_s, const int64_t vxc_ld_s, double* vxc_matrix_z,
+                                       const int64_t vxc_ld_z, double* vxc_matrix_y, const int64_t vxc_ld_y,
+                                       double* vxc_matrix_x, const int64_t vxc_ld_x);
+void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                        const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                        const double* density_matrix_z, const int64_t ldp_z, double* exc_grad);
+void gauxc_integrator_eval_exx_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                   const int64_t n, const double* density_matrix, const int64_t ldp, double* K,
+                                   const int64_t ldk);
+void gauxc_integrator_eval_fxc_contraction_rks(GauXCStatus* status, const GauXCIntegrator integrator,
+                                               const int64_t m, const int64_t n, const double* density_matrix,
+                                               const int64_t ldp, const double* t_density_matrix,
+                                               const int64_t ltdp, double* fxc, const int64_t ldfxc);
+void gauxc_integrator_eval_fxc_contraction_uks(GauXCStatus* status, const GauXCIntegrator integrator,
+                                               const int64_t m, const int64_t n, const double* density_matrix_s,
+                                               const int64_t ldp_s, const double* density_matrix_z,
+                                               const int64_t ldp_z, const double* t_density_matrix_s,
+                                               const int64_t ldtp_s, const double* t_density_matrix_z,
+                                               const int64_t ldtp_z, double* fxc_s, const int64_t ldfxc_s,
+                                               double* fxc_z, const int64_t ldfxc_z);
+
+/* ---- include/gauxc/c/hdf5.h:24-52 (HDF5 records of the reference's fixtures; self-contained reader /
+ * writer, no libhdf5) -------------------------------------------------------------------------- */
+void gauxc_molecule_write_hdf5_record(GauXCStatus* status, GauXCMolecule mol, const char* fname, const char* dset);
+void gauxc_basisset_write_hdf5_record(GauXCStatus* status, GauXCBasisSet basis, const char* fname,
+                                      const char* dset);
+void gauxc_molecule_read_hdf5_record(GauXCStatus* status, GauXCMolecule mol, const char* fname, const char* dset);
+void gauxc_basisset_read_hdf5_record(GauXCStatus* status, GauXCBasisSet basis, const char* fname, const char* dset);
 
 /* =============================== Part 2: extensions ======================================== */
 

@@ -146,10 +146,11 @@ void f_pw92(double rho, double& e, double& v) {
   v = e - rs / 3. * de;
 }
 
-void f_pbe_x(double rho, double sigma, double& e, double& v, double& vs) {
+// kappa = 0.8040: PBE (libxc gga_x_pbe); kappa = 1.245: revPBE (gga_x_pbe_r, Zhang & Yang 1998)
+void f_pbe_x(double rho, double sigma, double& e, double& v, double& vs, double kappa = 0.8040) {
   if (rho <= 1e-32) { e = v = vs = 0; return; }
   sigma = std::max(sigma, 1e-40);
-  const double kappa = 0.8040, mu = 0.2195149727645171;
+  const double mu = 0.2195149727645171;
   const double kf = std::cbrt(3. * PI * PI * rho);
   const double s = std::sqrt(sigma) / (2. * kf * rho);
   const double s2 = s * s;
@@ -194,13 +195,32 @@ void f_pbe_c(double rho, double sigma, double& e, double& v, double& vs) {
   vs = rho * dH_dt2 * t2 / sigma;
 }
 
-enum { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5, K_B88_X = 6, K_LYP_C = 7 };
+enum { K_SLATER_X = 0, K_VWN5_C = 1, K_PBE_X = 2, K_PBE_C = 3, K_VWN3_C = 4, K_PW92_C = 5, K_B88_X = 6, K_LYP_C = 7,
+       K_REVPBE_X = 8 };
 
 struct Func {
   int nkern, is_gga;
   int kern[4];
   double coeff[4];
 };
+
+void eval_func_pol_gga(const Func& f, int npts, const double* rho2, const double* gamma3, double* eps,
+                       double* vrho2, double* vgamma3);
+
+// B88 / LYP for a closed shell: the spin-resolved functional (pinned by the reference's BLYP UKS fixture) at
+// rho_a = rho_b = rho/2, sigma_aa = sigma_ab = sigma_bb = sigma/4; d/d rho = d/d rho_a, d/d sigma = the mean
+// of the three sigma derivatives... times 1 (chain rule: each of the three carries 1/4)
+void f_via_pol(int kern, double rho, double sigma, double& e, double& v, double& vs) {
+  Func one{1, 1, {kern, 0, 0, 0}, {1., 0., 0., 0.}};
+  const double r2[2] = {0.5 * rho, 0.5 * rho};
+  const double q = 0.25 * std::max(sigma, 0.);
+  const double g3[3] = {q, q, q};
+  double ee, v2[2], v3[3];
+  eval_func_pol_gga(one, 1, r2, g3, &ee, v2, v3);
+  e = ee;
+  v = v2[0];
+  vs = 0.25 * (v3[0] + v3[1] + v3[2]);
+}
 
 void eval_func(const Func& f, int npts, const double* rho, const double* sigma, double* eps, double* vrho,
                double* vsigma) {
@@ -209,6 +229,9 @@ void eval_func(const Func& f, int npts, const double* rho, const double* sigma, 
     for (int k = 0; k < f.nkern; ++k) {
       double e = 0, v = 0, s = 0;
       switch (f.kern[k]) {
+        case K_REVPBE_X: f_pbe_x(rho[i], sigma[i], e, v, s, 1.245); break;
+        case K_B88_X:
+        case K_LYP_C: f_via_pol(f.kern[k], rho[i], sigma ? sigma[i] : 0., e, v, s); break;
         case K_SLATER_X: f_slater(rho[i], e, v); break;
         case K_VWN5_C: f_vwn5(rho[i], e, v); break;
         case K_PW92_C: f_pw92(rho[i], e, v); break;

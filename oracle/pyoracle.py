@@ -16,7 +16,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lib = None
 
-KERN = dict(SLATER_X=0, VWN5_C=1, PBE_X=2, PBE_C=3, PW92_C=5, B88_X=6, LYP_C=7)
+KERN = dict(SLATER_X=0, VWN5_C=1, PBE_X=2, PBE_C=3, PW92_C=5, B88_X=6, LYP_C=7, REVPBE_X=8)
 FUNCTIONALS = {
     "SVWN5": (False, [("SLATER_X", 1.0), ("VWN5_C", 1.0)]),
     "LDA": (False, [("SLATER_X", 1.0)]),
@@ -24,7 +24,10 @@ FUNCTIONALS = {
     "SPW92": (False, [("SLATER_X", 1.0), ("PW92_C", 1.0)]),
     "PBE": (True, [("PBE_X", 1.0), ("PBE_C", 1.0)]),
     "PBE0": (True, [("PBE_X", 0.75), ("PBE_C", 1.0)]),
-    "BLYP": (True, [("B88_X", 1.0), ("LYP_C", 1.0)]),  # UKS oracle only (forward-mode differentiation)
+    "BLYP": (True, [("B88_X", 1.0), ("LYP_C", 1.0)]),  # forward-mode differentiation of the spin-resolved forms
+    "B3LYP": (True, [("SLATER_X", 0.08), ("B88_X", 0.72), ("VWN5_C", 0.19), ("LYP_C", 0.81)]),  # libxc hyb_gga_xc_b3lyp
+    "REVPBE": (True, [("REVPBE_X", 1.0), ("PBE_C", 1.0)]),
+    "REVPBE0": (True, [("REVPBE_X", 0.75), ("PBE_C", 1.0)]),
 }
 
 

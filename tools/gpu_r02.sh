@@ -1,0 +1,36 @@
+#!/bin/bash
+# Round-2 GPU session.  usage (under gpurun): bash tools/gpu_r02.sh <tag> <stages...>
+#   stages: quick (small parity tests) | pytest (all -m gpu) | smoke | bench:<workload>[:steps] | benchall |
+#           launches:<workload> | ncu:<workload>:<kernel-regex>:<skip> | knock
+TAG=$1; shift
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+nproc >> gpurun_out/${TAG}_gpu.txt; free -g | head -2 >> gpurun_out/${TAG}_gpu.txt
+for ST in "$@"; do
+  IFS=: read -r KIND A B C <<< "$ST"
+  case $KIND in
+    quick)
+      timeout 900 python -m pytest tests -m gpu -x -q -k "not large_config and not taxol_full and not two_rank" > gpurun_out/${TAG}_quick.log 2>&1
+      echo "quick exit $?" >> gpurun_out/${TAG}_quick.log; tail -15 gpurun_out/${TAG}_quick.log ;;
+    pytest)
+      timeout 2400 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${TAG}_pytest.log 2>&1
+      echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log; tail -25 gpurun_out/${TAG}_pytest.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; tail -3 gpurun_out/${TAG}_smoke.log ;;
+    bench)
+      timeout 1500 python bench.py --workload $A --steps ${B:-5} --warmup 3 --others "" > gpurun_out/${TAG}_bench_${A}.json 2> gpurun_out/${TAG}_bench_${A}.err
+      echo "bench $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_bench_${A}.json; tail -3 gpurun_out/${TAG}_bench_${A}.err ;;
+    benchall)
+      timeout 2400 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
+      echo "bench default exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_bench_default.json; tail -3 gpurun_out/${TAG}_bench_default.err ;;
+    launches)
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_${A}.csv \
+        python bench.py --workload $A --steps 1 --warmup 1 --no-cpu-baseline --others "" --parity-seconds 0.5 > gpurun_out/${TAG}_ncu_launch_${A}.log 2>&1
+      echo "launch list $A exit $?" ;;
+    ncu)
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$B -s ${C:-3} -c 1 -f -o gpurun_out/${TAG}_${A}_${B} \
+        python bench.py --workload $A --steps 1 --warmup 1 --no-cpu-baseline --others "" --parity-seconds 0.5 > gpurun_out/${TAG}_ncu_${A}_${B}.log 2>&1
+      echo "ncu $A $B exit $?" ;;
+    *) echo "unknown stage $ST" ;;
+  esac
+done
