@@ -135,6 +135,7 @@ def lib():
         "gauxc_b200_eval_collocation": (None, [S, _Handle, C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host_pol": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
+        "gauxc_b200_functional_eval_host_pol_full": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host_pol_gga": (None, [S, C.c_int, C.POINTER(C.c_int), _dp, C.c_int64, _dp, _dp,
                                                            _dp, _dp, _dp]),
         "gauxc_b200_probe_peak": (C.c_double, [S, C.c_int]),
@@ -423,6 +424,15 @@ class Functional(_Obj):
         _call("gauxc_b200_functional_eval_host", self.h, n, _d(rho), _d(sg), _d(eps), _d(vr), _d(vs))
         return eps, vr, vs
 
+
+    def eval_host_pol_full(self, rho_a, rho_b, s_aa, s_ab, s_bb):
+        """eps, (vrho_a, vrho_b), (vsigma_aa, vsigma_ab, vsigma_bb) of the polarised functional (LDA or GGA)."""
+        n = len(rho_a)
+        r2 = np.ascontiguousarray(np.stack([rho_a, rho_b], 1).ravel(), np.float64)
+        g3 = np.ascontiguousarray(np.stack([s_aa, s_ab, s_bb], 1).ravel(), np.float64)
+        eps, v2, v3 = np.zeros(n), np.zeros(2 * n), np.zeros(3 * n)
+        _call("gauxc_b200_functional_eval_host_pol_full", self.h, n, _d(r2), _d(g3), _d(eps), _d(v2), _d(v3))
+        return eps, (v2[0::2].copy(), v2[1::2].copy()), (v3[0::3].copy(), v3[1::3].copy(), v3[2::3].copy())
 
     def eval_host_pol(self, rho_a, rho_b):
         """Spin-polarised LDA kernels (UKS) on the host: eps, d(rho eps)/d rho_a, d(rho eps)/d rho_b."""

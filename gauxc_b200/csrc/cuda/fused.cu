@@ -117,11 +117,12 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
   }
 }
 
-// SPIN = 0: RKS (P = P_alpha, factor 2 inside).  UKS (LDA functionals) runs the kernel twice per batch:
-// SPIN = 1 with P = Ps = P_alpha + P_beta only stores rho_s per point (uks_den); SPIN = 2 with P = Pz
-// forms rho_z, rho_+- = (rho_s +- rho_z)/2, evaluates the polarised functional and writes BOTH
-// Z_s (matrix 1) and Z_z (matrix 2) -- eval_uvvar_lda_uks / eval_zmat_lda_vxc_uks of the reference host
-// driver (reference_local_host_work_driver.cxx:166-188, 607-634; X factor 1.0, driver :387-396).
+// SPIN = 0: RKS (P = P_alpha, factor 2 inside).  UKS runs the kernel twice per batch:
+// SPIN = 1 with P = Ps = P_alpha + P_beta only stores rho_s (GGA: and grad n) per point (uks_den, one array
+// of uks_stride doubles per component); SPIN = 2 with P = Pz forms rho_z (grad M_z), rho_+- = (rho_s +- rho_z)/2
+// (and the three gammas), evaluates the polarised functional and writes the factors of BOTH Z_s (rows 0-3)
+// and Z_z (rows 4-7) -- eval_uvvar_{lda,gga}_uks / eval_zmat_{lda,gga}_vxc_uks of the reference host driver
+// (reference_local_host_work_driver.cxx:166-188, 270-328, 607-634, 715-773; X factor 1.0, driver :387-396).
 template <bool GGA, int SPIN>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
@@ -129,8 +130,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
                            double* __restrict__ ws,
                            const double* __restrict__ P, int ldp, FunctionalDesc func,
                            double* __restrict__ exc_part, double* __restrict__ nel_part,
-                           int part_off, double* __restrict__ uks_den) {
-  static_assert(SPIN == 0 || !GGA, "UKS is implemented for LDA functionals");
+                           int part_off, double* __restrict__ uks_den, size_t uks_stride) {
   // no pointer arithmetic on the base: the compiler must see shared-space accesses (LDS/STS, not
   // generic LD/ST) in the fragment loads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -388,7 +388,9 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
           const double v = ((S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p])) +
                            ((S.dpart[4][qn][p] + S.dpart[5][qn][p]) + (S.dpart[6][qn][p] + S.dpart[7][qn][p]));
-          den[qn] = (SPIN != 0 ? 2. : (qn == 0 && GGA) ? 2. : 4.) * v;
+          // RKS: X carries 2, the gradient another 2, the LDA triangle another 2; UKS: X factor 1.0
+          const double f = SPIN != 0 ? (GGA ? (qn == 0 ? 1. : 2.) : 2.) : ((qn == 0 && GGA) ? 2. : 4.);
+          den[qn] = f * v;
         }
       }
       named_bar_sync(2, DEN_THREADS);  // dpart may be overwritten by the next tile
@@ -398,12 +400,42 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       const double rho = den[0];
       const double dx = den[1], dy = den[2], dz = den[3];
       const bool ok = p < tile.npts;
-      if (SPIN == 1) {  // UKS pass over Ps: keep rho_s for the pass over Pz, nothing else to do
-        if (ok) uks_den[tile.pt_off + p] = rho;
+      if (SPIN == 1) {  // UKS pass over Ps: keep rho_s (grad n) for the pass over Pz, nothing else to do
+        if (ok) {
+          uks_den[tile.pt_off + p] = rho;
+          if (GGA) {
+            uks_den[uks_stride + tile.pt_off + p] = dx;
+            uks_den[2 * uks_stride + tile.pt_off + p] = dy;
+            uks_den[3 * uks_stride + tile.pt_off + p] = dz;
+          }
+        }
         continue;
       }
       double a = 0., fx = 0., fy = 0., fz = 0., e_loc = 0., n_loc = 0.;
-      if (ok && SPIN == 2) {
+      double az = 0., gx = 0., gy = 0., gz = 0.;  // UKS GGA: factors of Z_z
+      if (ok && SPIN == 2 && GGA) {
+        // eval_uvvar_gga_uks :270-328, weights :453-466, eval_zmat_gga_vxc_uks :715-773
+        const double w = pv.w[tile.pt_off + p];
+        const size_t ip = tile.pt_off + p;
+        const double rho_s = uks_den[ip], nx = uks_den[uks_stride + ip], ny = uks_den[2 * uks_stride + ip],
+                     nz = uks_den[3 * uks_stride + ip];
+        const double rho_z = rho, mx = dx, my = dy, mz = dz;
+        const double dn_sq = nx * nx + ny * ny + nz * nz, dm_sq = mx * mx + my * my + mz * mz,
+                     dn_dm = nx * mx + ny * my + nz * mz;
+        const double gpp = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm, gpm = 0.25 * (dn_sq - dm_sq),
+                     gmm = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
+        const XcOutPolGga xc = eval_functional_pol(func, 0.5 * (rho_s + rho_z), 0.5 * (rho_s - rho_z), gpp, gpm, gmm);
+        const double eps = xc.eps * w;
+        const double factp = 0.5 * (xc.va * w), factm = 0.5 * (xc.vb * w);
+        const double vpp = xc.vaa * w, vpm = xc.vab * w, vmm = xc.vbb * w;
+        const double g1 = 0.5 * (vpp + vpm + vmm), g2 = 0.5 * (vpp - vmm), g3 = 0.5 * (vpp - vpm + vmm);
+        a = 0.5 * (factp + factm);
+        az = 0.5 * (factp - factm);
+        fx = g1 * nx + g2 * mx; fy = g1 * ny + g2 * my; fz = g1 * nz + g2 * mz;
+        gx = g3 * mx + g2 * nx; gy = g3 * my + g2 * ny; gz = g3 * mz + g2 * nz;
+        e_loc = eps * rho_s;
+        n_loc = w * rho_s;
+      } else if (ok && SPIN == 2) {
         const double w = pv.w[tile.pt_off + p];
         const double rho_s = uks_den[tile.pt_off + p], rho_z = rho;
         const XcOutPol xc = eval_functional_pol_lda(func, 0.5 * (rho_s + rho_z), 0.5 * (rho_s - rho_z));
@@ -433,7 +465,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         double* __restrict__ frow = ws + tile.ws_off + (size_t)NMAT * ms + p;
         frow[0] = a;
         if (GGA) { frow[TP] = fx; frow[2 * TP] = fy; frow[3 * TP] = fz; }
-        if (SPIN == 2) frow[4 * TP] = fx;  // z channel: Z_z = fx B
+        if (SPIN == 2 && !GGA) frow[4 * TP] = fx;  // z channel: Z_z = fx B
+        if (SPIN == 2 && GGA) { frow[4 * TP] = az; frow[5 * TP] = gx; frow[6 * TP] = gy; frow[7 * TP] = gz; }
       }
       // fixed-order tile partials of EXC / N_EL
       {
@@ -536,7 +569,7 @@ int fused_threads() { return FUSED_THREADS; }
 cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                          int* counter, int ncta, double* ws, const double* P, int ldp,
                          FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
-                         cudaStream_t s, int spin, double* uks_den) {
+                         cudaStream_t s, int spin, double* uks_den, size_t uks_stride) {
   if (ncta <= 0 || ntiles <= 0) return cudaSuccess;
   ncta = ncta < ntiles ? ncta : ntiles;
   // the attribute is per device and cheap to set: no process-wide "done" flag
@@ -544,9 +577,11 @@ cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     kern<<<ncta, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(tmapA, pv, tiles, ntiles, counter, ws, P, ldp, func,
-                                                       exc_part, nel_part, part_off, uks_den);
+                                                       exc_part, nel_part, part_off, uks_den, uks_stride);
     return cudaGetLastError();
   };
+  if (spin == 1 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 1>);
+  if (spin == 2 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 2>);
   if (spin == 1) return launch(fused_xmat_den_zmat_kernel<false, 1>);
   if (spin == 2) return launch(fused_xmat_den_zmat_kernel<false, 2>);
   if (func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 0>);

@@ -18,11 +18,12 @@ void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, do
 // K_F  fused persistent kernel: X = B P_sub (DMMA) -> rho / grad rho -> functional, weights,
 //      EXC / N_EL tile partials -> the per-point factors of Z in the tile's factor rows.  tmapA: boxes of
 //      16 rows x W points over the workspace; the ncta persistent CTAs pull tile indices [0, ntiles) from
-//      *counter (zeroed by the caller).  func.nkern == 0: density only (integrate_den).
+//      *counter (zeroed by the caller).  func.nkern == 0: density only (integrate_den).  spin 1 / 2: the two
+//      UKS passes (Ps then Pz), uks_den: 1 (LDA) or 4 (GGA) arrays of uks_stride doubles carried between them.
 cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                          int* counter, int ncta, double* ws, const double* P, int ldp,
                          FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
-                         cudaStream_t s, int spin = 0, double* uks_den = nullptr);
+                         cudaStream_t s, int spin = 0, double* uks_den = nullptr, size_t uks_stride = 0);
 
 // K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe with Z = a B (+ fx dBx + fy dBy + fz dBz for gga)
 //      formed on the fly from the tile's factor rows fac_row .. fac_row+3 (RKS / UKS s channel: 0, UKS z

@@ -38,8 +38,8 @@ constexpr int V_MMA_THREADS = V_MMA_WARPS * 32, V_COMB_THREADS = V_COMB_WARPS * 
 // warps 0-7 MMA, 8-15 combiners, 16-19 scatter, 20 producer, 21-23 idle (complete the producer's
 // warpgroup for setmaxnreg)
 constexpr int V_THREADS = (V_MMA_WARPS + V_COMB_WARPS + V_SCAT_WARPS + 4) * 32;
-// launch allocation 24 warps x 80; after re-partitioning 8 x 112 + 8 x 72 + 4 x 64 + 4 x 48
-constexpr int V_MMA_REGS = 112, V_COMB_REGS = 72, V_SCAT_REGS = 64, V_PROD_REGS = 48;
+// launch allocation 24 warps x 80; after re-partitioning 8 x 112 + 8 x 96 + 4 x 40 + 4 x 24
+constexpr int V_MMA_REGS = 112, V_COMB_REGS = 96, V_SCAT_REGS = 40, V_PROD_REGS = 24;
 constexpr int OUT_LD = VXC_BLK + 2;  // conflict-free accumulator dump (C fragment: rows g, columns 2t, 2t+1)
 
 struct VxcSlot {
@@ -50,6 +50,7 @@ struct VxcSmem {
   double A[VSTAGES][VXC_BLK][VK];
   double Z[VSTAGES][VXC_BLN][VK];
   double out[VXC_BLN][OUT_LD];  // out[nu][mu]
+  double fac[2][4][TP];         // factor rows of the tile the combiners work on (double-buffered)
   uint64_t full[VSTAGES], empty[VSTAGES];
   uint64_t qfull[VQ], qempty[VQ];
   uint64_t ofull, oempty;
@@ -240,6 +241,10 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const VxcItem
 
   if (warp >= V_MMA_WARPS) {
     // ---------------------------------------------------------------- combiner warps
+    // The stream of (tile, 16-point stage) steps of an item is software-pipelined: the 8 (GGA) 128-bit loads
+    // of step j + 1 are in flight while step j is combined and stored, so 64 KB per SM are on their way at any
+    // time -- the L2 / HBM latency (~1 us loaded) times the 31 GB/s per SM this stream must sustain at the
+    // DMMA peak.  The factor rows of a tile (4 x 1 KB) are staged in shared memory once per tile.
     reg_dec<V_COMB_REGS>();
     const int c = tid - V_MMA_THREADS;
     const int pq = c & 7;    // physical 16-byte pair inside the 128-byte line of a row
@@ -248,45 +253,68 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const VxcItem
     const int i0 = (2 * pq) ^ ((rr & 3) << 2);
     int s = 0;
     uint32_t ph = 0;
+    int fbuf = 0;
     for (int it = 0;; ++it) {
       const VxcSlot sl = next_item(it);
       if (sl.ntiles < 0) break;
       const int nbp = pad16(sl.nbe);
-      const int stride = tile_rows(NMAT, sl.nbe);
+      const size_t stride = (size_t)tile_rows(NMAT, sl.nbe) * TP;
       const size_t ms = (size_t)nbp * TP;
       const bool v0 = sl.n0 + rr < nbp, v1 = sl.n0 + rr + 32 < nbp;  // rows beyond the pad rows: zeros
-      for (int q = 0; q < sl.ntiles; ++q) {
-        const int rowT = sl.row0 + q * stride;
-        const double* __restrict__ src = ws + (size_t)(rowT + sl.n0 + rr) * TP + 2 * pq;
-        const double* __restrict__ fac = ws + (size_t)(rowT + NMAT * nbp + fac_row) * TP + i0;
-        const int nks = (q + 1 < sl.ntiles) ? TP / VK : sl.nks_last;
-        for (int ks = 0; ks < nks; ++ks) {
-          double b[2][NMAT][2], f[NMAT][2];
+      const int nsteps = (sl.ntiles - 1) * (TP / VK) + sl.nks_last;
+      const double* __restrict__ src0 = ws + (size_t)(sl.row0 + sl.n0 + rr) * TP + 2 * pq;
+      const double* __restrict__ fac0 = ws + (size_t)(sl.row0 + NMAT * nbp + fac_row) * TP;
+      auto load = [&](double (&b)[2][NMAT][2], int j) {
+        const double* src = src0 + (size_t)(j >> 3) * stride + (j & 7) * VK;
 #pragma unroll
-          for (int m = 0; m < NMAT; ++m) {
-            ldg128_stream(f[m], fac + (size_t)m * TP + ks * VK);
-            if (v0) ldg128_stream(b[0][m], src + m * ms + ks * VK);
-            else b[0][m][0] = b[0][m][1] = 0.;
-            if (v1) ldg128_stream(b[1][m], src + m * ms + (size_t)32 * TP + ks * VK);
-            else b[1][m][0] = b[1][m][1] = 0.;
-          }
-          double z[2][2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              double acc = f[0][j] * b[u][0][j];
-#pragma unroll
-              for (int m = 1; m < NMAT; ++m) acc = fma(f[m][j], b[u][m][j], acc);
-              z[u][j] = acc;
-            }
-          mbar_wait(&S.empty[s], ph ^ 1);
-          *reinterpret_cast<double2*>(&S.Z[s][rr][2 * pq]) = make_double2(z[0][0], z[0][1]);
-          *reinterpret_cast<double2*>(&S.Z[s][rr + 32][2 * pq]) = make_double2(z[1][0], z[1][1]);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&S.full[s]);
-          if (++s == VSTAGES) { s = 0; ph ^= 1; }
+        for (int m = 0; m < NMAT; ++m) {
+          if (v0) ldg128_stream(b[0][m], src + m * ms);
+          else b[0][m][0] = b[0][m][1] = 0.;
+          if (v1) ldg128_stream(b[1][m], src + m * ms + (size_t)32 * TP);
+          else b[1][m][0] = b[1][m][1] = 0.;
         }
+      };
+      // factor rows of tile q -> S.fac[fbuf]: 4 KB (GGA) = one 128-bit load + store per combiner thread
+      auto stage_factors = [&](int q) {
+        if (c < NMAT * (TP / 2)) {
+          double f[2];
+          ldg128_stream(f, fac0 + (size_t)q * stride + (size_t)(c >> 6) * TP + 2 * (c & 63));
+          *reinterpret_cast<double2*>(&S.fac[fbuf][c >> 6][2 * (c & 63)]) = make_double2(f[0], f[1]);
+        }
+        named_bar_sync(1, V_COMB_THREADS);
+      };
+      double bn[2][NMAT][2];
+      load(bn, 0);
+      for (int j = 0; j < nsteps; ++j) {
+        if ((j & 7) == 0) {
+          fbuf ^= 1;  // the previous tile's rows may still be read by slower warps of this stage
+          stage_factors(j >> 3);
+        }
+        double bc[2][NMAT][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) { bc[u][m][0] = bn[u][m][0]; bc[u][m][1] = bn[u][m][1]; }
+        if (j + 1 < nsteps) load(bn, j + 1);
+        double z[2][2];
+        const int col = (j & 7) * VK + i0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) z[u][0] = z[u][1] = 0.;
+#pragma unroll
+        for (int m = 0; m < NMAT; ++m) {
+          const double2 f = *reinterpret_cast<const double2*>(&S.fac[fbuf][m][col]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            z[u][0] = (m == 0) ? f.x * bc[u][0][0] : fma(f.x, bc[u][m][0], z[u][0]);
+            z[u][1] = (m == 0) ? f.y * bc[u][0][1] : fma(f.y, bc[u][m][1], z[u][1]);
+          }
+        }
+        mbar_wait(&S.empty[s], ph ^ 1);
+        *reinterpret_cast<double2*>(&S.Z[s][rr][2 * pq]) = make_double2(z[0][0], z[0][1]);
+        *reinterpret_cast<double2*>(&S.Z[s][rr + 32][2 * pq]) = make_double2(z[1][0], z[1][1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.full[s]);
+        if (++s == VSTAGES) { s = 0; ph ^= 1; }
       }
     }
     return;

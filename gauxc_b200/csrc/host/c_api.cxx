@@ -407,6 +407,21 @@ void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctio
   C_CATCH(status)
 }
 
+void gauxc_b200_functional_eval_host_pol_full(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
+                                              const double* rho2, const double* gamma3, double* eps, double* vrho2,
+                                              double* vgamma3) {
+  C_TRY(status)
+  const auto& f = **FN(functional);
+  for (int64_t i = 0; i < npts; ++i) {
+    const auto o = gxb::eval_functional_pol(f.desc, rho2[2 * i], rho2[2 * i + 1], gamma3[3 * i], gamma3[3 * i + 1],
+                                            gamma3[3 * i + 2]);
+    eps[i] = o.eps;
+    vrho2[2 * i] = o.va; vrho2[2 * i + 1] = o.vb;
+    vgamma3[3 * i] = o.vaa; vgamma3[3 * i + 1] = o.vab; vgamma3[3 * i + 2] = o.vbb;
+  }
+  C_CATCH(status)
+}
+
 void gauxc_b200_functional_eval_host_pol_gga(GauXCStatus* status, int nkern, const int* kern, const double* coeff,
                                              int64_t npts, const double* rho2, const double* gamma3, double* eps,
                                              double* vrho2, double* vgamma3) {

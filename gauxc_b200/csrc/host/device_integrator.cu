@@ -1025,9 +1025,9 @@ void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t 
 
 // UKS: Ps = P_alpha + P_beta, Pz = P_alpha - P_beta
 // (reference_replicated_xc_host_integrator_exc_vxc.hpp:107-601 with is_uks; device counterpart
-// incore_replicated_xc_device_integrator_exc_vxc.hpp:46-386).  LDA, per batch: collocation, the fused kernel
-// over Ps (rho_s per point), the fused kernel over Pz (rho_z -> rho_+- -> polarised functional -> factors of
-// Z_s and Z_z), the VXC rank update twice (factor rows 0 and 4).
+// incore_replicated_xc_device_integrator_exc_vxc.hpp:46-386).  Per batch: collocation, the fused kernel over Ps
+// (rho_s [, grad n] per point), the fused kernel over Pz (rho_z [, grad M_z] -> rho_+- [, gamma_++,+-,--] ->
+// polarised functional -> factors of Z_s and Z_z), the VXC rank update twice (factor rows 0.. and 4..).
 void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
                              double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC,
                              bool do_vxc) {
@@ -1035,17 +1035,17 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
   check_dims(*lb_, m, n, ldpz, ldvxcz, do_vxc);
   if (!lb_->state().modified_weights_are_stored) GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
   if (!func_->polarized) GAUXC_GENERIC_EXCEPTION("UKS Evaluation Requires A Polarized Functional");
-  if (func_->is_gga()) GAUXC_GENERIC_EXCEPTION("UKS GGA NYI in B200 path");
+  const bool gga = func_->is_gga();
   auto& I = *impl_;
   cudaStream_t s = I.stream;
   const size_t nbf = (size_t)m;
   const size_t nn = nbf * nbf;
   I.ensure_matrices(nbf, red_->comm_size(), true);
-  if (I.dPtri.n != nn) {
+  if (!gga && I.dPtri.n != nn) {
     I.dPtri.alloc(nn);
     CUDA_CHECK(cudaMemsetAsync(I.dPtri.p, 0, sizeof(double) * nn, s));
   }
-  if (I.dPtri_z.n != nn) {
+  if (!gga && I.dPtri_z.n != nn) {
     I.dPtri_z.alloc(nn);
     CUDA_CHECK(cudaMemsetAsync(I.dPtri_z.p, 0, sizeof(double) * nn, s));
   }
@@ -1055,9 +1055,10 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
   upload_density_(Pz, ldpz, I.dPz.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
-  I.prepare(*lb_, 1, true);
+  I.prepare(*lb_, gga ? 4 : 1, !gga);
   auto& plan = *I.plan;
-  if (I.d_uks_den.n < plan.npts) I.d_uks_den.alloc(std::max<size_t>(1, plan.npts));
+  const size_t nden = gga ? 4 : 1;  // rho_s (+ grad n) carried from the pass over Ps to the pass over Pz
+  if (I.d_uks_den.n < nden * plan.npts) I.d_uks_den.alloc(std::max<size_t>(1, nden * plan.npts));
   auto& sc = *I.sched;
   const gxb::PlanView pv = plan.view();
   const int inbf = plan.nbf;
@@ -1069,26 +1070,33 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
   }
   CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
   CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
-  gxb::launch_sym_half(I.dP.p, inbf, I.dPtri.p, inbf, s);
-  gxb::launch_sym_half(I.dPz.p, inbf, I.dPtri_z.p, inbf, s);
-  long long launches = 2;
+  long long launches = 0;
+  const double *dPs = I.dP.p, *dPzz = I.dPz.p;
+  if (!gga) {  // LDA: the triangular quadratic form, as in the RKS path
+    gxb::launch_sym_half(I.dP.p, inbf, I.dPtri.p, inbf, s);
+    gxb::launch_sym_half(I.dPz.p, inbf, I.dPtri_z.p, inbf, s);
+    dPs = I.dPtri.p;
+    dPzz = I.dPtri_z.p;
+    launches = 2;
+  }
   size_t ib = 0;
   for (auto& b : sc.batches) {
     const int nt = b.tile_end - b.tile_begin;
     const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
-    gxb::launch_collocation(pv, tl, nt, I.d_ws.p, false, s);
-    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, I.dPtri.p, inbf,
-                                 func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 1, I.d_uks_den.p));
-    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + nb + ib, sc.ncta, I.d_ws.p, I.dPtri_z.p,
-                                 inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 2,
-                                 I.d_uks_den.p));
+    gxb::launch_collocation(pv, tl, nt, I.d_ws.p, gga, s);
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + ib, sc.ncta, I.d_ws.p, dPs, inbf,
+                                 func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 1, I.d_uks_den.p,
+                                 plan.npts));
+    CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + nb + ib, sc.ncta, I.d_ws.p, dPzz, inbf,
+                                 func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 2, I.d_uks_den.p,
+                                 plan.npts));
     launches += 3;
     if (do_vxc) {
       CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                                 sc.d_counters.p + 2 * nb + ib, sc.ncta, I.d_ws.p, false, 0, true, I.dVXC.p, inbf,
+                                 sc.d_counters.p + 2 * nb + ib, sc.ncta, I.d_ws.p, gga, 0, !gga, I.dVXC.p, inbf,
                                  s));
       CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                                 sc.d_counters.p + 3 * nb + ib, sc.ncta, I.d_ws.p, false, 4, true, I.dVXCz.p,
+                                 sc.d_counters.p + 3 * nb + ib, sc.ncta, I.d_ws.p, gga, 4, !gga, I.dVXCz.p,
                                  inbf, s));
       launches += 2;
     }

@@ -366,6 +366,11 @@ void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional 
 void gauxc_b200_functional_eval_host_pol(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
                                          const double* rho_a, const double* rho_b, double* eps, double* vrho_a,
                                          double* vrho_b);
+/* the functional's spin-polarised evaluation as the UKS GGA path of the fused kernel performs it (host evaluation
+ * for unit tests): rho2 = {rho_a, rho_b}, gamma3 = {sigma_aa, sigma_ab, sigma_bb} per point */
+void gauxc_b200_functional_eval_host_pol_full(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,
+                                              const double* rho2, const double* gamma3, double* eps, double* vrho2,
+                                              double* vgamma3);
 /* spin-polarised GGA kernels prepared for the UKS GGA path (host evaluation for unit tests; kern: 0 = B88
  * exchange, 1 = LYP correlation; rho2 = {rho_a, rho_b}, gamma3 = {sigma_aa, sigma_ab, sigma_bb} per point) */
 void gauxc_b200_functional_eval_host_pol_gga(GauXCStatus* status, int nkern, const int* kern, const double* coeff,

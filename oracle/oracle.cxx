@@ -382,6 +382,48 @@ D5 lyp_energy(const D5& ra, const D5& rb, const D5& saa, const D5& sab, const D5
   return -(D5(a) * D5(4.) / den * rab / rho) - D5(a * b) * omega * brace;
 }
 
+inline D5 dlog(const D5& a) { return lift(a, std::log(a.v), 1. / a.v); }
+
+// PBE correlation for a spin-polarised density, written as in the paper (Perdew, Burke, Ernzerhof, PRL 77,
+// 3865 (1996), eqs. 3, 7, 8) on top of PW92 (Perdew & Wang, PRB 45, 13244 (1992), eqs. 8-10, the "modified"
+// higher-precision constants libxc / ExchCXX use inside PBE):
+//   eps_c(rs, zeta) = eps0 + alpha_c f(zeta)/f''(0) (1 - zeta^4) + (eps1 - eps0) f(zeta) zeta^4,
+//   H = gamma phi^3 ln{1 + (beta/gamma) t^2 [1 + A t^2] / [1 + A t^2 + A^2 t^4]},
+//   t = |grad n| / (2 phi k_s n),  k_s = sqrt(4 k_F / pi),  A = (beta/gamma) / (exp(-eps_c / (gamma phi^3)) - 1)
+D5 pbe_c_pol_energy(const D5& na, const D5& nb, const D5& saa, const D5& sab, const D5& sbb) {
+  const D5 n = na + nb;
+  if (n.v <= 1e-12) return D5(0.);
+  const double beta = 0.06672455060314922, gamma = (1. - std::log(2.)) / (PI * PI);
+  const D5 rs = dpow(D5(3. / (4. * PI)) / n, 1. / 3.);
+  auto Gpw = [&](double A, double a1, double b1, double b2, double b3, double b4) {
+    const D5 q1 = D5(2. * A) * (D5(b1) * dsqrt(rs) + D5(b2) * rs + D5(b3) * dpow(rs, 1.5) + D5(b4) * rs * rs);
+    return D5(-2. * A) * (D5(1.) + D5(a1) * rs) * dlog(D5(1.) + D5(1.) / q1);
+  };
+  const D5 e0 = Gpw(0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const D5 e1 = Gpw(0.01554535, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  const D5 mac = Gpw(0.0168869, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);  // -alpha_c
+  D5 zeta = (na - nb) / n;
+  const double zmax = 1. - 1e-12;
+  if (zeta.v > zmax) zeta = D5(zmax);
+  if (zeta.v < -zmax) zeta = D5(-zmax);
+  const D5 up = D5(1.) + zeta, dn = D5(1.) - zeta;
+  const double fpp0 = 1.709920934161365617563962776245;  // f''(0) = 8 / (9 (2^{4/3} - 2))
+  const D5 fz = (dpow(up, 4. / 3.) + dpow(dn, 4. / 3.) - D5(2.)) / D5(std::pow(2., 4. / 3.) - 2.);
+  const D5 z4 = zeta * zeta * zeta * zeta;
+  const D5 ec = e0 - mac * fz / D5(fpp0) * (D5(1.) - z4) + (e1 - e0) * fz * z4;
+  const D5 phi = (dpow(up, 2. / 3.) + dpow(dn, 2. / 3.)) / D5(2.);
+  const D5 phi3 = phi * phi * phi;
+  D5 grad2 = saa + D5(2.) * sab + sbb;
+  if (grad2.v < 1e-32) grad2 = D5(1e-32);
+  const D5 kF = dpow(D5(3. * PI * PI) * n, 1. / 3.);
+  const D5 ks2 = D5(4. / PI) * kF;
+  const D5 t2 = grad2 / (D5(4.) * phi * phi * ks2 * n * n);
+  const D5 A = D5(beta / gamma) / (dexp(-(ec / (D5(gamma) * phi3))) - D5(1.));
+  const D5 At2 = A * t2;
+  const D5 H = D5(gamma) * phi3 * dlog(D5(1.) + D5(beta / gamma) * t2 * (D5(1.) + At2) / (D5(1.) + At2 + At2 * At2));
+  return n * (ec + H);
+}
+
 // gamma = (sigma_aa, sigma_ab, sigma_bb) interleaved per point like the reference (eval_uvvar_gga_uks)
 void eval_func_pol_gga(const Func& f, int npts, const double* rho2, const double* gamma3, double* eps,
                        double* vrho2, double* vgamma3) {
@@ -397,6 +439,26 @@ void eval_func_pol_gga(const Func& f, int npts, const double* rho2, const double
       switch (f.kern[k]) {
         case K_B88_X: e = b88_energy(ra, rb, saa, sbb); break;
         case K_LYP_C: e = lyp_energy(ra, rb, saa, sab, sbb); break;
+        case K_PBE_C: e = pbe_c_pol_energy(ra, rb, saa, sab, sbb); break;
+        case K_SLATER_X:
+        case K_VWN5_C: {  // LDA kernels inside a GGA functional (B3LYP): closed forms, d/d sigma = 0
+          double el, va, vb;
+          if (f.kern[k] == K_SLATER_X) f_slater_pol(ra.v, rb.v, el, va, vb);
+          else f_vwn5_pol(ra.v, rb.v, el, va, vb);
+          e = D5(el * (ra.v + rb.v));
+          e.d[0] = va; e.d[1] = vb;
+          break;
+        }
+        case K_PBE_X:
+        case K_REVPBE_X: {  // exact spin scaling E_x[na, nb] = (E_x[2 na] + E_x[2 nb]) / 2
+          const double kappa = f.kern[k] == K_PBE_X ? 0.8040 : 1.245;
+          double ea, va, sa, eb, vb, sb;
+          f_pbe_x(2. * ra.v, 4. * saa.v, ea, va, sa, kappa);
+          f_pbe_x(2. * rb.v, 4. * sbb.v, eb, vb, sb, kappa);
+          e = D5(ra.v * ea + rb.v * eb);
+          e.d[0] = va; e.d[1] = vb; e.d[2] = 2. * sa; e.d[4] = 2. * sb;
+          break;
+        }
         default: e = D5(std::nan("")); break;  // not restated for UKS GGA
       }
       E = E + D5(f.coeff[k]) * e;

@@ -338,6 +338,42 @@ def test_uks_lda_golden_and_oracle(orc):
     assert abs(integ.eval_exc_uks(Ps, Pz) - exc) <= 1e-12
 
 
+@pytest.mark.parametrize("func", ["BLYP", "PBE", "B3LYP"])
+def test_uks_gga_golden_and_oracle(orc, func):
+    """UKS GGA on the reference's cytosine BLYP fixture (tests/xc_integrator.cxx:468-472): Device against the oracle's
+    UKS GGA path on the same tasks (1e-10) and, for BLYP, against the golden VXC_s / VXC_z with the reference's own
+    criterion |VXC - ref|_F / nbf < 1e-10.  PBE / B3LYP run on the same densities (no fixture: oracle only); the
+    spin-unpolarised limit reproduces RKS."""
+    d = systems.golden("cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks")
+    atoms = [(int(Z), *xyz) for Z, xyz in zip(d["mol_Z"], d["mol_xyz"])]
+    shells = []
+    for i in range(len(d["sh_l"])):
+        n = int(d["sh_nprim"][i])
+        shells.append(dict(l=int(d["sh_l"][i]), pure=bool(d["sh_pure"][i]), exps=list(d["sh_alpha"][i, :n]),
+                           coefs=list(d["sh_coeff"][i, :n]), origin=tuple(d["sh_O"][i]), tol=np.finfo(float).eps))
+    _, basis, lb = make_lb(atoms, shells, "UltraFineGrid", "Robust", normalize=False, device=True)
+    gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(lb)
+    tasks = lb.export_tasks()
+    nbf = basis.nbf()
+    Ps, Pz = d["DENSITY_SCALAR"], d["DENSITY_Z"]
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func, polarized=True), lb)
+    exc, vs, vz = integ.eval_exc_vxc_uks(Ps, Pz)
+    ref = orc.exc_vxc_uks(basis.flat(), nbf, Ps, Pz, tasks, func)
+    assert abs(exc - ref["exc"]) <= TOL
+    assert np.abs(vs - ref["vxc_s"]).max() <= TOL and np.abs(vz - ref["vxc_z"]).max() <= TOL
+    assert abs(integ.stats()["n_el"] - ref["nel"]) <= TOL
+    assert np.array_equal(vs, vs.T) and np.array_equal(vz, vz.T)
+    assert abs(integ.eval_exc_uks(Ps, Pz) - exc) <= 1e-12
+    if func == "BLYP":
+        assert np.linalg.norm(vs - d["VXC_SCALAR"]) / nbf < 1e-10 and np.linalg.norm(vz - d["VXC_Z"]) / nbf < 1e-10
+        assert abs(exc - float(d["EXC"][0])) < 5e-9
+    # Pz = 0: UKS(Ps) == RKS(P_alpha = Ps / 2), VXC_z == 0
+    exc0, vs0, vz0 = integ.eval_exc_vxc_uks(Ps, np.zeros_like(Pz))
+    rks = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func), lb)
+    exc_r, vxc_r = rks.eval_exc_vxc(0.5 * Ps)
+    assert abs(exc0 - exc_r) <= 1e-10 and np.abs(vs0 - vxc_r).max() <= 1e-10 and np.abs(vz0).max() <= 1e-12
+
+
 def test_empty_task_list_gives_zero():
     atoms = systems.geometry("water")
     shells = systems.make_basis_shells(atoms, "cc-pvdz")

@@ -238,7 +238,7 @@ def test_functionals_product_vs_oracle_and_fd(orc):
     rho = 10 ** rng.uniform(-9, 2, 4000)
     s = 10 ** rng.uniform(-2, 1.5, 4000)  # reduced gradient
     sigma = (s * 2 * (3 * np.pi ** 2) ** (1 / 3) * rho ** (4 / 3)) ** 2
-    for fn in ("SVWN5", "SPW92", "LDA", "PBE", "PBE0"):
+    for fn in ("SVWN5", "SPW92", "LDA", "PBE", "PBE0", "BLYP", "B3LYP", "REVPBE"):
         f = gx.Functional(fn)
         e1, v1, s1 = f.eval_host(rho, sigma)
         e2, v2, s2 = orc.functional(fn, rho, sigma)
@@ -254,12 +254,65 @@ def test_functionals_product_vs_oracle_and_fd(orc):
         em, _, _ = orc.functional(fn, r_ - h, g_)
         fd = ((r_ + h) * ep - (r_ - h) * em) / (2 * h)
         assert (np.abs(fd - vr) / np.abs(vr)).max() < 1e-6, fn
-        if fn in ("PBE", "PBE0"):
+        if fn in ("PBE", "PBE0", "BLYP", "B3LYP", "REVPBE"):
             hs = 1e-4 * g_
             ep, _, _ = orc.functional(fn, r_, g_ + hs)
             em, _, _ = orc.functional(fn, r_, g_ - hs)
             fd = r_ * (ep - em) / (2 * hs)
             assert (np.abs(fd - vs) / np.abs(vs)).max() < 1e-5, fn
+
+
+def test_polarised_functionals_product_vs_oracle_limits_and_fd(orc):
+    """Spin-polarised evaluation of every functional the UKS path accepts: (1) product (host hook over the
+    __host__ __device__ source of the fused kernel) vs the oracle's separately written forms; (2) at zeta = 0
+    both reproduce the unpolarised functional, which the reference's benzene SVWN5 / PBE0 goldens pin (the
+    reference has no PBE UKS fixture: this limit, the BLYP UKS fixture for the UKS machinery and (3) finite
+    differences of E are what holds polarised PBE in place); (4) spin-flip symmetry."""
+    import gauxc_b200 as gx
+    rng = np.random.default_rng(21)
+    n = 2000
+    ra, rb = 10 ** rng.uniform(-6, 1.2, n), 10 ** rng.uniform(-6, 1.2, n)
+    ga, gb = rng.standard_normal((n, 3)) * ra[:, None] ** (4 / 3), rng.standard_normal((n, 3)) * rb[:, None] ** (4 / 3)
+    saa, sab, sbb = (ga * ga).sum(1), (ga * gb).sum(1), (gb * gb).sum(1)
+    flat = lambda r: [r[0], *r[1], *r[2]]  # noqa: E731
+    for fn in ("PBE", "PBE0", "BLYP", "B3LYP", "REVPBE", "SVWN5"):
+        f = gx.Functional(fn, polarized=True)
+        got = f.eval_host_pol_full(ra, rb, saa, sab, sbb)
+        if fn == "SVWN5":
+            e, va, vb = orc.functional_pol_lda(fn, ra, rb)
+            ref = (e, (va, vb), (0 * e, 0 * e, 0 * e))
+        else:
+            ref = orc.functional_pol_gga(fn, ra, rb, saa, sab, sbb)
+        for x, y in zip(flat(got), flat(ref)):
+            assert np.all(np.isfinite(x)), fn
+            assert (np.abs(x - y) / (np.abs(y) + 1e-11)).max() < 1e-8, fn
+        # spin flip
+        sw = f.eval_host_pol_full(rb, ra, sbb, sab, saa)
+        assert np.allclose(sw[0], got[0], rtol=1e-12, atol=1e-14)
+        assert np.allclose(sw[1][0], got[1][1], rtol=1e-11, atol=1e-13)
+        assert np.allclose(sw[2][0], got[2][2], rtol=1e-10, atol=1e-13)
+        # zeta = 0 limit against the unpolarised functional
+        rho = 10 ** rng.uniform(-5, 1.5, n)
+        sred = 10 ** rng.uniform(-2, 1.2, n)
+        sigma = (sred * 2 * (3 * np.pi ** 2) ** (1 / 3) * rho ** (4 / 3)) ** 2
+        e0, v0, s0 = gx.Functional(fn).eval_host(rho, sigma)
+        ep, (va, vb), (vaa, vab, vbb) = f.eval_host_pol_full(rho / 2, rho / 2, sigma / 4, sigma / 4, sigma / 4)
+        assert (np.abs(ep - e0) / (np.abs(e0) + 1e-13)).max() < 1e-10, fn
+        assert (np.abs(va - v0) / (np.abs(v0) + 1e-13)).max() < 1e-9 and np.allclose(va, vb, rtol=1e-12), fn
+        if fn != "SVWN5":
+            assert (np.abs(0.25 * (vaa + vab + vbb) - s0) / (np.abs(s0) + 1e-13)).max() < 1e-8, fn
+        # finite differences of E = (ra + rb) eps in rho_a and sigma_ab on a well-conditioned range
+        m = (ra > 1e-3) & (rb > 1e-3) & (ra < 10) & (rb < 10)
+        a_, b_, x_, y_, z_ = ra[m], rb[m], saa[m], sab[m], sbb[m]
+        E = lambda a, b, x, y, z: (a + b) * f.eval_host_pol_full(a, b, x, y, z)[0]  # noqa: E731
+        _, (va_, _), (_, vab_, _) = f.eval_host_pol_full(a_, b_, x_, y_, z_)
+        h = 1e-5 * a_
+        fd = (E(a_ + h, b_, x_, y_, z_) - E(a_ - h, b_, x_, y_, z_)) / (2 * h)
+        assert (np.abs(fd - va_) / (np.abs(va_) + 1e-8)).max() < 1e-5, fn
+        if fn not in ("SVWN5",):
+            hs = 1e-4 * np.sqrt(x_ * z_) + 1e-12
+            fd = (E(a_, b_, x_, y_ + hs, z_) - E(a_, b_, x_, y_ - hs, z_)) / (2 * hs)
+            assert (np.abs(fd - vab_) / (np.abs(vab_) + 1e-6)).max() < 1e-4, fn
 
 
 def test_functional_thresholds(orc):
