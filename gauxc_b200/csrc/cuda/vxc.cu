@@ -40,6 +40,7 @@ constexpr int V_MMA_THREADS = V_MMA_WARPS * 32, V_COMB_THREADS = V_COMB_WARPS * 
 constexpr int V_THREADS = (V_MMA_WARPS + V_COMB_WARPS + V_SCAT_WARPS + 4) * 32;
 // launch allocation 24 warps x 80; after re-partitioning 8 x 112 + 8 x 96 + 4 x 40 + 4 x 24
 constexpr int V_MMA_REGS = 112, V_COMB_REGS = 96, V_SCAT_REGS = 40, V_PROD_REGS = 24;
+static_assert(8 * V_MMA_REGS + 8 * V_COMB_REGS + 4 * V_SCAT_REGS + 4 * V_PROD_REGS <= 24 * 80, "register pool");
 constexpr int OUT_LD = VXC_BLK + 2;  // conflict-free accumulator dump (C fragment: rows g, columns 2t, 2t+1)
 
 struct VxcSlot {
@@ -245,7 +246,7 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapV, PlanView pv, const VxcItem
     // of step j + 1 are in flight while step j is combined and stored, so 64 KB per SM are on their way at any
     // time -- the L2 / HBM latency (~1 us loaded) times the 31 GB/s per SM this stream must sustain at the
     // DMMA peak.  The factor rows of a tile (4 x 1 KB) are staged in shared memory once per tile.
-    reg_dec<V_COMB_REGS>();
+    reg_inc<V_COMB_REGS>();  // 96 > the 80 of the launch allocation
     const int c = tid - V_MMA_THREADS;
     const int pq = c & 7;    // physical 16-byte pair inside the 128-byte line of a row
     const int rr = c >> 3;   // rows rr and rr + 32 of the 64-row block (same row & 3: same swizzle)

@@ -1,5 +1,6 @@
 // Lebedev expansion, radial rules, pruning specs, atomic grid generation + octree batcher.
 #include "grid.hpp"
+#include <cstdlib>
 #include <algorithm>
 #include <mutex>
 
@@ -249,6 +250,8 @@ void split(std::vector<Pt>& pts, size_t b, size_t e, std::array<double, 3> lo,
       g.points.push_back(pts[i].p);
       g.weights.push_back(pts[i].w);
     }
+    static const bool cell_box = std::getenv("GAUXC_B200_BATCH_BOX_CELL") != nullptr;
+    if (cell_box) { g.lo = lo; g.up = up; }
     out.push_back(std::move(g));
     return;
   }

@@ -31,6 +31,12 @@ for ST in "$@"; do
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$B -s ${C:-3} -c 1 -f -o gpurun_out/${TAG}_${A}_${B} \
         python bench.py --workload $A --steps 1 --warmup 1 --no-cpu-baseline --others "" --parity-seconds 0.5 > gpurun_out/${TAG}_ncu_${A}_${B}.log 2>&1
       echo "ncu $A $B exit $?" ;;
+    tpi)   # bench:<workload> with GAUXC_B200_TILES_PER_ITEM=<B>
+      GAUXC_B200_TILES_PER_ITEM=$B timeout 900 python bench.py --workload $A --steps 3 --warmup 2 --others "" --no-cpu-baseline --parity-seconds 1 > gpurun_out/${TAG}_tpi${B}_${A}.json 2> gpurun_out/${TAG}_tpi${B}_${A}.err
+      echo "tpi $B $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_tpi${B}_${A}.json | head -3 ;;
+    lib)   # bench:<workload> with the diagnostic library variant <B>
+      GAUXC_B200_LIB=$PWD/gauxc_b200/libgauxc_b200_$B.so timeout 900 python bench.py --workload $A --steps 3 --warmup 2 --others "" --no-cpu-baseline --parity-seconds 1 > gpurun_out/${TAG}_lib${B}_${A}.json 2> gpurun_out/${TAG}_lib${B}_${A}.err
+      echo "lib $B $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_lib${B}_${A}.json | head -3 ;;
     *) echo "unknown stage $ST" ;;
   esac
 done
