@@ -7,15 +7,12 @@
 //      incore_replicated_xc_device_integrator_exc_vxc.hpp:254-257).  Resident across calls.
 //   * a task is cut into TILES of <= TP consecutive points that share the task's shell list.
 //   * per batch of tiles a workspace holds, per tile, NMAT matrices [nbp][TP] (nbp = nbe
-//     rounded up to 16 rows, pad rows are zero): B, (dBx,dBy,dBz for GGA), followed by FAC_ROWS
-//     rows of per-point factors (a, fx, fy, fz | the same for the z channel of UKS) written by
-//     the fused kernel: Z = a B + fx dBx + fy dBy + fz dBz is never stored, the VXC kernel forms
-//     it on the fly.  Matrix rows are 1 KB (point index fastest) and XOR-swizzled: element
-//     (row, i) lives at column i ^ ((row & 3) << 2).  With that one permutation a TMA box of
-//     16 rows x 128 points (the A operand of X = B P) and a box of 128 rows x 16 points (the
-//     B^T operand of B^T Z) land in shared memory dense AND conflict-free for the m8n8k4 DMMA
-//     fragment loads, while every global row access stays fully coalesced.  Factor rows are
-//     not swizzled.
+//     rounded up to 16 rows, pad rows are zero): B, (dBx,dBy,dBz for GGA), Z (UKS: Z_s, Z_z).  Rows are
+//     1 KB (point index fastest) and XOR-swizzled: element (row, i) lives at column
+//     i ^ ((row & 3) << 2).  With that one permutation a TMA box of 16 rows x 128 points (the
+//     A operand of X = B P) and TMA boxes of 128 / 64 rows x 16 points (the operands of B^T Z)
+//     land in shared memory dense AND conflict-free for the m8n8k4 DMMA fragment loads,
+//     while every global row access stays fully coalesced.
 #pragma once
 #include <cstdint>
 
@@ -28,14 +25,13 @@
 namespace gxb {
 
 constexpr int TP = 128;  // points per tile
-constexpr int FAC_ROWS = 16;  // factor rows appended to a tile's matrices (8 used, 16 keeps row alignment)
 
 GXB_HOST_DEVICE inline int pad16(int nbe) { return (nbe + 15) & ~15; }
 // columns of a tile that are ever written / read: npts rounded up to 32
 GXB_HOST_DEVICE inline int tile_width(int npts) { return (npts + 31) & ~31; }
 GXB_HOST_DEVICE inline int swz(int row, int i) { return i ^ ((row & 3) << 2); }
-// workspace rows of one tile: nmat matrices of pad16(nbe) rows + the factor rows
-GXB_HOST_DEVICE inline int tile_rows(int nmat, int nbe) { return nmat * pad16(nbe) + FAC_ROWS; }
+// workspace rows of one tile: nmat matrices of pad16(nbe) rows
+GXB_HOST_DEVICE inline int tile_rows(int nmat, int nbe) { return nmat * pad16(nbe); }
 
 struct DevShell {
   double x, y, z;

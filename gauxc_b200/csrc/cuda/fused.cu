@@ -1,6 +1,6 @@
 // K_F: the fused, persistent, warp-specialised middle of the EXC/VXC path.  Per tile of 128 points
 //
-//     X = B P_sub (FP64 DMMA)  ->  rho, grad rho  ->  functional, weights, EXC/N_EL  ->  Z factors
+//     X = B P_sub (FP64 DMMA)  ->  rho, grad rho  ->  functional, weights, EXC/N_EL  ->  Z
 //
 // replacing the reference device path's pack_submat + per-task cuBLAS dgemm + uvvars kernels +
 // ExchCXX device call + factor/inc kernels + zmat kernel (SURVEY.md 2.1 K2-K9;
@@ -10,7 +10,7 @@
 //
 // One persistent CTA per SM pulls tiles from a device-side queue (atomic counter, task order: the
 // tiles in flight share P_sub / VXC regions in L2; no static partition to go out of balance) and
-// broadcasts them to its roles through a 4-slot shared-memory ring.  Three role families, 20 warps:
+// broadcasts them to its roles through a 4-slot shared-memory ring.  Five roles, 20 warps:
 //   producer (4 warps): TMA box loads of B^T (16 basis rows x 128 points) + LDGSTS gather of the
 //                       matching 16 x 64 block of P through the task's AO map (4 rows per warp),
 //                       5-stage mbarrier ring
@@ -18,16 +18,13 @@
 //                       row halves of a column strip on the SAME SM sub-partition, so ragged tiles
 //                       (npts < 128) load the four DMMA pipes evenly.  Each finished chunk is handed
 //                       to the density warps through shared memory
-//   density  (8 warps): lane = 4 consecutive grid points, warp = every 8th basis row:
-//                       rho += X.B, grad rho += X.dB with 256-bit streaming loads (64 KB in flight per SM);
-//                       after the last chunk the first four of them evaluate the functional, the weight
-//                       scaling and the EXC/N_EL tile partials (thread = point) and leave the four factors of
-//                       Z = a B + fx dBx + fy dBy + fz dBz (a = 1/2 w vrho, f = 2 w vgamma grad rho) in the
-//                       tile's factor rows.  Z itself is never written: the VXC kernel forms it on the fly,
-//                       so this kernel reads B / dB once (B a second time out of L2) and writes 32 bytes per
-//                       point -- 4 matrix passes of HBM traffic where the version with a Z stage moved 10.
-// so the HBM-bound stream of the density stage runs underneath the DMMA work of the next chunk / next
-// tile instead of in kernels of their own, and X never leaves the SM.
+//   density  (4 warps): lane = 4 consecutive grid points, warp = every 4th basis row:
+//                       rho += X.B, grad rho += X.dB with 256-bit streaming loads
+//   zmat     (4 warps): functional, weight scaling, EXC/N_EL tile partials (thread = point), then
+//                       Z = 1/2 vrho B + 2 vgamma (grad rho . dB) with 256-bit loads/stores, rows walked
+//                       in reverse so the most recently streamed rows are still in L2
+// so the HBM-bound streams of the density and Z stages run underneath the DMMA work of the next
+// chunk / next tile instead of in kernels of their own, and X never leaves the SM.
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "xc_functionals.cuh"
@@ -49,33 +46,35 @@ constexpr int FSTAGES = 5;
 constexpr int TQ = 4;         // tile-queue ring slots
 constexpr int P_LD = FN + 4;   // (ld mod 16) == 4: conflict-free DMMA B-fragment loads
 constexpr int X_LD = TP + 2;   // conflict-free C-fragment stores, rows stay 16-byte aligned
-constexpr int MMA_WARPS = 8, DEN_WARPS = 8, FUNC_WARPS = 4, PROD_WARPS = 4;
-constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, FUNC_THREADS = FUNC_WARPS * 32;
-// warps 0-7 MMA, 8-15 density (8-11 also evaluate the functional), 16-19 producers (whole warpgroups per
-// role family so that setmaxnreg can move registers from the producers to the MMA warps)
+constexpr int MMA_WARPS = 8, DEN_WARPS = 4, Z_WARPS = 4, PROD_WARPS = 4;
+constexpr int MMA_THREADS = MMA_WARPS * 32, DEN_THREADS = DEN_WARPS * 32, Z_THREADS = Z_WARPS * 32;
+// warps 0-7 MMA, 8-11 density, 12-15 functional+Z, 16-19 producers (one warpgroup per role family so
+// that setmaxnreg can move registers from the producers to the MMA warps)
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + PROD_THREADS;
-// launch allocation 20 warps x 96; after re-partitioning 8 x 112 (MMA) + 8 x 104 (density) + 4 x 48
-// (producers) (must not exceed it)
-constexpr int MMA_REGS = 112, DEN_REGS = 104, PROD_REGS = 48;
+constexpr int FUSED_THREADS = MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS;
+// launch allocation 20 warps x 96; after re-partitioning 8 x 112 (MMA) + 4 x 112 (density) + 4 x 96 (Z)
+// + 4 x 48 (producers) (must not exceed it)
+constexpr int MMA_REGS = 112, DEN_REGS = 112, PROD_REGS = 48;
 
 struct FusedSmem {
   double A[FSTAGES][FK][TP];    // TMA destination, dense + global XOR swizzle
   double P[FSTAGES][FK][P_LD];
   double X[FN][X_LD];
   double dpart[DEN_WARPS][4][TP];  // per density warp partial sums
-  double red[2][2][FUNC_WARPS];
+  double den[4][TP];
+  double fac[2][8][TP];            // 1/2 w vrho, 2 w vsigma grad rho per point (UKS GGA: s and z channel)
+  double red[2][2][Z_WARPS];
   uint64_t full[FSTAGES], empty[FSTAGES];
-  uint64_t xfull, xempty;
+  uint64_t xfull, xempty, denfull, denempty;
   uint64_t tqfull[TQ], tqempty[TQ];
   int tq[TQ];  // tile index inside the batch, -1 = queue drained
 };
 constexpr size_t FUSED_SMEM_BYTES = sizeof(FusedSmem) + 1024;
 static_assert(FUSED_SMEM_BYTES <= 232448, "fused kernel shared memory");
 
-// L2 priority of the density pass over a tile's B / dB rows: evict_first -- nothing touches those lines
-// again before the VXC kernel of the batch, while the B^T boxes of the NEXT chunks (same rows of B, read by
-// TMA) and the P gather should stay.  GXB_L2_HINTS=0 builds without the hint.
+// L2 priorities of the two streaming passes over a tile's B / dB rows: the density pass marks them
+// evict_last (the Z pass of the same tile re-reads them a few hundred microseconds later), the Z
+// pass reads and writes evict_first (nothing touches those lines again before the VXC kernel).
 #ifndef GXB_L2_HINTS
 #define GXB_L2_HINTS 1
 #endif
@@ -83,6 +82,11 @@ __device__ __forceinline__ void ldg_stream(double (&v)[4], const double* p, uint
   if (GXB_KNOCKOUT & 1) { v[0] = v[1] = v[2] = v[3] = 1.; return; }
   if (GXB_L2_HINTS) ldg256_stream_hint(v, p, pol);
   else ldg256_stream(v, p);
+}
+__device__ __forceinline__ void stg_stream(double* p, const double (&v)[4], uint64_t pol) {
+  if (GXB_KNOCKOUT & 1) { if (v[0] == 1.2345e-300) stg256(p, v); return; }
+  if (GXB_L2_HINTS) stg256_hint(p, v, pol);
+  else stg256(p, v);
 }
 __device__ __forceinline__ void lds4(double (&v)[4], const double* p) {
   const double2 a = *reinterpret_cast<const double2*>(p);
@@ -120,9 +124,10 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
 // SPIN = 0: RKS (P = P_alpha, factor 2 inside).  UKS runs the kernel twice per batch:
 // SPIN = 1 with P = Ps = P_alpha + P_beta only stores rho_s (GGA: and grad n) per point (uks_den, one array
 // of uks_stride doubles per component); SPIN = 2 with P = Pz forms rho_z (grad M_z), rho_+- = (rho_s +- rho_z)/2
-// (and the three gammas), evaluates the polarised functional and writes the factors of BOTH Z_s (rows 0-3)
-// and Z_z (rows 4-7) -- eval_uvvar_{lda,gga}_uks / eval_zmat_{lda,gga}_vxc_uks of the reference host driver
+// (and the three gammas), evaluates the polarised functional and writes BOTH Z_s and Z_z (the two matrices
+// after B / dB) -- eval_uvvar_{lda,gga}_uks / eval_zmat_{lda,gga}_vxc_uks of the reference host driver
 // (reference_local_host_work_driver.cxx:166-188, 270-328, 607-634, 715-773; X factor 1.0, driver :387-396).
+// func.nkern == 0: density only (integrate_den): no functional, no Z pass.
 template <bool GGA, int SPIN>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
@@ -154,9 +159,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     }
     mbar_init(&S.xfull, MMA_THREADS);
     mbar_init(&S.xempty, DEN_THREADS);
+    mbar_init(&S.denfull, DEN_THREADS);
+    mbar_init(&S.denempty, Z_THREADS);
     for (int i = 0; i < TQ; ++i) {
       mbar_init(&S.tqfull[i], 1);
-      mbar_init(&S.tqempty[i], MMA_THREADS + DEN_THREADS + PROD_THREADS - 32);
+      mbar_init(&S.tqempty[i], MMA_THREADS + DEN_THREADS + Z_THREADS + PROD_THREADS - 32);
     }
     mbar_fence_init();
   }
@@ -299,15 +306,14 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       }
     }
   } else if (warp < MMA_WARPS + DEN_WARPS) {
-    // ------------------------------------------------------------------ density (+ functional) warps
+    // ------------------------------------------------------------------ density warps
     reg_inc<DEN_REGS>();
-    const int p = tid - MMA_THREADS;       // point owned by the functional threads (p < TP)
-    const int dw = warp - MMA_WARPS;       // rows with (row & 7) == dw
+    const int p = tid - MMA_THREADS;       // point owned in the cross-warp reduction
+    const int dw = warp - MMA_WARPS;       // rows with (row & 3) == dw
     const int p4 = lane * 4;               // 4 consecutive points
-    const int cofs = p4 ^ ((dw & 3) << 2); // their (swizzled) column in every row of this warp
-    constexpr int NMAT = GGA ? 4 : 1;
-    uint32_t xph = 0;
-    const uint64_t pol_drop = l2_policy_evict_first();
+    const int cofs = p4 ^ (dw << 2);       // their (swizzled) column in every row of this warp
+    uint32_t xph = 0, dph = 0;
+    const uint64_t pol_keep = l2_policy_evict_last();
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
@@ -324,18 +330,18 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         const int ncols = lane_on ? min(FN, nbe - n0) : 0;
         mbar_wait(&S.xfull, xph);
         int n = dw;
-        for (; n + 8 < ncols; n += 16) {
+        for (; n + 4 < ncols; n += 8) {
           double x[2][4], b0[2][4], b1[2][4], b2[2][4], b3[2][4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const double* src = Bt + (size_t)(n0 + n + 8 * u) * TP;
-            ldg_stream(b0[u], src, pol_drop);
+            const double* src = Bt + (size_t)(n0 + n + 4 * u) * TP;
+            ldg_stream(b0[u], src, pol_keep);
             if (GGA) {
-              ldg_stream(b1[u], src + ms, pol_drop);
-              ldg_stream(b2[u], src + 2 * ms, pol_drop);
-              ldg_stream(b3[u], src + 3 * ms, pol_drop);
+              ldg_stream(b1[u], src + ms, pol_keep);
+              ldg_stream(b2[u], src + 2 * ms, pol_keep);
+              ldg_stream(b3[u], src + 3 * ms, pol_keep);
             }
-            lds4(x[u], &S.X[n + 8 * u][p4]);
+            lds4(x[u], &S.X[n + 4 * u][p4]);
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u)
@@ -352,11 +358,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         if (n < ncols) {
           double x[4], b0[4], b1[4], b2[4], b3[4];
           const double* src = Bt + (size_t)(n0 + n) * TP;
-          ldg_stream(b0, src, pol_drop);
+          ldg_stream(b0, src, pol_keep);
           if (GGA) {
-            ldg_stream(b1, src + ms, pol_drop);
-            ldg_stream(b2, src + 2 * ms, pol_drop);
-            ldg_stream(b3, src + 3 * ms, pol_drop);
+            ldg_stream(b1, src + ms, pol_keep);
+            ldg_stream(b2, src + 2 * ms, pol_keep);
+            ldg_stream(b3, src + 3 * ms, pol_keep);
           }
           lds4(x, &S.X[n][p4]);
 #pragma unroll
@@ -380,25 +386,45 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         sts4(&S.dpart[dw][3][p4], r3);
       }
       named_bar_sync(2, DEN_THREADS);
+      mbar_wait(&S.denempty, dph ^ 1);
       // X carries the RKS factor 2 (eval_xmat fac = 2), the gradient another 2; the LDA path sums
-      // the lower triangle of the quadratic form only (another 2).  UKS: X factor 1.0
-      double den[4] = {0., 0., 0., 0.};
-      if (dw < FUNC_WARPS) {
+      // the lower triangle of the quadratic form only (another 2)
 #pragma unroll
-        for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
-          const double v = ((S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p])) +
-                           ((S.dpart[4][qn][p] + S.dpart[5][qn][p]) + (S.dpart[6][qn][p] + S.dpart[7][qn][p]));
-          // RKS: X carries 2, the gradient another 2, the LDA triangle another 2; UKS: X factor 1.0
-          const double f = SPIN != 0 ? (GGA ? (qn == 0 ? 1. : 2.) : 2.) : ((qn == 0 && GGA) ? 2. : 4.);
-          den[qn] = f * v;
-        }
+      for (int qn = 0; qn < (GGA ? 4 : 1); ++qn) {
+        const double v = (S.dpart[0][qn][p] + S.dpart[1][qn][p]) + (S.dpart[2][qn][p] + S.dpart[3][qn][p]);
+        // RKS: X carries 2, the gradient another 2, the LDA triangle another 2; UKS: X factor 1.0
+        S.den[qn][p] = (SPIN != 0 ? (GGA ? (qn == 0 ? 1. : 2.) : 2.) : ((qn == 0 && GGA) ? 2. : 4.)) * v;
       }
+      mbar_arrive(&S.denfull);
+      dph ^= 1;
       named_bar_sync(2, DEN_THREADS);  // dpart may be overwritten by the next tile
-      if (dw >= FUNC_WARPS) continue;
+    }
+  } else if (warp < MMA_WARPS + DEN_WARPS + Z_WARPS) {
+    // ------------------------------------------------------------------ functional + Z warps
+    const int p = tid - MMA_THREADS - DEN_THREADS;
+    const int zw = p >> 5;
+    const int p4 = lane * 4;
+    const int cofs = p4 ^ (zw << 2);
+    uint32_t dph = 0;
+    const uint64_t pol_drop = l2_policy_evict_first();
+    for (int it = 0;; ++it) {
+      const int tile_idx = next_tile(it);
+      if (tile_idx < 0) break;
+      const DevTile tile = tiles[tile_idx];
+      const int nbe = tile.nbe;
+      const int nbp = pad16(nbe);
+      const size_t ms = (size_t)nbp * TP;
+      const double* __restrict__ Bt = ws + tile.ws_off + cofs;
+      double* __restrict__ Z = ws + tile.ws_off + (GGA ? 4 : 1) * ms + cofs;
+      double* __restrict__ Zz = Z + ms;  // UKS: Z_z follows Z_s
 
-      // ---- functional, weights, EXC / N_EL partials, Z factors: thread = point ----------------------
-      const double rho = den[0];
-      const double dx = den[1], dy = den[2], dz = den[3];
+      mbar_wait(&S.denfull, dph);
+      const double rho = S.den[0][p];
+      double dx = 0., dy = 0., dz = 0.;
+      if (GGA) { dx = S.den[1][p]; dy = S.den[2][p]; dz = S.den[3][p]; }
+      mbar_arrive(&S.denempty);
+      dph ^= 1;
+
       const bool ok = p < tile.npts;
       if (SPIN == 1) {  // UKS pass over Ps: keep rho_s (grad n) for the pass over Pz, nothing else to do
         if (ok) {
@@ -459,29 +485,115 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         e_loc = eps * rho;                  // :490-497
         n_loc = w * rho;
       }
-      // Z = a B + fx dBx + fy dBy + fz dBz (eval_zmat_{lda,gga}_vxc_rks, host driver :586-604, 678-713) is
-      // formed by the VXC kernel from these rows; points beyond the tile carry zeros
-      {
-        double* __restrict__ frow = ws + tile.ws_off + (size_t)NMAT * ms + p;
-        frow[0] = a;
-        if (GGA) { frow[TP] = fx; frow[2 * TP] = fy; frow[3 * TP] = fz; }
-        if (SPIN == 2 && !GGA) frow[4 * TP] = fx;  // z channel: Z_z = fx B
-        if (SPIN == 2 && GGA) { frow[4 * TP] = az; frow[5 * TP] = gx; frow[6 * TP] = gy; frow[7 * TP] = gz; }
-      }
+      double(*fac)[TP] = S.fac[it & 1];
+      fac[0][p] = a;
+      if (GGA || SPIN == 2) fac[1][p] = fx;
+      if (GGA) { fac[2][p] = fy; fac[3][p] = fz; }
+      if (GGA && SPIN == 2) { fac[4][p] = az; fac[5][p] = gx; fac[6][p] = gy; fac[7][p] = gz; }
       // fixed-order tile partials of EXC / N_EL
       {
-        double e = e_loc, nn2 = n_loc;
+        double e = e_loc, nn = n_loc;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
           e += __shfl_xor_sync(0xffffffffu, e, d);
-          nn2 += __shfl_xor_sync(0xffffffffu, nn2, d);
+          nn += __shfl_xor_sync(0xffffffffu, nn, d);
         }
         double* red = &S.red[it & 1][0][0];
-        if (lane == 0) { red[dw] = e; red[FUNC_WARPS + dw] = nn2; }
-        named_bar_sync(1, FUNC_THREADS);
+        if (lane == 0) { red[zw] = e; red[Z_WARPS + zw] = nn; }
+        named_bar_sync(1, Z_THREADS);
         if (p == 0) {
           exc_part[part_off + tile_idx] = (red[0] + red[1]) + (red[2] + red[3]);
           nel_part[part_off + tile_idx] = (red[4] + red[5]) + (red[6] + red[7]);
+        }
+      }
+      if (func.nkern == 0) continue;  // integrate_den: nothing reads a Z
+      // Z rows (pad rows are never read as valid output rows); warp zw owns rows = zw (mod 4),
+      // last rows first: they were streamed most recently by the density warps
+      double a4[4], fx4[4], fy4[4], fz4[4];
+      lds4(a4, &fac[0][p4]);
+      if (GGA || SPIN == 2) lds4(fx4, &fac[1][p4]);
+      if (GGA) { lds4(fy4, &fac[2][p4]); lds4(fz4, &fac[3][p4]); }
+      double az4[4], gx4[4], gy4[4], gz4[4];
+      if (GGA && SPIN == 2) {
+        lds4(az4, &fac[4][p4]); lds4(gx4, &fac[5][p4]); lds4(gy4, &fac[6][p4]); lds4(gz4, &fac[7][p4]);
+      }
+      int mu = ((nbe - 1 - zw) & ~3) + zw;  // largest row <= nbe-1 with (row & 3) == zw
+      if (p4 >= tile_width(tile.npts)) mu = -1;  // columns beyond the tile width do not exist
+      for (; mu - 4 >= 0; mu -= 8) {
+        double b0[2][4], b1[2][4], b2[2][4], b3[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const double* src = Bt + (size_t)(mu - 4 * u) * TP;
+          ldg_stream(b0[u], src, pol_drop);
+          if (GGA) {
+            ldg_stream(b1[u], src + ms, pol_drop);
+            ldg_stream(b2[u], src + 2 * ms, pol_drop);
+            ldg_stream(b3[u], src + 3 * ms, pol_drop);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          double z[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            z[j] = a4[j] * b0[u][j];
+            if (GGA) {
+              z[j] = fma(fx4[j], b1[u][j], z[j]);
+              z[j] = fma(fy4[j], b2[u][j], z[j]);
+              z[j] = fma(fz4[j], b3[u][j], z[j]);
+            }
+          }
+          stg_stream(Z + (size_t)(mu - 4 * u) * TP, z, pol_drop);
+          if (SPIN == 2) {  // Z_z from the same rows of B (dB)
+            double zz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (GGA) {
+                zz[j] = az4[j] * b0[u][j];
+                zz[j] = fma(gx4[j], b1[u][j], zz[j]);
+                zz[j] = fma(gy4[j], b2[u][j], zz[j]);
+                zz[j] = fma(gz4[j], b3[u][j], zz[j]);
+              } else {
+                zz[j] = fx4[j] * b0[u][j];
+              }
+            }
+            stg_stream(Zz + (size_t)(mu - 4 * u) * TP, zz, pol_drop);
+          }
+        }
+      }
+      if (mu >= 0) {
+        double b0[4], b1[4], b2[4], b3[4], z[4];
+        const double* src = Bt + (size_t)mu * TP;
+        ldg_stream(b0, src, pol_drop);
+        if (GGA) {
+          ldg_stream(b1, src + ms, pol_drop);
+          ldg_stream(b2, src + 2 * ms, pol_drop);
+          ldg_stream(b3, src + 3 * ms, pol_drop);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          z[j] = a4[j] * b0[j];
+          if (GGA) {
+            z[j] = fma(fx4[j], b1[j], z[j]);
+            z[j] = fma(fy4[j], b2[j], z[j]);
+            z[j] = fma(fz4[j], b3[j], z[j]);
+          }
+        }
+        stg_stream(Z + (size_t)mu * TP, z, pol_drop);
+        if (SPIN == 2) {
+          double zz[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (GGA) {
+              zz[j] = az4[j] * b0[j];
+              zz[j] = fma(gx4[j], b1[j], zz[j]);
+              zz[j] = fma(gy4[j], b2[j], zz[j]);
+              zz[j] = fma(gz4[j], b3[j], zz[j]);
+            } else {
+              zz[j] = fx4[j] * b0[j];
+            }
+          }
+          stg_stream(Zz + (size_t)mu * TP, zz, pol_drop);
         }
       }
     }
@@ -490,7 +602,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     // warp pw gathers rows 4pw..4pw+3 of every 16-row stage of P; warp 0 also owns the tile queue
     // and the TMA loads of B^T
     reg_dec<PROD_REGS>();
-    const int pw = warp - (MMA_WARPS + DEN_WARPS);
+    const int pw = warp - (MMA_WARPS + DEN_WARPS + Z_WARPS);
     int s = 0;
     uint32_t ph = 0;
     if (pw == 0 && lane < 4) tma_prefetch_desc(&tmaps.m[lane]);

@@ -16,23 +16,23 @@ void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, do
                         bool gradient, cudaStream_t s);
 
 // K_F  fused persistent kernel: X = B P_sub (DMMA) -> rho / grad rho -> functional, weights,
-//      EXC / N_EL tile partials -> the per-point factors of Z in the tile's factor rows.  tmapA: boxes of
-//      16 rows x W points over the workspace; the ncta persistent CTAs pull tile indices [0, ntiles) from
-//      *counter (zeroed by the caller).  func.nkern == 0: density only (integrate_den).  spin 1 / 2: the two
-//      UKS passes (Ps then Pz), uks_den: 1 (LDA) or 4 (GGA) arrays of uks_stride doubles carried between them.
+//      EXC / N_EL tile partials -> Z.  tmapA: boxes of 16 rows x W points over the workspace;
+//      the ncta persistent CTAs pull tile indices [0, ntiles) from *counter (zeroed by the caller).
+//      func.nkern == 0: density only (integrate_den).  spin 1 / 2: the two UKS passes (Ps then Pz),
+//      uks_den: 1 (LDA) or 4 (GGA) arrays of uks_stride doubles carried between them.
 cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                          int* counter, int ncta, double* ws, const double* P, int ldp,
                          FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
                          cudaStream_t s, int spin = 0, double* uks_den = nullptr, size_t uks_stride = 0);
 
-// K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe with Z = a B (+ fx dBx + fy dBy + fz dBz for gga)
-//      formed on the fly from the tile's factor rows fac_row .. fac_row+3 (RKS / UKS s channel: 0, UKS z
-//      channel: 4), scatter-added (lower triangle) into VXC.  tmapV: box of 128 rows x 16 points over the
-//      workspace `ws`; sym: M = B^T Z symmetric (LDA).  ncta persistent CTAs pull items [0, nitems) from
+// K_D  VXC_sub += B^T Z (+ transpose) on the DMMA pipe, scatter-added (lower triangle) into VXC.
+//      tmapA / tmapZ: boxes of 128 / 64 rows x 16 points over the workspace; Z is matrix `zmat` of the `nmat`
+//      matrices of a tile (RKS: LDA 1 of 2, GGA 4 of 5; UKS: Z_s / Z_z = 1 / 2 of 3 (LDA), 4 / 5 of 6 (GGA));
+//      sym: M = B^T Z symmetric (LDA).  Two persistent CTAs per SM (nsm SMs) pull items [0, nitems) from
 //      *counter (zeroed by the caller).
-cudaError_t launch_vxc(const CUtensorMap& tmapV, const PlanView& pv, const VxcItem* items, int nitems,
-                       int* counter, int ncta, const double* ws, bool gga, int fac_row, bool sym, double* VXC,
-                       int ldv, cudaStream_t s);
+cudaError_t launch_vxc(const CUtensorMap& tmapA, const CUtensorMap& tmapZ, const PlanView& pv, const VxcItem* items,
+                       int nitems, int* counter, int nsm, int zmat, int nmat, bool sym, double* VXC, int ldv,
+                       cudaStream_t s);
 
 // finalisation
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

@@ -634,7 +634,7 @@ struct XCIntegrator::Impl {
   DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2, d_pack;
   DevBuf<double> dPz, dPtri_z, dVXCz, d_uks_den;  // UKS: z density / potential, densities per point
   gxb::TmapSet tmapA{};  // TMA views of d_ws: 16 rows x (32..128) points
-  CUtensorMap tmapV{};   // 128 rows x 16 points
+  CUtensorMap tmapV{}, tmapZ{};  // 128 / 64 rows x 16 points
   int ncta = 0;
   std::shared_ptr<DevicePlan> plan;
   std::shared_ptr<Schedule> sched;
@@ -651,7 +651,7 @@ struct XCIntegrator::Impl {
     if (h_out2) cudaFreeHost(h_out2);
   }
 
-  // plan + schedule + workspace + TMA views for tiles of `nmat` matrices (1: B; 4: B, dBx, dBy, dBz)
+  // plan + schedule + workspace + TMA views for tiles of `nmat` matrices (B [, dBx, dBy, dBz], Z [, Z_z])
   void prepare(LoadBalancer& lb, int nmat, bool sym);
   // P (nbf x nbf, ld = nbf) and VXC buffers of the host-buffer entry points; P is padded so that an
   // all-gather of per-rank column slabs fits
@@ -703,6 +703,7 @@ void XCIntegrator::Impl::prepare(LoadBalancer& lb, int nmat, bool sym) {
     CUDA_CHECK(cudaMemsetAsync(d_ws.p, 0, sched->ws_doubles * sizeof(double), stream));
     for (int w = 0; w < 4; ++w) tmapA.m[w] = make_ws_tensor_map(d_ws.p, sched->ws_doubles, 32 * (w + 1), 16);
     tmapV = make_ws_tensor_map(d_ws.p, sched->ws_doubles, 16, gxb::VXC_BLK);
+    tmapZ = make_ws_tensor_map(d_ws.p, sched->ws_doubles, 16, gxb::VXC_BLN);
   }
   d_exc_part.alloc(std::max<size_t>(1, sched->tiles.size()));
   d_nel_part.alloc(std::max<size_t>(1, sched->tiles.size()));
@@ -789,7 +790,7 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
   if (!lb_->state().modified_weights_are_stored)
     GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
   const bool gga = func_->is_gga();
-  const int nmat = gga ? 4 : 1;
+  const int nmat = gga ? 5 : 2;
   I.prepare(*lb_, nmat, !gga);
   auto& plan = *I.plan;
   cudaStream_t s = I.stream;
@@ -844,8 +845,8 @@ void XCIntegrator::eval_exc_vxc_device(const double* dP, double* dVXC, double* d
     if (ev) CUDA_CHECK(cudaEventRecord(ev[3], s));
     launches += 2;
     if (do_vxc) {
-      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                                 sc.d_counters.p + sc.batches.size() + ib, sc.ncta, I.d_ws.p, gga, 0, !gga,
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, I.tmapZ, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + sc.batches.size() + ib, sc.ncta, gga ? 4 : 1, nmat, !gga,
                                  dVXC, nbf, s));
       ++launches;
     }
@@ -989,7 +990,7 @@ void XCIntegrator::integrate_den(int64_t m, int64_t n, const double* P, int64_t 
   upload_density_(P, ldp, I.dP.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
-  I.prepare(*lb_, 1, true);
+  I.prepare(*lb_, 2, true);
   auto& plan = *I.plan;
   auto& sc = *I.sched;
   const gxb::PlanView pv = plan.view();
@@ -1055,7 +1056,8 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
   upload_density_(Pz, ldpz, I.dPz.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
-  I.prepare(*lb_, gga ? 4 : 1, !gga);
+  const int nmat = gga ? 6 : 3;  // B [, dBx, dBy, dBz], Z_s, Z_z
+  I.prepare(*lb_, nmat, !gga);
   auto& plan = *I.plan;
   const size_t nden = gga ? 4 : 1;  // rho_s (+ grad n) carried from the pass over Ps to the pass over Pz
   if (I.d_uks_den.n < nden * plan.npts) I.d_uks_den.alloc(std::max<size_t>(1, nden * plan.npts));
@@ -1092,11 +1094,11 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
                                  plan.npts));
     launches += 3;
     if (do_vxc) {
-      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                                 sc.d_counters.p + 2 * nb + ib, sc.ncta, I.d_ws.p, gga, 0, !gga, I.dVXC.p, inbf,
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, I.tmapZ, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + 2 * nb + ib, sc.ncta, gga ? 4 : 1, nmat, !gga, I.dVXC.p, inbf,
                                  s));
-      CUDA_CHECK(gxb::launch_vxc(I.tmapV, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
-                                 sc.d_counters.p + 3 * nb + ib, sc.ncta, I.d_ws.p, gga, 4, !gga, I.dVXCz.p,
+      CUDA_CHECK(gxb::launch_vxc(I.tmapV, I.tmapZ, pv, sc.d_items.p + b.item_begin, b.item_end - b.item_begin,
+                                 sc.d_counters.p + 3 * nb + ib, sc.ncta, gga ? 5 : 2, nmat, !gga, I.dVXCz.p,
                                  inbf, s));
       launches += 2;
     }
