@@ -128,7 +128,9 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
 // after B / dB) -- eval_uvvar_{lda,gga}_uks / eval_zmat_{lda,gga}_vxc_uks of the reference host driver
 // (reference_local_host_work_driver.cxx:166-188, 270-328, 607-634, 715-773; X factor 1.0, driver :387-396).
 // func.nkern == 0: density only (integrate_den): no functional, no Z pass.
-template <bool GGA, int SPIN>
+// DUAL: the functional contains kernels evaluated with dual numbers (B88, LYP; every polarised GGA) -- kept out
+// of the instantiations that do not need them (xc_functionals.cuh)
+template <bool GGA, int SPIN, bool DUAL>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
                            const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
@@ -439,7 +441,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       }
       double a = 0., fx = 0., fy = 0., fz = 0., e_loc = 0., n_loc = 0.;
       double az = 0., gx = 0., gy = 0., gz = 0.;  // UKS GGA: factors of Z_z
-      if (ok && SPIN == 2 && GGA) {
+      if (ok && SPIN == 2 && GGA && DUAL) {
         // eval_uvvar_gga_uks :270-328, weights :453-466, eval_zmat_gga_vxc_uks :715-773
         const double w = pv.w[tile.pt_off + p];
         const size_t ip = tile.pt_off + p;
@@ -474,7 +476,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       } else if (ok) {
         const double w = pv.w[tile.pt_off + p];
         const double sigma = GGA ? dx * dx + dy * dy + dz * dz : 0.;
-        const XcOut xc = eval_functional(func, rho, sigma);
+        const XcOut xc = eval_functional_t<DUAL>(func, rho, sigma);
         const double eps = xc.eps * w;      // host driver :453-466
         const double vrho = xc.vrho * w;
         a = 0.5 * vrho;
@@ -692,12 +694,13 @@ cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile
                                                        exc_part, nel_part, part_off, uks_den, uks_stride);
     return cudaGetLastError();
   };
-  if (spin == 1 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 1>);
-  if (spin == 2 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 2>);
-  if (spin == 1) return launch(fused_xmat_den_zmat_kernel<false, 1>);
-  if (spin == 2) return launch(fused_xmat_den_zmat_kernel<false, 2>);
-  if (func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 0>);
-  return launch(fused_xmat_den_zmat_kernel<false, 0>);
+  if (spin == 1 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 1, false>);
+  if (spin == 2 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 2, true>);
+  if (spin == 1) return launch(fused_xmat_den_zmat_kernel<false, 1, false>);
+  if (spin == 2) return launch(fused_xmat_den_zmat_kernel<false, 2, false>);
+  if (func.is_gga && functional_needs_dual(func)) return launch(fused_xmat_den_zmat_kernel<true, 0, true>);
+  if (func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 0, false>);
+  return launch(fused_xmat_den_zmat_kernel<false, 0, false>);
 }
 
 }  // namespace gxb

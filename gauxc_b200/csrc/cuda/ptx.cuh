@@ -85,6 +85,11 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// 2-D tile prefetch global -> L2 (no shared memory, no completion): hides the HBM latency of a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tmap), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }

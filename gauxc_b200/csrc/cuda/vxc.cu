@@ -11,8 +11,7 @@
 // run of that task's tiles (K = points).  Both operands arrive as TMA boxes (128 resp. 64 basis rows x
 // 16 points) straight from the swizzled workspace (dense + conflict-free, device_plan.hpp) through
 // a 4-stage mbarrier ring fed by one producer thread; 8 MMA warps (4 x 2, warp tile 32 x 32).
-// The kernel is PERSISTENT and runs TWO CTAs PER SM (288 threads, 97 KB of shared memory, 112
-// registers each): every CTA pulls items from a device-side queue (atomic counter, task order -> the
+// The kernel is PERSISTENT and runs TWO CTAs PER SM (384 threads, 97 KB of shared memory each): every CTA pulls items from a device-side queue (atomic counter, task order -> the
 // VXC region being scattered into stays in L2), its producer runs ahead into the next item's loads, and
 // while the MMA warps of one CTA scatter a finished block with FP64 reductions (RED.ADD.F64: nbe^2 of
 // them per task and tile run, as expensive as the K loop itself for the ~100-point tasks that dominate
@@ -28,6 +27,8 @@
 // 286 -> 436 ms.  The step is bound by feeding the DMMA pipe, not by HBM; Z stays materialised.
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace gxb {
 
@@ -36,11 +37,18 @@ namespace {
 constexpr int VK = 16;  // points (K) per stage
 constexpr int VSTAGES = 4;
 constexpr int VQ = 4;   // item-queue ring slots
+#ifndef GXB_VPF
+#define GXB_VPF 0
+#endif
+constexpr int VPF = GXB_VPF;  // stages prefetched into L2 ahead of the ring (0: none)
 constexpr int V_MMA_WARPS = 8;
 constexpr int V_MMA_THREADS = V_MMA_WARPS * 32;
-// warps 0-7 MMA, warp 8 producer (one thread).  288 threads x 112 registers x 2 CTAs fill the SM's
-// register file exactly; no setmaxnreg needed.
-constexpr int V_THREADS = V_MMA_THREADS + 32;
+// warps 0-7 MMA, warp 8 producer (one thread), 9-11 idle (complete the producer's warpgroup: registers are
+// allocated in units of four warps, and setmaxnreg is a warpgroup instruction).  Launch allocation 12 warps
+// x 80; after re-partitioning 8 x 104 + 4 x 32 -- twice per SM.
+constexpr int V_THREADS = V_MMA_THREADS + 128;
+constexpr int V_MMA_REGS = 104, V_PROD_REGS = 32;
+static_assert(8 * V_MMA_REGS + 4 * V_PROD_REGS <= 12 * 80, "register pool of one CTA");
 
 struct VxcSlot {
   int nbe, ao_off, m0, n0, nks, diag, pad0, pad1;  // nks < 0: queue drained
@@ -78,8 +86,7 @@ __device__ __forceinline__ void vxc_step(double (&acc)[4][4][2], const double* _
   }
 }
 
-// 112 registers: 2 CTAs x 9 warps x 32 x 112 = 64 512 of the 65 536 registers of an SM
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(V_THREADS, 2)
 vxc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapZ, PlanView pv,
            const VxcItem* __restrict__ items, int nitems, int* __restrict__ counter, int zmat, int nmat,
            int sym, double* __restrict__ VXC, int ldv) {
@@ -106,7 +113,8 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
 
   if (warp >= V_MMA_WARPS) {
     // ---------------------------------------------------------------- producer (one thread)
-    if (lane != 0) return;
+    reg_dec<V_PROD_REGS>();
+    if (warp != V_MMA_WARPS || lane != 0) return;
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapZ);
     int s = 0;
@@ -158,17 +166,24 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
       S.q[slot] = sl;
       mbar_arrive(&S.qfull[slot]);
       const int stride = nmat * nbp;  // workspace rows of one tile
-      for (int q = 0; q < item.ntiles; ++q) {
-        const int rowB = item.row0 + q * stride;
-        const int rowZ = rowB + zmat * nbp;
-        const int nks = (q + 1 < item.ntiles) ? TP / VK : item.nks_last;
-        for (int ks = 0; ks < nks; ++ks) {
-          mbar_wait(&S.empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&S.full[s], (VXC_BLK + VXC_BLN) * VK * sizeof(double));
-          tma_load_2d(&S.A[s][0][0], &tmapA, &S.full[s], ks * VK, rowB + m0);
-          tma_load_2d(&S.Z[s][0][0], &tmapZ, &S.full[s], ks * VK, rowZ + n0);
-          if (++s == VSTAGES) { s = 0; ph ^= 1; }
-        }
+      // The boxes of stage j + VPF are prefetched into L2 (TMA prefetch: no shared memory, no completion)
+      // when stage j is issued: the ring holds only 4 stages per CTA, HBM latency under load is several of
+      // them, and the ring cannot grow (two CTAs share the SM's shared memory).
+      const int nst = (item.ntiles - 1) * (TP / VK) + item.nks_last;
+      auto prefetch = [&](int j) {
+        const int rowB = item.row0 + (j >> 3) * stride, ks = j & 7;
+        tma_prefetch_2d(&tmapA, ks * VK, rowB + m0);
+        tma_prefetch_2d(&tmapZ, ks * VK, rowB + zmat * nbp + n0);
+      };
+      for (int j = 0; j < VPF && j < nst; ++j) prefetch(j);
+      for (int j = 0; j < nst; ++j) {
+        const int rowB = item.row0 + (j >> 3) * stride, ks = j & 7;
+        if (j + VPF < nst) prefetch(j + VPF);
+        mbar_wait(&S.empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&S.full[s], (VXC_BLK + VXC_BLN) * VK * sizeof(double));
+        tma_load_2d(&S.A[s][0][0], &tmapA, &S.full[s], ks * VK, rowB + m0);
+        tma_load_2d(&S.Z[s][0][0], &tmapZ, &S.full[s], ks * VK, rowB + zmat * nbp + n0);
+        if (++s == VSTAGES) { s = 0; ph ^= 1; }
       }
       if (idx1 < 0) {  // tail of the queue: lazy pop
         idx1 = pop();
@@ -182,6 +197,7 @@ vxc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CU
   }
 
   // ------------------------------------------------------------------ MMA warps
+  reg_inc<V_MMA_REGS>();
   const int g = lane >> 2, t = lane & 3;
   // 4 x 2 warps; sub-partition = warp & 3 = (wm + wn) & 3: idle row blocks of ragged output blocks are
   // spread over the DMMA pipes
@@ -380,6 +396,19 @@ cudaError_t launch_vxc(const CUtensorMap& tmapA, const CUtensorMap& tmapZ, const
   // the attribute is per device and cheap to set: no process-wide "done" flag
   cudaError_t e = cudaFuncSetAttribute(vxc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VXC_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  // two CTAs of 97 KB each must be co-resident: ask for the largest shared-memory carveout (the default
+  // heuristic sizes the carveout for ONE block)
+  e = cudaFuncSetAttribute(vxc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  if (std::getenv("GAUXC_B200_DEBUG")) {
+    static bool said = false;
+    if (!said) {
+      int nb = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vxc_kernel, V_THREADS, VXC_SMEM_BYTES);
+      std::fprintf(stderr, "[gauxc_b200] vxc_kernel: %d resident CTAs per SM (%zu B shared each)\n", nb, VXC_SMEM_BYTES);
+      said = true;
+    }
+  }
   int ncta = 2 * nsm;  // two co-resident CTAs per SM
   ncta = ncta < nitems ? ncta : nitems;
   vxc_kernel<<<ncta, V_THREADS, VXC_SMEM_BYTES, s>>>(tmapA, tmapZ, pv, items, nitems, counter, zmat, nmat,

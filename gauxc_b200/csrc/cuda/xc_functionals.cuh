@@ -150,18 +150,22 @@ GXB_HD XcOut pbe_c(double rho, double sigma) {
   return o;
 }
 
+// out of line on the device: the dual-number code is large, and inlined into the persistent kernel it costs
+// the MMA loops instruction-cache hits (taxol fused 123 -> 130 ms); it runs once per grid point
+// B88 exchange / LYP correlation at zeta = 0 go through the spin-resolved dual-number kernels
+// (xc_functionals_pol_gga.cuh).  That code is large: a persistent kernel that carries it loses
+// instruction-cache hits in its MMA loops (taxol PBE fused: 123 -> 130 ms inlined, 145 ms as an out-of-line
+// call), so the kernels are instantiated twice (DUAL = false: closed forms only) and dispatched on the
+// functional's kernel list.
 #ifndef GXB_VIA_POL_INLINE
 #define GXB_VIA_POL_INLINE __forceinline__
 #endif
-// B88 exchange / LYP correlation at zeta = 0 through the spin-resolved dual-number kernels
-// (xc_functionals_pol_gga.cuh); out of line: evaluated once per grid point, must not weigh on the
-// register allocation of the streaming loops around it
 #ifdef __CUDACC__
 __host__ __device__ GXB_VIA_POL_INLINE
 #endif
 XcOut eval_kernel_via_pol(int id, double rho, double sigma);
 
-GXB_HD XcOut eval_kernel(int id, double rho, double sigma) {
+GXB_HD XcOut eval_kernel_closed(int id, double rho, double sigma) {
   switch (id) {
     case K_SLATER_X: return slater_x(rho);
     case K_VWN5_C: return vwn5_c(rho);
@@ -169,21 +173,32 @@ GXB_HD XcOut eval_kernel(int id, double rho, double sigma) {
     case K_PBE_X: return pbe_x(rho, sigma, 0.8040, 0.2195149727645171);
     case K_REVPBE_X: return pbe_x(rho, sigma, 1.245, 0.2195149727645171);  // libxc gga_x_pbe_r
     case K_PBE_C: return pbe_c(rho, sigma);
-    case K_B88_X:
-    case K_LYP_C: return eval_kernel_via_pol(id, rho, sigma);
     default: return XcOut{0., 0., 0.};
   }
 }
 
-GXB_HD XcOut eval_functional(const FunctionalDesc& f, double rho, double sigma) {
+GXB_HD bool kernel_needs_dual(int id) { return id == K_B88_X || id == K_LYP_C; }
+inline bool functional_needs_dual(const FunctionalDesc& f) {
+  for (int k = 0; k < f.nkern; ++k)
+    if (kernel_needs_dual(f.kern[k])) return true;
+  return false;
+}
+
+template <bool DUAL>
+GXB_HD XcOut eval_functional_t(const FunctionalDesc& f, double rho, double sigma) {
   XcOut t{0., 0., 0.};
   for (int k = 0; k < f.nkern; ++k) {
-    const XcOut o = eval_kernel(f.kern[k], rho, sigma);
+    XcOut o;
+    if (DUAL && kernel_needs_dual(f.kern[k])) o = eval_kernel_via_pol(f.kern[k], rho, sigma);
+    else o = eval_kernel_closed(f.kern[k], rho, sigma);
     t.eps += f.coeff[k] * o.eps;
     t.vrho += f.coeff[k] * o.vrho;
     t.vsigma += f.coeff[k] * o.vsigma;
   }
   return t;
+}
+GXB_HD XcOut eval_functional(const FunctionalDesc& f, double rho, double sigma) {
+  return eval_functional_t<true>(f, rho, sigma);
 }
 
 // ---- spin-polarised LDA (UKS) -----------------------------------------------------------------

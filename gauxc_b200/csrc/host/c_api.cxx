@@ -649,6 +649,14 @@ void gauxc_b200_load_balancer_task_info(GauXCStatus* status, const GauXCLoadBala
   }
   C_CATCH(status)
 }
+void gauxc_b200_load_balancer_state(GauXCStatus* status, const GauXCLoadBalancer lb, int* modified_weights_are_stored,
+                                    int* weight_alg) {
+  C_TRY(status)
+  const auto& st = (*LB(lb))->state();
+  *modified_weights_are_stored = st.modified_weights_are_stored ? 1 : 0;
+  *weight_alg = (int)st.weight_alg;
+  C_CATCH(status)
+}
 void gauxc_b200_load_balancer_get_task(GauXCStatus* status, const GauXCLoadBalancer lb, int64_t it,
                                        double* points, double* weights, int32_t* shell_list) {
   C_TRY(status)

@@ -330,6 +330,9 @@ int64_t gauxc_b200_load_balancer_total_npts(GauXCStatus* status, const GauXCLoad
 /* per task: iParent, npts, nbe, nshells, dist_nearest (arrays of length ntasks) */
 void gauxc_b200_load_balancer_task_info(GauXCStatus* status, const GauXCLoadBalancer lb, int32_t* iParent,
                                         int32_t* npts, int32_t* nbe, int32_t* nshells, double* dist_nearest);
+/* LoadBalancer::state() (include/gauxc/load_balancer.hpp:37-48): weights already partitioned? by which scheme? */
+void gauxc_b200_load_balancer_state(GauXCStatus* status, const GauXCLoadBalancer lb, int* modified_weights_are_stored,
+                                    int* weight_alg);
 /* copy one task out (points npts x 3 row-major, weights npts, shell_list nshells) */
 void gauxc_b200_load_balancer_get_task(GauXCStatus* status, const GauXCLoadBalancer lb, int64_t itask,
                                        double* points, double* weights, int32_t* shell_list);

@@ -32,12 +32,17 @@
 #pragma once
 #include "gauxc_b200.h"
 
+#include <algorithm>
 #include <array>
+#include <cctype>
+#include <cmath>
 #include <cstdint>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -272,6 +277,50 @@ public:
   }
 };
 
+// ---- tasks, molecular meta data (include/gauxc/xc_task.hpp:25-62, include/gauxc/molmeta.hpp) ------------------
+struct XCTask {
+  struct screening_data {
+    std::vector<int32_t> shell_list;
+    int32_t nbe = 0;
+  };
+  int32_t iParent = -1;
+  std::vector<std::array<double, 3>> points;
+  std::vector<double> weights;
+  int32_t npts = 0;
+  double dist_nearest = 0.;
+  screening_data bfn_screening;
+};
+
+class MolMeta {
+  size_t natoms_ = 0;
+  std::vector<double> rab_, dist_nearest_;
+
+public:
+  MolMeta() = default;
+  explicit MolMeta(const std::vector<Atom>& mol) : natoms_(mol.size()), rab_(mol.size() * mol.size(), 0.),
+                                                   dist_nearest_(mol.size(), 0.) {
+    // src/molmeta.cxx:28-58
+    for (size_t i = 0; i < natoms_; ++i) {
+      double best = std::numeric_limits<double>::infinity();
+      for (size_t j = 0; j < natoms_; ++j) {
+        const double dx = mol[i].x - mol[j].x, dy = mol[i].y - mol[j].y, dz = mol[i].z - mol[j].z;
+        const double r = std::sqrt(dx * dx + dy * dy + dz * dz);
+        rab_[i + j * natoms_] = r;
+        if (i != j) best = std::min(best, r);
+      }
+      dist_nearest_[i] = best;
+    }
+  }
+  size_t natoms() const { return natoms_; }
+  const std::vector<double>& rab() const { return rab_; }
+  const std::vector<double>& dist_nearest() const { return dist_nearest_; }
+};
+
+struct LoadBalancerState {
+  bool modified_weights_are_stored = false;
+  XCWeightAlg weight_alg = XCWeightAlg::NOTPARTITIONED;
+};
+
 // ---- load balancer -----------------------------------------------------------------------------------
 class LoadBalancer {
   std::shared_ptr<GauXCLoadBalancer> h_;
@@ -280,6 +329,7 @@ class LoadBalancer {
   std::shared_ptr<GauXCBasisSet> basis_;
   MolGrid mg_;
   RuntimeEnvironment rt_;
+  MolMeta meta_;
   friend class LoadBalancerFactory;
   LoadBalancer(const MolGrid& mg, const RuntimeEnvironment& rt) : mg_(mg), rt_(rt) {}
 
@@ -298,6 +348,47 @@ public:
   }
   const RuntimeEnvironment& runtime() const { return rt_; }
   const GauXCLoadBalancer& c_handle() const { return *h_; }
+
+  // include/gauxc/load_balancer.hpp:71-119.  The task list lives behind the C ABI (and, once the weights
+  // are modified, on the device): get_tasks() materialises a copy.
+  std::vector<XCTask> get_tasks() const {
+    const size_t nt = ntasks();
+    std::vector<int32_t> ip(nt), np(nt), nbe(nt), nsh(nt);
+    std::vector<double> dn(nt);
+    detail::StatusGuard g;
+    gauxc_b200_load_balancer_task_info(&g.st, *h_, ip.data(), np.data(), nbe.data(), nsh.data(), dn.data());
+    g.check();
+    std::vector<XCTask> tasks(nt);
+    for (size_t t = 0; t < nt; ++t) {
+      auto& x = tasks[t];
+      x.iParent = ip[t]; x.npts = np[t]; x.dist_nearest = dn[t];
+      x.points.resize(np[t]); x.weights.resize(np[t]);
+      x.bfn_screening.nbe = nbe[t]; x.bfn_screening.shell_list.resize(nsh[t]);
+      gauxc_b200_load_balancer_get_task(&g.st, *h_, (int64_t)t, x.points.empty() ? nullptr : x.points[0].data(),
+                                        x.weights.data(), x.bfn_screening.shell_list.data());
+      g.check();
+    }
+    return tasks;
+  }
+  LoadBalancerState state() const {
+    int mod = 0, alg = 0;
+    detail::StatusGuard g;
+    gauxc_b200_load_balancer_state(&g.st, *h_, &mod, &alg);
+    g.check();
+    return LoadBalancerState{mod != 0, (XCWeightAlg)alg};
+  }
+  size_t max_npts() const {
+    size_t m = 0;
+    for (auto& t : get_tasks()) m = std::max(m, (size_t)t.npts);
+    return m;
+  }
+  size_t max_nbe() const {
+    size_t m = 0;
+    for (auto& t : get_tasks()) m = std::max(m, (size_t)t.bfn_screening.nbe);
+    return m;
+  }
+  const MolGrid& molgrid() const { return mg_; }
+  const MolMeta& molmeta() const { return meta_; }
 };
 
 class LoadBalancerFactory {
@@ -313,6 +404,7 @@ public:
     auto del_status = [](GauXCStatus& st) { gauxc_status_delete(&st); };
     (void)del_status;
     std::shared_ptr<LoadBalancer> lb(new LoadBalancer(mg, rt));
+    lb->meta_ = MolMeta(mol);
     lb->mol_ = std::shared_ptr<GauXCMolecule>(new GauXCMolecule(detail::to_c(mol)), [](GauXCMolecule* p) {
       GauXCStatus st{0, nullptr};
       gauxc_molecule_delete(&st, p);
@@ -402,6 +494,42 @@ public:
   std::shared_ptr<MolecularWeights> get_shared_instance() { return std::make_shared<MolecularWeights>(get_instance()); }
 };
 
+// ---- reduction driver (include/gauxc/reduction_driver.hpp:26-70) ------------------------------------------
+enum class ReductionOp { Sum };
+// "Default" / "NCCL": in-place sum over the ranks of the job of a DEVICE buffer through the library's NCCL
+// communicator (gauxc_b200_nccl_init); a single rank reduces to a no-op.  "BasicMPI" does not exist here.
+class ReductionDriver {
+  int size_ = 1;
+
+public:
+  explicit ReductionDriver(int comm_size) : size_(comm_size) {}
+  bool takes_host_memory() const { return false; }
+  bool takes_device_memory() const { return true; }
+  int comm_size() const { return size_; }
+  // queue (the reference's std::any holding a stream) is ignored: the call returns when the sum is complete
+  template <typename T, typename... Queue>
+  void allreduce_inplace(T* data, size_t n, ReductionOp, Queue&&...) {
+    static_assert(std::is_same<T, double>::value, "FP64 buffers only");
+    detail::StatusGuard g;
+    gauxc_b200_allreduce_device(&g.st, data, n);
+    g.check();
+  }
+};
+struct ReductionDriverFactory {
+  static std::shared_ptr<ReductionDriver> get_shared_instance(const RuntimeEnvironment& rt,
+                                                              std::string kernel_name = "Default") {
+    for (auto& c : kernel_name) c = (char)std::toupper((unsigned char)c);
+    if (kernel_name == "BASICMPI")
+      throw generic_gauxc_exception("BasicMPI ReductionDriver unavailable: no MPI in this build (use NCCL)");
+    if (kernel_name != "DEFAULT" && kernel_name != "NCCL")
+      throw generic_gauxc_exception("ReductionDriver Not Recognized: " + kernel_name);
+    return std::make_shared<ReductionDriver>(rt.comm_size());
+  }
+  static ReductionDriver get_instance(const RuntimeEnvironment& rt, std::string kernel_name = "Default") {
+    return *get_shared_instance(rt, std::move(kernel_name));
+  }
+};
+
 // ---- functional ----------------------------------------------------------------------------------------
 // Stands in for ExchCXX::XCFunctional: a functional NAME of the reference's functional_map
 // (tests/standalone_driver.cxx:428-433); SVWN5, PBE, PBE0, LDA/SLATER, VWN5, SPW92 are implemented.
@@ -461,6 +589,24 @@ public:
     gauxc_integrator_eval_exc_rks(&g.st, *h_, (int64_t)P.rows(), (int64_t)P.cols(), P.data(), (int64_t)P.rows(), &EXC);
     g.check();
     return EXC;
+  }
+  // UKS EXC only
+  value_type eval_exc(const MatrixType& Ps, const MatrixType& Pz) {
+    value_type EXC = 0;
+    detail::StatusGuard g;
+    gauxc_integrator_eval_exc_uks(&g.st, *h_, (int64_t)Ps.rows(), (int64_t)Ps.cols(), Ps.data(), (int64_t)Ps.rows(),
+                                  Pz.data(), (int64_t)Pz.rows(), &EXC);
+    g.check();
+    return EXC;
+  }
+  // EXC gradient w.r.t. the nuclear coordinates, 3 * natoms (include/gauxc/xc_integrator.hpp eval_exc_grad)
+  std::vector<value_type> eval_exc_grad(const MatrixType& P, size_t natoms) {
+    std::vector<value_type> grad(3 * natoms, 0);
+    detail::StatusGuard g;
+    gauxc_integrator_eval_exc_grad_rks(&g.st, *h_, (int64_t)P.rows(), (int64_t)P.cols(), P.data(), (int64_t)P.rows(),
+                                       grad.data());
+    g.check();
+    return grad;
   }
   value_type integrate_den(const MatrixType& P) {
     value_type N_EL = 0;
