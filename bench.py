@@ -245,6 +245,9 @@ def parity_block(s, world, rank, seconds, dmma_rate_hint=None):
     out = None
     if rank == 0:
         orc.init_blas()
+        # the checker runs on rank 0 alone: give it every host core (torchrun workers default to a 1/N share)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        orc.lib().oracle_set_num_threads(int(ncores))
         t0 = time.time()
         ref = orc.exc_vxc(s.basis.flat(), s.nbf, s.P, allt, s.func_name)
         dt = time.time() - t0
@@ -349,6 +352,19 @@ def run_workload(args, workload, steps, warmup, full, rank, local_rank, world, b
                "d2h_bytes_per_step": int(nbf * nbf * 8 + 16),
                "api": "gauxc_integrator_eval_exc_vxc_rks(host P, host VXC), pinned host buffers; per rank" +
                       ("; P uploaded as 1/N column slabs + NCCL all-gather" if slab else "")}
+        if world > 1:
+            # extension: VXC copied back on rank 0 only (the replicated D2H is what bounds e2e at large nbf)
+            integ.set_vxc_root_only(True)
+            integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
+            barrier()
+            t0 = time.time()
+            for _ in range(steps):
+                integ.eval_exc_vxc_raw(nbf, nbf, Pn, nbf, Vn, nbf)
+            barrier()
+            tr = torch.tensor([(time.time() - t0) * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            e2e["root_only_ms_per_step"] = float(tr[0]) / steps
+            integ.set_vxc_root_only(False)
         del Ph, Vh
 
     # ---- parity against the oracle, through the reduction, at this N ---------------------------------

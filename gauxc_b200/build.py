@@ -91,6 +91,22 @@ def build_variant(suffix, defs):
     return out
 
 
+def build_driver():
+    """tools/standalone_driver.cxx -> gauxc_b200/standalone_driver (plain g++ over the C++ facade + C ABI)."""
+    src = os.path.join(ROOT, "tools", "standalone_driver.cxx")
+    exe = os.path.join(HERE, "standalone_driver")
+    hdrs = [os.path.join(ROOT, "include", h) for h in ("gauxc_b200.h", "gauxc_b200.hpp")]
+    newest = max(os.path.getmtime(f) for f in [src, LIB] + hdrs)
+    if os.path.exists(exe) and os.path.getmtime(exe) > newest:
+        return exe
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", HERE, "-lgauxc_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("standalone_driver build failed:\n" + r.stdout + r.stderr)
+    return exe
+
+
 def build_oracle(force=False):
     """Compile oracle/ (CPU restatement) and, when /root/reference is present, oracle/_ref."""
     odir = os.path.join(ROOT, "oracle")
@@ -103,5 +119,6 @@ def build_oracle(force=False):
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_library(force=force, verbose="-v" in sys.argv))
+    print(build_driver())
     if "--no-oracle" not in sys.argv:
         print(build_oracle(force=force))

@@ -112,6 +112,16 @@ def lib():
         "gauxc_integrator_eval_exc_grad_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
                                                       _dp]),
         "gauxc_integrator_eval_exx_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64]),
+        "gauxc_molecule_new": (_Handle, [S]),
+        "gauxc_basisset_new": (_Handle, [S]),
+        "gauxc_molecule_read_hdf5_record": (None, [S, _Handle, C.c_char_p, C.c_char_p]),
+        "gauxc_molecule_write_hdf5_record": (None, [S, _Handle, C.c_char_p, C.c_char_p]),
+        "gauxc_basisset_read_hdf5_record": (None, [S, _Handle, C.c_char_p, C.c_char_p]),
+        "gauxc_basisset_write_hdf5_record": (None, [S, _Handle, C.c_char_p, C.c_char_p]),
+        "gauxc_b200_hdf5_dataset_size": (C.c_int64, [S, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+        "gauxc_b200_hdf5_read_dataset": (None, [S, C.c_char_p, C.c_char_p, _dp, C.c_int64]),
+        "gauxc_b200_hdf5_write_dataset": (None, [S, C.c_char_p, C.c_char_p, _dp, C.POINTER(C.c_int64), C.c_int]),
+        "gauxc_b200_molecule_get_atoms": (None, [S, _Handle, C.POINTER(_Atom)]),
         "gauxc_b200_nccl_get_unique_id": (None, [S, C.c_char_p]),
         "gauxc_b200_nccl_init": (None, [S, C.c_char_p, C.c_int, C.c_int]),
         "gauxc_b200_nccl_finalize": (None, [S]),
@@ -129,6 +139,7 @@ def lib():
         "gauxc_b200_load_balancer_set_tasks": (None, [S, _Handle, C.c_int64, _ip, _ip, _dp, _dp, _dp, _ip, _ip, C.c_int]),
         "gauxc_b200_integrator_stats": (None, [S, _Handle, _dp]),
         "gauxc_b200_integrator_set_profile": (None, [S, _Handle, C.c_int]),
+        "gauxc_b200_integrator_set_vxc_root_only": (None, [S, _Handle, C.c_int]),
         "gauxc_b200_molecular_weights_last_ms": (C.c_double, [S, _Handle]),
         "gauxc_b200_lebedev": (C.c_int64, [S, C.c_int, _dp, _dp]),
         "gauxc_b200_radial": (None, [S, C.c_int, C.c_int, C.c_double, _dp, _dp]),
@@ -214,8 +225,40 @@ class Molecule(_Obj):
         arr = (_Atom * len(self.atoms))(*[_Atom(*a) for a in self.atoms])
         super().__init__(_call("gauxc_molecule_new_from_atoms", arr, len(self.atoms)))
 
+    @classmethod
+    def from_hdf5(cls, fname, dset="/MOLECULE"):
+        m = cls.__new__(cls)
+        _Obj.__init__(m, _call("gauxc_molecule_new"))
+        _call("gauxc_molecule_read_hdf5_record", m.h, fname.encode(), dset.encode())
+        return m
+
+    def write_hdf5(self, fname, dset="/MOLECULE"):
+        _call("gauxc_molecule_write_hdf5_record", self.h, fname.encode(), dset.encode())
+
+    def atoms(self):
+        n = self.natoms()
+        buf = (_Atom * n)()
+        _call("gauxc_b200_molecule_get_atoms", self.h, buf)
+        return [(int(a.Z), a.x, a.y, a.z) for a in buf]
+
     def natoms(self):
         return _call("gauxc_molecule_natoms", self.h)
+
+
+def hdf5_read_dataset(fname, dset):
+    """Dense FP64 dataset of an HDF5 file (dims in file order, i.e. the column-major matrices come out transposed)."""
+    dims = (C.c_int64 * 4)()
+    rank = C.c_int(0)
+    n = _call("gauxc_b200_hdf5_dataset_size", fname.encode(), dset.encode(), dims, C.byref(rank))
+    out = np.zeros(n)
+    _call("gauxc_b200_hdf5_read_dataset", fname.encode(), dset.encode(), _d(out), n)
+    return out.reshape([dims[i] for i in range(rank.value)])
+
+
+def hdf5_write_dataset(fname, dset, a):
+    a = np.ascontiguousarray(a, np.float64)
+    dims = (C.c_int64 * max(1, a.ndim))(*a.shape)
+    _call("gauxc_b200_hdf5_write_dataset", fname.encode(), dset.encode(), _d(a), dims, a.ndim)
 
 
 class BasisSet(_Obj):
@@ -238,6 +281,16 @@ class BasisSet(_Obj):
                 arr[k].origin[j] = s["origin"][j]
             arr[k].shell_tolerance = s.get("tol", 1e-10)
         super().__init__(_call("gauxc_basisset_new_from_shells", arr, len(shells), normalize))
+
+    @classmethod
+    def from_hdf5(cls, fname, dset="/BASIS"):
+        b = cls.__new__(cls)
+        _Obj.__init__(b, _call("gauxc_basisset_new"))
+        _call("gauxc_basisset_read_hdf5_record", b.h, fname.encode(), dset.encode())
+        return b
+
+    def write_hdf5(self, fname, dset="/BASIS"):
+        _call("gauxc_basisset_write_hdf5_record", self.h, fname.encode(), dset.encode())
 
     def nbf(self):
         return _call("gauxc_b200_basisset_nbf", self.h)
@@ -534,6 +587,9 @@ class XCIntegrator(_Obj):
     def stream(self):
         """cudaStream_t (int) the integrator launches on."""
         return _call("gauxc_b200_integrator_stream", self.h)
+
+    def set_vxc_root_only(self, on):
+        _call("gauxc_b200_integrator_set_vxc_root_only", self.h, int(on))
 
     def set_profile(self, on):
         _call("gauxc_b200_integrator_set_profile", self.h, int(on))

@@ -27,6 +27,15 @@
 // 2499-atom water cluster need this.  Products / sums run in neighbour order instead of index
 // order (a reordering of exact factors 0 and 1 plus O(1e-16) rounding).  The host additionally
 // skips pairs whose two partials are both <= 1e-13; that only perturbs terms below 1e-13 of the sum.
+//
+// FP32 screen.  Of the pairs (C, B) the two loops visit, only a handful per point are "active"
+// (|mu_CB| < 0.64: a factor strictly between 0 and 1); all others contribute EXACTLY 1 (mu <= -0.64) or make
+// P_C EXACTLY 0 (mu >= 0.64).  Which of the three a pair is follows from a single-precision mu (distances
+// from FP32 atom coordinates, an FP32 copy of 1 / R_AB: ~8 FP32 instructions, no FP64 square root) whenever
+// that mu is farther than 2e-3 from +-0.64 -- three orders of magnitude more than its rounding error; only
+// the rest takes the FP64 path, with the operand order above.  The set of active factors and the order they
+// are multiplied in are unchanged, so the weights are bit-identical to the all-FP64 kernel; the FP64 work per
+// point drops from O(near atoms^2) to O(active pairs).
 #include "kernels.cuh"
 
 namespace gxb {
@@ -34,6 +43,7 @@ namespace gxb {
 namespace {
 
 constexpr double magic_ssf = 0.64;
+constexpr float screen_lo = 0.64f - 2e-3f, screen_hi = 0.64f + 2e-3f;
 
 __device__ __forceinline__ double g_frisch(double mu) {
   const double s = mu * 1.5625;  // 1 / 0.64 (exactly representable; the host divides by 0.64)
@@ -43,7 +53,9 @@ __device__ __forceinline__ double g_frisch(double mu) {
 
 __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __restrict__ tiles,
                                                   const double* __restrict__ atoms,
+                                                  const float4* __restrict__ atoms_f,
                                                   const double* __restrict__ rab_inv,
+                                                  const float* __restrict__ rab_inv_f,
                                                   const double* __restrict__ dist_nearest,
                                                   const int* __restrict__ nbr_idx,
                                                   const double* __restrict__ nbr_dist,
@@ -83,10 +95,16 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   const int ip = tile.pt_off + i;
   const int par = pv.tasks[tile.task].iParent;
   const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];
+  const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
 
   auto dist = [&](int A) {
     const double dx = px - atoms[3 * A], dy = py - atoms[3 * A + 1], dz = pz - atoms[3 * A + 2];
     return sqrt(dx * dx + dy * dy + dz * dz);
+  };
+  auto dist_f = [&](int A) {
+    const float4 a = __ldg(atoms_f + A);
+    const float dx = pxf - a.x, dy = pyf - a.y, dz = pzf - a.z;
+    return sqrtf(dx * dx + dy * dy + dz * dz);
   };
 
   const double r_par = dist(par);
@@ -106,26 +124,40 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
     const double r = dist(A);
     if (r < rmin) { rmin = r; imin = A; }
   }
+  const float rminf = (float)rmin;
 
   double sum = 0., p_par = 0.;
-  const double c_cut = kappa * rmin;
+  const double c_lim = kappa * rmin + r_anc;  // candidates: R(anchor, C) < c_lim
   for (int kc = 0; kc < natoms; ++kc) {
-    if (nd[kc] - r_anc >= c_cut) break;  // every remaining C has P_C == 0
+    if (nd[kc] >= c_lim) break;  // every remaining C has P_C == 0
     const int C = nb[kc];
-    const double rC = dist(C);
+    const float* __restrict__ rabCf = rab_inv_f + (size_t)C * natoms;
+    const float rCf = dist_f(C);
     if (C != imin) {
-      const double Rinv = rab_inv[(size_t)C * natoms + imin];
-      // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
-      const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
-      if (mu >= magic_ssf) continue;  // P_C == 0
+      // mu(C, nearest) >= 0.64  =>  P_C == 0: decided in FP32 unless too close to the threshold
+      const float muf = (rCf - rminf) * __ldg(rabCf + imin);
+      if (muf >= screen_hi) continue;
+      if (muf > screen_lo) {
+        const double rC = dist(C);
+        const double Rinv = rab_inv[(size_t)C * natoms + imin];
+        // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
+        const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
+        if (mu >= magic_ssf) continue;  // P_C == 0
+      }
     }
+    const double rC = dist(C);
     double Pc = 1.;
     const double* __restrict__ rabC = rab_inv + (size_t)C * natoms;
-    const double b_cut = kappa * rC;
+    const double b_lim = kappa * rC + r_anc;  // factors beyond R(anchor, B) >= b_lim are exactly 1
     for (int kb = 0; kb < natoms; ++kb) {
-      if (nd[kb] - r_anc >= b_cut) break;  // every remaining factor is exactly 1
+      if (nd[kb] >= b_lim) break;
       const int Bq = nb[kb];
       if (Bq == C) continue;
+      // FP32 screen: mu_CB = (r_C - r_B) / R_CB
+      const float muf = (rCf - dist_f(Bq)) * __ldg(rabCf + Bq);
+      if (muf <= -screen_hi) continue;              // factor exactly 1
+      if (muf >= screen_hi) { Pc = 0.; break; }     // factor exactly 0
+      // FP64 path, host operand order
       const double rB = dist(Bq);
       const double Rinv = rabC[Bq];
       if (Bq < C) {
@@ -150,10 +182,12 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
 }  // namespace
 
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
-                        const double* nbr_dist, int natoms, cudaStream_t s) {
+                        const float* atoms_f4, const double* rab_inv, const float* rab_inv_f,
+                        const double* dist_nearest, const int* nbr_idx, const double* nbr_dist, int natoms,
+                        cudaStream_t s) {
   if (ntiles <= 0) return;
-  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab_inv, dist_nearest, nbr_idx, nbr_dist, natoms);
+  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, reinterpret_cast<const float4*>(atoms_f4), rab_inv, rab_inv_f,
+                                   dist_nearest, nbr_idx, nbr_dist, natoms);
 }
 
 }  // namespace gxb

@@ -542,6 +542,11 @@ void gauxc_b200_integrator_stats(GauXCStatus* status, const GauXCIntegrator inte
   o[14] = o[15] = 0.;
   C_CATCH(status)
 }
+void gauxc_b200_integrator_set_vxc_root_only(GauXCStatus* status, const GauXCIntegrator integrator, int on) {
+  C_TRY(status)
+  INTG(integrator)->set_vxc_root_only(on != 0);
+  C_CATCH(status)
+}
 void gauxc_b200_integrator_set_profile(GauXCStatus* status, const GauXCIntegrator integrator, int on) {
   C_TRY(status)
   INTG(integrator)->set_profile(on != 0);
@@ -567,6 +572,44 @@ void gauxc_molecule_read_hdf5_record(GauXCStatus* status, GauXCMolecule mol, con
 void gauxc_basisset_read_hdf5_record(GauXCStatus* status, GauXCBasisSet basis, const char* fname, const char* dset) {
   C_TRY(status)
   read_hdf5_record(*BAS(basis), fname ? fname : "", dset ? dset : "");
+  C_CATCH(status)
+}
+
+// dense FP64 datasets (/DENSITY, /VXC, /EXC ... of the reference's fixtures)
+int64_t gauxc_b200_hdf5_dataset_size(GauXCStatus* status, const char* fname, const char* dset, int64_t* dims4, int* rank) {
+  int64_t n = 0;
+  C_TRY(status)
+  std::vector<double> data;
+  std::vector<size_t> dims;
+  read_hdf5_dataset(fname ? fname : "", dset ? dset : "", data, dims);
+  if (dims.size() > 4) GAUXC_GENERIC_EXCEPTION("HDF5: rank > 4");
+  if (rank) *rank = (int)dims.size();
+  for (size_t i = 0; i < dims.size() && dims4; ++i) dims4[i] = (int64_t)dims[i];
+  n = (int64_t)data.size();
+  C_CATCH(status)
+  return n;
+}
+void gauxc_b200_hdf5_read_dataset(GauXCStatus* status, const char* fname, const char* dset, double* out, int64_t n) {
+  C_TRY(status)
+  std::vector<double> data;
+  std::vector<size_t> dims;
+  read_hdf5_dataset(fname ? fname : "", dset ? dset : "", data, dims);
+  if ((int64_t)data.size() != n) GAUXC_GENERIC_EXCEPTION("HDF5: dataset size mismatch");
+  std::copy(data.begin(), data.end(), out);
+  C_CATCH(status)
+}
+void gauxc_b200_hdf5_write_dataset(GauXCStatus* status, const char* fname, const char* dset, const double* data,
+                                   const int64_t* dims, int rank) {
+  C_TRY(status)
+  std::vector<size_t> d(dims, dims + rank);
+  write_hdf5_dataset(fname ? fname : "", dset ? dset : "", data, d);
+  C_CATCH(status)
+}
+// molecule / basis accessors for records read from a file
+void gauxc_b200_molecule_get_atoms(GauXCStatus* status, const GauXCMolecule mol, GauXCAtom* atoms) {
+  C_TRY(status)
+  auto* m = MOL(mol);
+  for (size_t i = 0; i < m->size(); ++i) atoms[i] = GauXCAtom{(*m)[i].Z, (*m)[i].x, (*m)[i].y, (*m)[i].z};
   C_CATCH(status)
 }
 
@@ -660,6 +703,7 @@ void gauxc_b200_load_balancer_state(GauXCStatus* status, const GauXCLoadBalancer
 void gauxc_b200_load_balancer_get_task(GauXCStatus* status, const GauXCLoadBalancer lb, int64_t it,
                                        double* points, double* weights, int32_t* shell_list) {
   C_TRY(status)
+  (*LB(lb))->sync_host_tasks();  // weights modified on the device are fetched on first use
   auto& t = (*LB(lb))->get_tasks().at((size_t)it);
   for (size_t i = 0; i < t.points.size(); ++i) {
     if (points) { points[3 * i] = t.points[i][0]; points[3 * i + 1] = t.points[i][1]; points[3 * i + 2] = t.points[i][2]; }
@@ -672,6 +716,7 @@ void gauxc_b200_load_balancer_set_task_weights(GauXCStatus* status, GauXCLoadBal
                                                const double* weights) {
   C_TRY(status)
   auto& l = **LB(lb);
+  l.sync_host_tasks();
   auto& t = l.get_tasks().at((size_t)it);
   std::copy(weights, weights + t.weights.size(), t.weights.begin());
   l.touch();

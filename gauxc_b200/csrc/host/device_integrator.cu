@@ -103,6 +103,7 @@ struct DevicePlan {
   DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
   DevBuf<double> d_px, d_py, d_pz, d_w;
   DevBuf<double> d_atoms, d_rab, d_dist_nearest, d_nbr_dist;
+  DevBuf<float> d_atoms_f4, d_rab_f;  // FP32 copies for the SSF screen
   DevBuf<int> d_nbr_idx;  // per atom: all atoms sorted by distance from it (SSF loop cut-offs)
   double f_dense = 0., sum_nbe_npts = 0.;
   std::map<int, std::shared_ptr<Schedule>> schedules;  // key: nmat
@@ -284,6 +285,13 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
     std::vector<double> rab_inv(meta.rab.size());
     for (size_t q = 0; q < rab_inv.size(); ++q) rab_inv[q] = meta.rab[q] > 0. ? 1. / meta.rab[q] : 0.;
     plan->d_rab.upload(rab_inv);
+    std::vector<float> rab_inv_f(rab_inv.begin(), rab_inv.end());
+    plan->d_rab_f.upload(rab_inv_f);
+    std::vector<float> atoms_f4(4 * mol.size(), 0.f);
+    for (size_t a = 0; a < mol.size(); ++a) {
+      atoms_f4[4 * a] = (float)mol[a].x; atoms_f4[4 * a + 1] = (float)mol[a].y; atoms_f4[4 * a + 2] = (float)mol[a].z;
+    }
+    plan->d_atoms_f4.upload(atoms_f4);
   }
   plan->d_dist_nearest.upload(meta.dist_nearest);
   {
@@ -312,8 +320,12 @@ std::shared_ptr<DevicePlan> get_device_plan(LoadBalancer& lb) {
   lb.get_tasks();
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
-  if (lb.device_cache && std::static_pointer_cast<DevicePlan>(lb.device_cache)->device != dev)
-    lb.device_cache.reset();  // the calling thread moved to another device: rebuild there
+  const bool moved = lb.device_cache && std::static_pointer_cast<DevicePlan>(lb.device_cache)->device != dev;
+  if (moved || !lb.device_cache || lb.device_cache_version != lb.version()) {
+    // a rebuild reads the host task list: weights that so far live only in the old plan come home first
+    lb.sync_host_tasks();
+    if (moved) lb.device_cache.reset();  // the calling thread moved to another device: rebuild there
+  }
   if (!lb.device_cache || lb.device_cache_version != lb.version()) {
     lb.device_cache = build_plan(lb);
     lb.device_cache_version = lb.version();
@@ -598,26 +610,38 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, 0));
   gxb::launch_ssf_weights(plan->view(), plan->d_tiles.p, (int)plan->tiles.size(), plan->d_atoms.p,
-                          plan->d_rab.p, plan->d_dist_nearest.p, plan->d_nbr_idx.p, plan->d_nbr_dist.p,
-                          plan->natoms, 0);
+                          plan->d_atoms_f4.p, plan->d_rab.p, plan->d_rab_f.p, plan->d_dist_nearest.p,
+                          plan->d_nbr_idx.p, plan->d_nbr_dist.p, plan->natoms, 0);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(e1, 0));
-  // copy_weights_to_tasks: the host XCTask list stays the source of truth for other consumers
-  std::vector<double> w(plan->npts);
-  if (plan->npts)
-    CUDA_CHECK(cudaMemcpy(w.data(), plan->d_w.p, plan->npts * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaEventSynchronize(e1));
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   timer_.add("MolecularWeights", ms);
-  auto& tasks = lb.get_tasks();
-  size_t off = 0;
-  for (auto& t : tasks) {
-    std::copy(w.begin() + off, w.begin() + off + t.weights.size(), t.weights.begin());
-    off += t.weights.size();
-    t.max_weight = t.weights.empty() ? 0. : *std::max_element(t.weights.begin(), t.weights.end());
-  }
+  // The weights stay on the device, where the integrator reads them.  The host XCTask list is brought up to
+  // date only when a consumer asks for it (LoadBalancer::sync_host_tasks, called by the task accessors of the
+  // C ABI): the reference copies every weight back task by task (device_molecular_weights.cxx:60-80), 1.2 GB
+  // and a host loop over 1e6 tasks for the 2499-atom cluster.
+  std::weak_ptr<DevicePlan> wplan = plan;
+  lb.set_host_sync([wplan](std::vector<XCTask>& tasks) {
+    auto p = wplan.lock();
+    if (!p || !p->npts) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != p->device) cudaSetDevice(p->device);
+    std::vector<double> w(p->npts);
+    cudaError_t e = cudaMemcpy(w.data(), p->d_w.p, p->npts * sizeof(double), cudaMemcpyDeviceToHost);
+    if (prev != p->device && prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) GAUXC_GENERIC_EXCEPTION(std::string("CUDA Failed: ") + cudaGetErrorString(e));
+    size_t off = 0;
+    for (auto& t : tasks) {
+      std::copy(w.begin() + off, w.begin() + off + t.weights.size(), t.weights.begin());
+      off += t.weights.size();
+      t.max_weight = t.weights.empty() ? 0. : *std::max_element(t.weights.begin(), t.weights.end());
+    }
+  });
   lb.state().modified_weights_are_stored = true;
   lb.state().weight_alg = XCWeightAlg::SSF;
   // device copy is already current: no version bump
@@ -947,7 +971,7 @@ void XCIntegrator::eval_exc_vxc(int64_t m, int64_t n, const double* P, int64_t l
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   I.p_pending = true;
   eval_exc_vxc_device(I.dP.p, I.dVXC.p, I.d_out2.p, true);
-  download_matrix(VXC, ldvxc, I.dVXC.p, nbf, s);
+  if (!vxc_root_only_ || lb_->runtime().comm_rank() == 0) download_matrix(VXC, ldvxc, I.dVXC.p, nbf, s);
   CUDA_CHECK(cudaMemcpyAsync(I.h_out2, I.d_out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaEventRecord(I.e_end, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1111,8 +1135,10 @@ void XCIntegrator::eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldp
   if (do_vxc) {
     reduce_and_symmetrize_(I.dVXC.p, I.dVXCz.p, I.d_out2.p, inbf, true);
     launches += 2;
-    download_matrix(VXCs, ldvxcs, I.dVXC.p, nbf, s);
-    download_matrix(VXCz, ldvxcz, I.dVXCz.p, nbf, s);
+    if (!vxc_root_only_ || lb_->runtime().comm_rank() == 0) {
+      download_matrix(VXCs, ldvxcs, I.dVXC.p, nbf, s);
+      download_matrix(VXCz, ldvxcz, I.dVXCz.p, nbf, s);
+    }
   } else if (red_->comm_size() > 1) {
     red_->allreduce_inplace(I.d_out2.p, 2, ReductionOp::Sum, s);
   }

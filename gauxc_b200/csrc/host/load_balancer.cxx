@@ -35,6 +35,7 @@ LoadBalancer::LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecul
 }
 
 void LoadBalancer::replace_tasks(std::vector<XCTask> tasks) {
+  host_sync_ = nullptr;
   local_tasks_ = std::move(tasks);
   tasks_created_ = true;
   ++version_;

@@ -6,6 +6,7 @@
 #pragma once
 #include "grid.hpp"
 #include "types.hpp"
+#include <functional>
 #include <memory>
 #include <string>
 
@@ -60,6 +61,8 @@ class LoadBalancer {
   LoadBalancerState state_;
   uint64_t version_ = 0;  // bumped whenever tasks / weights change (device caches key on it)
 
+  // pending refresh of host-side task data that currently lives on the device (SSF weights)
+  std::function<void(std::vector<XCTask>&)> host_sync_;
   bool fill_in_ = false;  // REPLICATED-FILLIN: contiguous shell range first..last instead of the exact list
 
   std::vector<XCTask> create_local_tasks_() const;
@@ -74,6 +77,15 @@ public:
   // install a user supplied task list without generating the default one first
   void replace_tasks(std::vector<XCTask> tasks);
   bool tasks_created() const { return tasks_created_; }
+  // Device MolecularWeights leave the partitioned weights on the device; the host copy is refreshed on demand
+  void set_host_sync(std::function<void(std::vector<XCTask>&)> f) { host_sync_ = std::move(f); }
+  void sync_host_tasks() {
+    if (host_sync_) {
+      auto f = std::move(host_sync_);
+      host_sync_ = nullptr;
+      f(local_tasks_);
+    }
+  }
   const Molecule& molecule() const { return *mol_; }
   const MolGrid& molgrid() const { return *mg_; }
   const BasisSet& basis() const { return *basis_; }

@@ -101,6 +101,7 @@ class XCIntegrator {
   std::shared_ptr<Impl> impl_;
   Timer timer_;
   XCIntegratorStats stats_;
+  bool vxc_root_only_ = false;
 
   void reduce_and_symmetrize_(double* dV, double* dVz, double* d_out2, int nbf, bool do_vxc);
   void upload_density_(const double* P, int64_t ldp, double* dP, size_t nbf);
@@ -130,6 +131,10 @@ public:
   void eval_exc_vxc_device(const double* dP, double* dVXC, double* d_out2, bool do_vxc = true);
 
   void set_profile(bool on);
+  // Extension: only rank 0 copies VXC back to its host buffer (the other ranks' buffers are left untouched).  The
+  // replicated contract of the reference makes every rank of a box pull nbf^2 * 8 bytes through the host's PCIe
+  // root / memory controllers at once; a caller that diagonalises on one rank does not need that.
+  void set_vxc_root_only(bool on) { vxc_root_only_ = on; }
   const XCIntegratorStats& stats() const { return stats_; }
   const Timer& get_timings() const { return timer_; }
   LoadBalancer& load_balancer() { return *lb_; }

@@ -317,6 +317,15 @@ void gauxc_b200_allreduce_device(GauXCStatus* status, double* dptr, size_t n);
 void gauxc_b200_integrator_eval_exc_vxc_rks_device(GauXCStatus* status, const GauXCIntegrator integrator,
                                                    const double* dP, double* dVXC, double* d_out2);
 
+/* Dense FP64 datasets of the reference's HDF5 fixtures (/DENSITY, /VXC, /EXC, ...): size query (returns the element
+ * count, fills up to 4 dims in file order), read, and append-to-file write (root group, contiguous). */
+int64_t gauxc_b200_hdf5_dataset_size(GauXCStatus* status, const char* fname, const char* dset, int64_t* dims4,
+                                     int* rank);
+void gauxc_b200_hdf5_read_dataset(GauXCStatus* status, const char* fname, const char* dset, double* out, int64_t n);
+void gauxc_b200_hdf5_write_dataset(GauXCStatus* status, const char* fname, const char* dset, const double* data,
+                                   const int64_t* dims, int rank);
+void gauxc_b200_molecule_get_atoms(GauXCStatus* status, const GauXCMolecule mol, GauXCAtom* atoms);
+
 /* Introspection (tests / bench). */
 int64_t gauxc_b200_basisset_nbf(GauXCStatus* status, const GauXCBasisSet basis);
 int64_t gauxc_b200_basisset_nshells(GauXCStatus* status, const GauXCBasisSet basis);
@@ -351,6 +360,8 @@ void gauxc_b200_load_balancer_set_tasks(GauXCStatus* status, GauXCLoadBalancer l
  * 0, 0}; per-kernel ms are only filled in profile mode */
 void gauxc_b200_integrator_stats(GauXCStatus* status, const GauXCIntegrator integrator, double* out16);
 void gauxc_b200_integrator_set_profile(GauXCStatus* status, const GauXCIntegrator integrator, int on);
+/* extension: only rank 0 copies VXC back to host memory (default off = the reference's replicated result) */
+void gauxc_b200_integrator_set_vxc_root_only(GauXCStatus* status, const GauXCIntegrator integrator, int on);
 double gauxc_b200_molecular_weights_last_ms(GauXCStatus* status, const GauXCMolecularWeights mw);
 /* Lebedev / radial tables of the grid generator (tests) */
 int64_t gauxc_b200_lebedev(GauXCStatus* status, int npts, double* xyz, double* w);

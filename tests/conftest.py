@@ -18,6 +18,7 @@ def _built():
     """The C-ABI library and the oracle must exist; build them if they are missing."""
     from gauxc_b200 import build as b
     b.build_library()
+    b.build_driver()
     b.build_oracle()
 
 

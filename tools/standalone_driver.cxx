@@ -1,0 +1,339 @@
+// INI-driven stand-alone driver for the B200 Device path, reading the reference's own input decks and HDF5
+// fixture files unchanged (reference: tests/standalone_driver.cxx:31-851, tests/ini_input.cxx).
+//
+//   standalone_driver input.inp
+//
+//   [GAUXC]
+//   ref_file = benzene_svwn5_cc-pvdz_ufg_ssf.hdf5     required: /MOLECULE, /BASIS, /DENSITY (RKS) or
+//                                                     /DENSITY_SCALAR + /DENSITY_Z (UKS), optional /EXC, /VXC...
+//   grid = UltraFine | Fine | SuperFine | GM3 | GM5     rad_quad = MuraKnowles | MurrayHandyLaming
+//   pruning_scheme = Unpruned | Robust | Treutler        batch_size = 512       basis_tol = 1e-10
+//   func = PBE0 | SVWN5 | PBE | BLYP | B3LYP | ...       integrate_vxc / integrate_den / integrate_exc_grad = TRUE|FALSE
+//   lb_exec_space / int_exec_space / integrator_kernel / lwd_kernel / reduction_kernel as in the reference
+//   outfile = result.hdf5                                 writes /MOLECULE /BASIS /DENSITY[_SCALAR,_Z] /VXC[...] /EXC
+//
+// The Host execution space of the integrator does not exist in this build: INT_EXEC_SPACE defaults to Device and
+// "Host" is refused, as the library itself refuses it.  Keys of paths outside the LDA/GGA EXC/VXC scope
+// (INTEGRATE_EXX, INTEGRATE_FXC_CONTRACTION, INTEGRATE_DD_PSI*) are reported and skipped.
+#include <gauxc_b200.hpp>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+using namespace GauXC;
+
+namespace {
+
+struct matrix_type {
+  using value_type = double;
+  matrix_type() = default;
+  matrix_type(long r, long c) : r_(r), c_(c), v_((size_t)(r * c), 0.) {}
+  long rows() const { return r_; }
+  long cols() const { return c_; }
+  double* data() { return v_.data(); }
+  const double* data() const { return v_.data(); }
+  long r_ = 0, c_ = 0;
+  std::vector<double> v_;
+};
+
+std::string upper(std::string s) {
+  for (auto& c : s) c = (char)std::toupper((unsigned char)c);
+  return s;
+}
+std::string trim(const std::string& s) {
+  const auto b = s.find_first_not_of(" \t\r\n"), e = s.find_last_not_of(" \t\r\n");
+  return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+}
+
+// tests/ini_input.cxx: [SECTION] headers, key = value, '#' comments; keys are case-insensitive "SECTION.KEY"
+class INIFile {
+  std::map<std::string, std::string> kv_;
+
+public:
+  explicit INIFile(const std::string& fname) {
+    std::ifstream f(fname);
+    if (!f) throw std::runtime_error("Cannot open input file " + fname);
+    std::string line, section;
+    while (std::getline(f, line)) {
+      const auto hash = line.find('#');
+      if (hash != std::string::npos) line.erase(hash);
+      line = trim(line);
+      if (line.empty()) continue;
+      if (line.front() == '[' && line.back() == ']') {
+        section = upper(trim(line.substr(1, line.size() - 2)));
+        continue;
+      }
+      const auto eq = line.find('=');
+      if (eq == std::string::npos) throw std::runtime_error("Malformed input line: " + line);
+      kv_[section + "." + upper(trim(line.substr(0, eq)))] = trim(line.substr(eq + 1));
+    }
+  }
+  bool contains(const std::string& k) const { return kv_.count(upper(k)) > 0; }
+  std::string str(const std::string& k) const {
+    auto it = kv_.find(upper(k));
+    if (it == kv_.end()) throw std::runtime_error("Required keyword missing: " + k);
+    return it->second;
+  }
+  std::string str(const std::string& k, const std::string& dflt) const { return contains(k) ? str(k) : dflt; }
+  bool flag(const std::string& k, bool dflt) const {
+    if (!contains(k)) return dflt;
+    const auto v = upper(str(k));
+    return v == "TRUE" || v == "1" || v == "YES" || v == "ON";
+  }
+  double num(const std::string& k, double dflt) const { return contains(k) ? std::stod(str(k)) : dflt; }
+};
+
+matrix_type read_matrix(const std::string& fname, const std::string& dset, long nbf) {
+  detail::StatusGuard g;
+  int64_t dims[4] = {0, 0, 0, 0};
+  int rank = 0;
+  const int64_t n = gauxc_b200_hdf5_dataset_size(&g.st, fname.c_str(), dset.c_str(), dims, &rank);
+  g.check();
+  if (rank != 2 || dims[0] != nbf || dims[1] != nbf) throw std::runtime_error(dset + " has the wrong shape");
+  matrix_type M(nbf, nbf);
+  gauxc_b200_hdf5_read_dataset(&g.st, fname.c_str(), dset.c_str(), M.data(), n);
+  g.check();
+  return M;  // symmetric: the row-major file order needs no transpose
+}
+bool has_dataset(const std::string& fname, const std::string& dset) {
+  GauXCStatus st{0, nullptr};
+  int64_t dims[4];
+  int rank = 0;
+  gauxc_b200_hdf5_dataset_size(&st, fname.c_str(), dset.c_str(), dims, &rank);
+  const bool ok = st.code == 0;
+  gauxc_status_delete(&st);
+  return ok;
+}
+double read_scalar(const std::string& fname, const std::string& dset) {
+  detail::StatusGuard g;
+  double v = 0;
+  gauxc_b200_hdf5_read_dataset(&g.st, fname.c_str(), dset.c_str(), &v, 1);
+  g.check();
+  return v;
+}
+void write_matrix(const std::string& fname, const std::string& dset, const matrix_type& M) {
+  detail::StatusGuard g;
+  const int64_t dims[2] = {M.rows(), M.cols()};
+  gauxc_b200_hdf5_write_dataset(&g.st, fname.c_str(), dset.c_str(), M.data(), dims, 2);
+  g.check();
+}
+double frob_diff(const matrix_type& A, const matrix_type& B) {
+  double s = 0;
+  for (size_t i = 0; i < A.v_.size(); ++i) s += (A.v_[i] - B.v_[i]) * (A.v_[i] - B.v_[i]);
+  return std::sqrt(s);
+}
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc != 2) {
+    std::fprintf(stderr, "usage: standalone_driver input.inp\n");
+    return 2;
+  }
+  try {
+    INIFile input(argv[1]);
+    const std::string ref_file = input.str("GAUXC.REF_FILE");
+    const std::string grid_spec = upper(input.str("GAUXC.GRID", "ULTRAFINE"));
+    const std::string rad_quad_spec = upper(input.str("GAUXC.RAD_QUAD", "MURAKNOWLES"));
+    const std::string prune_spec = upper(input.str("GAUXC.PRUNING_SCHEME", "UNPRUNED"));
+    const std::string lb_ex_str = upper(input.str("GAUXC.LB_EXEC_SPACE", "HOST"));
+    const std::string int_ex_str = upper(input.str("GAUXC.INT_EXEC_SPACE", "DEVICE"));
+    const std::string integrator_kernel = input.str("GAUXC.INTEGRATOR_KERNEL", "Default");
+    const std::string lwd_kernel = input.str("GAUXC.LWD_KERNEL", "Default");
+    const std::string reduction_kernel = input.str("GAUXC.REDUCTION_KERNEL", "Default");
+    const size_t batch_size = (size_t)input.num("GAUXC.BATCH_SIZE", 512);
+    const double basis_tol = input.num("GAUXC.BASIS_TOL", 1e-10);
+    const std::string func_spec = upper(input.str("GAUXC.FUNC", "PBE0"));
+    const bool integrate_den = input.flag("GAUXC.INTEGRATE_DEN", false);
+    const bool integrate_vxc = input.flag("GAUXC.INTEGRATE_VXC", true);
+    const bool integrate_exc_grad = input.flag("GAUXC.INTEGRATE_EXC_GRAD", false);
+
+    std::cout << std::boolalpha << "DRIVER SETTINGS: \n"
+              << "  REF_FILE          = " << ref_file << "\n  GRID              = " << grid_spec
+              << "\n  RAD_QUAD          = " << rad_quad_spec << "\n  PRUNING_SCHEME    = " << prune_spec
+              << "\n  BATCH_SIZE        = " << batch_size << "\n  BASIS_TOL         = " << basis_tol
+              << "\n  FUNCTIONAL        = " << func_spec << "\n  LB_EXEC_SPACE     = " << lb_ex_str
+              << "\n  INT_EXEC_SPACE    = " << int_ex_str << "\n  INTEGRATOR_KERNEL = " << integrator_kernel
+              << "\n  LWD_KERNEL        = " << lwd_kernel << "\n  REDUCTION_KERNEL  = " << reduction_kernel
+              << "\n  DEN (?)           = " << integrate_den << "\n  VXC (?)           = " << integrate_vxc
+              << "\n  EXC_GRAD (?)      = " << integrate_exc_grad << "\n\n";
+    for (const char* k : {"GAUXC.INTEGRATE_EXX", "GAUXC.INTEGRATE_FXC_CONTRACTION", "GAUXC.INTEGRATE_DD_PSI",
+                          "GAUXC.INTEGRATE_DD_PSI_POTENTIAL"})
+      if (input.flag(k, false)) std::cout << "  (" << k << " is outside the EXC/VXC scope of this build: skipped)\n";
+
+    const std::map<std::string, AtomicGridSizeDefault> mg_map = {{"FINE", AtomicGridSizeDefault::FineGrid},
+                                                                 {"ULTRAFINE", AtomicGridSizeDefault::UltraFineGrid},
+                                                                 {"SUPERFINE", AtomicGridSizeDefault::SuperFineGrid},
+                                                                 {"GM3", AtomicGridSizeDefault::GM3},
+                                                                 {"GM5", AtomicGridSizeDefault::GM5}};
+    const std::map<std::string, PruningScheme> prune_map = {
+        {"UNPRUNED", PruningScheme::Unpruned}, {"ROBUST", PruningScheme::Robust}, {"TREUTLER", PruningScheme::Treutler}};
+    const std::map<std::string, RadialQuad> rq_map = {{"BECKE", RadialQuad::Becke},
+                                                      {"MURAKNOWLES", RadialQuad::MuraKnowles},
+                                                      {"TREUTLERAHLRICHS", RadialQuad::TreutlerAhlrichs},
+                                                      {"MURRAYHANDYLAMING", RadialQuad::MurrayHandyLaming}};
+    const std::map<std::string, ExecutionSpace> ex_map = {{"HOST", ExecutionSpace::Host}, {"DEVICE", ExecutionSpace::Device}};
+
+    // ---- molecule, basis (hdf5_read.cxx records), densities ----
+    detail::StatusGuard g;
+    GauXCMolecule cmol = gauxc_molecule_new(&g.st);
+    g.check();
+    gauxc_molecule_read_hdf5_record(&g.st, cmol, ref_file.c_str(), "/MOLECULE");
+    g.check();
+    const size_t natoms = gauxc_molecule_natoms(&g.st, cmol);
+    std::vector<GauXCAtom> catoms(natoms);
+    gauxc_b200_molecule_get_atoms(&g.st, cmol, catoms.data());
+    g.check();
+    Molecule mol;
+    for (auto& a : catoms) mol.emplace_back(AtomicNumber(a.Z), a.x, a.y, a.z);
+    gauxc_molecule_delete(&g.st, &cmol);
+
+    GauXCBasisSet cbas = gauxc_basisset_new(&g.st);
+    g.check();
+    gauxc_basisset_read_hdf5_record(&g.st, cbas, ref_file.c_str(), "/BASIS");
+    g.check();
+    const long nsh = (long)gauxc_b200_basisset_nshells(&g.st, cbas);
+    BasisSet<double> basis;
+    for (long s = 0; s < nsh; ++s) {
+      int32_t l, pure, nprim;
+      double cutoff, origin[3], alpha[32], coeff[32];
+      gauxc_b200_basisset_get_shell(&g.st, cbas, s, &l, &pure, &nprim, &cutoff, origin, alpha, coeff);
+      g.check();
+      Shell<double>::prim_array a{}, c{};
+      for (int k = 0; k < nprim; ++k) { a[k] = alpha[k]; c[k] = coeff[k]; }
+      Shell<double> sh(PrimSize(nprim), AngularMomentum(l), SphericalType(pure), a, c, {origin[0], origin[1], origin[2]},
+                       /*normalize=*/false);  // the records hold normalised coefficients
+      sh.set_shell_tolerance(basis_tol);
+      basis.push_back(sh);
+    }
+    gauxc_basisset_delete(&g.st, &cbas);
+    const long nbf = basis.nbf();
+
+    const bool uks = has_dataset(ref_file, "/DENSITY_Z");
+    matrix_type P, Pz;
+    if (uks) {
+      P = read_matrix(ref_file, "/DENSITY_SCALAR", nbf);
+      Pz = read_matrix(ref_file, "/DENSITY_Z", nbf);
+    } else {
+      P = read_matrix(ref_file, "/DENSITY", nbf);
+    }
+    std::cout << "Molecule: " << natoms << " atoms, basis: " << nsh << " shells / " << nbf << " functions, "
+              << (uks ? "UKS" : "RKS") << "\n";
+
+    // ---- GauXC objects, in the reference driver's order (:223-445) ----
+    auto mg = MolGridFactory::create_default_molgrid(mol, prune_map.at(prune_spec), BatchSize(batch_size),
+                                                     rq_map.at(rad_quad_spec), mg_map.at(grid_spec));
+    auto rt = DeviceRuntimeEnvironment(0.9);
+    double t0 = now();
+    LoadBalancerFactory lb_factory(ex_map.at(lb_ex_str), "Default");
+    auto lb = lb_factory.get_shared_instance(rt, mol, mg, basis);
+    const size_t npts = lb->total_npts();
+    const double t_lb = now() - t0;
+    t0 = now();
+    MolecularWeightsFactory mw_factory(ex_map.at(int_ex_str), "Default", MolecularWeightsSettings{});
+    auto mw = mw_factory.get_instance();
+    mw.modify_weights(*lb);
+    const double t_w = now() - t0;
+    XCIntegratorFactory<matrix_type> integrator_factory(ex_map.at(int_ex_str), "Replicated", integrator_kernel, lwd_kernel,
+                                                        reduction_kernel);
+    auto integrator = integrator_factory.get_instance(functional_type(func_spec, uks), lb);
+    std::cout << "Grid: " << npts << " points in " << lb->ntasks() << " tasks\n";
+
+    double EXC = 0., N_EL = 0.;
+    matrix_type VXC, VXCz;
+    double t_den = 0., t_vxc = 0.;
+    if (integrate_den) {
+      t0 = now();
+      N_EL = integrator.integrate_den(P);
+      t_den = now() - t0;
+      std::cout << std::scientific;
+      std::cout.precision(12);
+      std::cout << "N_EL = " << N_EL << "\n";
+    }
+    if (integrate_vxc) {
+      integrator.eval_exc(P.rows() ? P : P);  // first call builds the device plan and the schedules (not timed)
+      t0 = now();
+      if (uks) std::tie(EXC, VXC, VXCz) = integrator.eval_exc_vxc(P, Pz);
+      else std::tie(EXC, VXC) = integrator.eval_exc_vxc(P);
+      t_vxc = now() - t0;
+    }
+    std::vector<double> grad;
+    if (integrate_exc_grad) {
+      if (uks) std::cout << "  (UKS EXC gradient is NYI: skipped)\n";
+      else grad = integrator.eval_exc_grad(P, natoms);
+    }
+
+    std::cout << std::scientific;
+    std::cout.precision(12);
+    std::printf("Load Balancer %.3f s, Molecular Weights %.3f s (SSF kernel %.1f ms), integrate_den %.3f s, EXC/VXC %.3f s\n",
+                t_lb, t_w, mw.last_ms(), t_den, t_vxc);
+    int rc = 0;
+    if (integrate_vxc) {
+      std::cout << "EXC (calc)   = " << EXC << "\n";
+      if (has_dataset(ref_file, "/EXC")) {
+        const double EXC_ref = read_scalar(ref_file, "/EXC");
+        std::cout << "EXC (ref)    = " << EXC_ref << "\nEXC Diff     = " << std::abs(EXC_ref - EXC) / std::abs(EXC_ref) << "\n";
+      }
+      const char* vname = uks ? "/VXC_SCALAR" : "/VXC";
+      if (has_dataset(ref_file, vname)) {
+        const auto V_ref = read_matrix(ref_file, vname, nbf);
+        const double d = frob_diff(V_ref, VXC) / (double)nbf;
+        std::cout << "| VXC (ref) - VXC (calc) |_F / nbf = " << d << "\n";
+        if (!(d < 1e-8)) rc = 1;
+      }
+      if (uks && has_dataset(ref_file, "/VXC_Z")) {
+        const auto V_ref = read_matrix(ref_file, "/VXC_Z", nbf);
+        const double d = frob_diff(V_ref, VXCz) / (double)nbf;
+        std::cout << "| VXCz (ref) - VXCz (calc) |_F / nbf = " << d << "\n";
+        if (!(d < 1e-8)) rc = 1;
+      }
+    }
+    if (!grad.empty()) {
+      std::cout << "EXC Gradient:\n";
+      for (size_t a = 0; a < natoms; ++a)
+        std::printf("  %4zu %20.12e %20.12e %20.12e\n", a, grad[3 * a], grad[3 * a + 1], grad[3 * a + 2]);
+    }
+
+    // ---- OUTFILE (:768-851) ----
+    if (input.contains("GAUXC.OUTFILE")) {
+      const std::string out = input.str("GAUXC.OUTFILE");
+      std::remove(out.c_str());
+      GauXCMolecule m2 = gauxc_molecule_new_from_atoms(&g.st, catoms.data(), catoms.size());
+      g.check();
+      gauxc_molecule_write_hdf5_record(&g.st, m2, out.c_str(), "/MOLECULE");
+      g.check();
+      gauxc_molecule_delete(&g.st, &m2);
+      GauXCBasisSet b2 = detail::to_c(basis);
+      gauxc_basisset_write_hdf5_record(&g.st, b2, out.c_str(), "/BASIS");
+      g.check();
+      gauxc_basisset_delete(&g.st, &b2);
+      write_matrix(out, uks ? "/DENSITY_SCALAR" : "/DENSITY", P);
+      if (uks) write_matrix(out, "/DENSITY_Z", Pz);
+      if (integrate_vxc) {
+        write_matrix(out, uks ? "/VXC_SCALAR" : "/VXC", VXC);
+        if (uks) write_matrix(out, "/VXC_Z", VXCz);
+        const int64_t one[1] = {1};
+        gauxc_b200_hdf5_write_dataset(&g.st, out.c_str(), "/EXC", &EXC, one, 1);
+        g.check();
+      }
+      if (integrate_den) {
+        const int64_t one[1] = {1};
+        gauxc_b200_hdf5_write_dataset(&g.st, out.c_str(), "/N_EL", &N_EL, one, 1);
+        g.check();
+      }
+      std::cout << "Wrote " << out << "\n";
+    }
+    return rc;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "standalone_driver: %s\n", e.what());
+    return 1;
+  }
+}
