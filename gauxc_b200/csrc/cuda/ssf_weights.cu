@@ -44,6 +44,7 @@ namespace {
 
 constexpr double magic_ssf = 0.64;
 constexpr float screen_lo = 0.64f - 2e-3f, screen_hi = 0.64f + 2e-3f;
+constexpr int SSF_MAXC = 40;  // surviving candidates kept per point before they are flushed (20 KB of shared memory)
 
 __device__ __forceinline__ double g_frisch(double mu) {
   const double s = mu * 1.5625;  // 1 / 0.64 (exactly representable; the host divides by 0.64)
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   // anchor atom of the tile: nearest atom to the tile's first point
   __shared__ double s_best[TP / 32];
   __shared__ int s_arg[TP / 32];
+  __shared__ int s_cand[SSF_MAXC][TP];  // per lane: surviving candidates (column = thread: conflict-free)
   int anchor;
   {
     const double ax = pv.px[tile.pt_off], ay = pv.py[tile.pt_off], az = pv.pz[tile.pt_off];
@@ -126,26 +128,11 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   }
   const float rminf = (float)rmin;
 
-  double sum = 0., p_par = 0.;
-  const double c_lim = kappa * rmin + r_anc;  // candidates: R(anchor, C) < c_lim
-  for (int kc = 0; kc < natoms; ++kc) {
-    if (nd[kc] >= c_lim) break;  // every remaining C has P_C == 0
-    const int C = nb[kc];
-    const float* __restrict__ rabCf = rab_inv_f + (size_t)C * natoms;
-    const float rCf = dist_f(C);
-    if (C != imin) {
-      // mu(C, nearest) >= 0.64  =>  P_C == 0: decided in FP32 unless too close to the threshold
-      const float muf = (rCf - rminf) * __ldg(rabCf + imin);
-      if (muf >= screen_hi) continue;
-      if (muf > screen_lo) {
-        const double rC = dist(C);
-        const double Rinv = rab_inv[(size_t)C * natoms + imin];
-        // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
-        const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
-        if (mu >= magic_ssf) continue;  // P_C == 0
-      }
-    }
+  // P_C = prod_{B != C} s(mu_CB) for one candidate: neighbour order, FP32 screen, FP64 for the active pairs
+  auto partition_function = [&](int C) {
     const double rC = dist(C);
+    const float4 cf = __ldg(atoms_f + C);
+    const float rCf = dist_f(C);
     double Pc = 1.;
     const double* __restrict__ rabC = rab_inv + (size_t)C * natoms;
     const double b_lim = kappa * rC + r_anc;  // factors beyond R(anchor, B) >= b_lim are exactly 1
@@ -153,8 +140,12 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
       if (nd[kb] >= b_lim) break;
       const int Bq = nb[kb];
       if (Bq == C) continue;
-      // FP32 screen: mu_CB = (r_C - r_B) / R_CB
-      const float muf = (rCf - dist_f(Bq)) * __ldg(rabCf + Bq);
+      // FP32 screen: mu_CB = (r_C - r_B) / R_CB, everything from FP32 coordinates (no table gather: the lanes of
+      // a warp work on different C)
+      const float4 bf = __ldg(atoms_f + Bq);
+      const float bx = pxf - bf.x, by = pyf - bf.y, bz = pzf - bf.z;
+      const float cx = cf.x - bf.x, cy = cf.y - bf.y, cz = cf.z - bf.z;
+      const float muf = (rCf - sqrtf(bx * bx + by * by + bz * bz)) * rsqrtf(cx * cx + cy * cy + cz * cz);
       if (muf <= -screen_hi) continue;              // factor exactly 1
       if (muf >= screen_hi) { Pc = 0.; break; }     // factor exactly 0
       // FP64 path, host operand order
@@ -173,6 +164,47 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
         Pc *= 1. - gq;
       }
     }
+    return Pc;
+  };
+
+  // Pass 1 (cheap, per lane): the candidates C that the nearest atom does not already zero.  Pass 2 walks each
+  // lane's OWN list, so all lanes of a warp sit in the pair loop together -- with one shared candidate index
+  // per warp iteration only ~6 of 32 lanes had work (ncu: 6.5 active threads per instruction), because each
+  // point keeps a different ~15 % of the candidates.
+  double sum = 0., p_par = 0.;
+  int cnt = 0;
+  const double c_lim = kappa * rmin + r_anc;  // candidates: R(anchor, C) < c_lim
+  for (int kc = 0; kc < natoms; ++kc) {
+    if (nd[kc] >= c_lim) break;  // every remaining C has P_C == 0
+    const int C = nb[kc];
+    if (C != imin) {
+      // mu(C, nearest) >= 0.64  =>  P_C == 0: decided in FP32 unless too close to the threshold
+      const float muf = (dist_f(C) - rminf) * __ldg(rab_inv_f + (size_t)C * natoms + imin);
+      if (muf >= screen_hi) continue;
+      if (muf > screen_lo) {
+        const double rC = dist(C);
+        const double Rinv = rab_inv[(size_t)C * natoms + imin];
+        // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
+        const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
+        if (mu >= magic_ssf) continue;  // P_C == 0
+      }
+    }
+    if (cnt < SSF_MAXC) {
+      s_cand[cnt++][i] = C;
+    } else {  // list full (rare): evaluate in place, same order of the sum
+      for (int j = 0; j < cnt; ++j) {
+        const int Cj = s_cand[j][i];
+        const double Pc = partition_function(Cj);
+        sum += Pc;
+        if (Cj == par) p_par = Pc;
+      }
+      cnt = 0;
+      s_cand[cnt++][i] = C;
+    }
+  }
+  for (int j = 0; j < cnt; ++j) {
+    const int C = s_cand[j][i];
+    const double Pc = partition_function(C);
     sum += Pc;
     if (C == par) p_par = Pc;
   }
