@@ -28,14 +28,14 @@
 // order (a reordering of exact factors 0 and 1 plus O(1e-16) rounding).  The host additionally
 // skips pairs whose two partials are both <= 1e-13; that only perturbs terms below 1e-13 of the sum.
 //
-// FP32 screen.  Of the pairs (C, B) the two loops visit, only a handful per point are "active"
-// (|mu_CB| < 0.64: a factor strictly between 0 and 1); all others contribute EXACTLY 1 (mu <= -0.64) or make
-// P_C EXACTLY 0 (mu >= 0.64).  Which of the three a pair is follows from a single-precision mu (distances
-// from FP32 atom coordinates, an FP32 copy of 1 / R_AB: ~8 FP32 instructions, no FP64 square root) whenever
-// that mu is farther than 2e-3 from +-0.64 -- three orders of magnitude more than its rounding error; only
-// the rest takes the FP64 path, with the operand order above.  The set of active factors and the order they
-// are multiplied in are unchanged, so the weights are bit-identical to the all-FP64 kernel; the FP64 work per
-// point drops from O(near atoms^2) to O(active pairs).
+// Measured and dropped (round 2, profiles/r02_ssf_ncu.txt): ncu shows 6.5 active threads per instruction --
+// for a given candidate C only the ~15-20 % of a warp's points that keep C enter the pair loop.  (1) An FP32
+// screen of mu (exactly-0 / exactly-1 factors decided in single precision, FP64 only for the active pairs,
+// bit-identical weights) changed nothing (ubiquitin 1096 -> 1114 ms): 25-33 % of the visited pairs ARE active
+// and the loop is issue-bound, not FP64-bound.  (2) Per-lane candidate lists (every lane walks its OWN surviving
+// candidates, so all lanes sit in the pair loop together) were 5-7x SLOWER (ubiquitin 7.4 s, (H2O)833 32 s): a
+// candidate is competitive for all points of a tile or for none, so the shared-candidate loop is long for ~8
+// candidates per warp, the per-lane one for every list position; and 1 / R_CB becomes a 32-row gather.
 #include "kernels.cuh"
 
 namespace gxb {
@@ -43,8 +43,6 @@ namespace gxb {
 namespace {
 
 constexpr double magic_ssf = 0.64;
-constexpr float screen_lo = 0.64f - 2e-3f, screen_hi = 0.64f + 2e-3f;
-constexpr int SSF_MAXC = 40;  // surviving candidates kept per point before they are flushed (20 KB of shared memory)
 
 __device__ __forceinline__ double g_frisch(double mu) {
   const double s = mu * 1.5625;  // 1 / 0.64 (exactly representable; the host divides by 0.64)
@@ -54,9 +52,7 @@ __device__ __forceinline__ double g_frisch(double mu) {
 
 __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __restrict__ tiles,
                                                   const double* __restrict__ atoms,
-                                                  const float4* __restrict__ atoms_f,
                                                   const double* __restrict__ rab_inv,
-                                                  const float* __restrict__ rab_inv_f,
                                                   const double* __restrict__ dist_nearest,
                                                   const int* __restrict__ nbr_idx,
                                                   const double* __restrict__ nbr_dist,
@@ -67,7 +63,6 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   // anchor atom of the tile: nearest atom to the tile's first point
   __shared__ double s_best[TP / 32];
   __shared__ int s_arg[TP / 32];
-  __shared__ int s_cand[SSF_MAXC][TP];  // per lane: surviving candidates (column = thread: conflict-free)
   int anchor;
   {
     const double ax = pv.px[tile.pt_off], ay = pv.py[tile.pt_off], az = pv.pz[tile.pt_off];
@@ -97,16 +92,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
   const int ip = tile.pt_off + i;
   const int par = pv.tasks[tile.task].iParent;
   const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];
-  const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
 
   auto dist = [&](int A) {
     const double dx = px - atoms[3 * A], dy = py - atoms[3 * A + 1], dz = pz - atoms[3 * A + 2];
     return sqrt(dx * dx + dy * dy + dz * dz);
-  };
-  auto dist_f = [&](int A) {
-    const float4 a = __ldg(atoms_f + A);
-    const float dx = pxf - a.x, dy = pyf - a.y, dz = pzf - a.z;
-    return sqrtf(dx * dx + dy * dy + dz * dz);
   };
 
   const double r_par = dist(par);
@@ -126,29 +115,26 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
     const double r = dist(A);
     if (r < rmin) { rmin = r; imin = A; }
   }
-  const float rminf = (float)rmin;
 
-  // P_C = prod_{B != C} s(mu_CB) for one candidate: neighbour order, FP32 screen, FP64 for the active pairs
-  auto partition_function = [&](int C) {
+  double sum = 0., p_par = 0.;
+  const double c_cut = kappa * rmin;
+  for (int kc = 0; kc < natoms; ++kc) {
+    if (nd[kc] - r_anc >= c_cut) break;  // every remaining C has P_C == 0
+    const int C = nb[kc];
     const double rC = dist(C);
-    const float4 cf = __ldg(atoms_f + C);
-    const float rCf = dist_f(C);
+    if (C != imin) {
+      const double Rinv = rab_inv[(size_t)C * natoms + imin];
+      // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
+      const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
+      if (mu >= magic_ssf) continue;  // P_C == 0
+    }
     double Pc = 1.;
     const double* __restrict__ rabC = rab_inv + (size_t)C * natoms;
-    const double b_lim = kappa * rC + r_anc;  // factors beyond R(anchor, B) >= b_lim are exactly 1
+    const double b_cut = kappa * rC;
     for (int kb = 0; kb < natoms; ++kb) {
-      if (nd[kb] >= b_lim) break;
+      if (nd[kb] - r_anc >= b_cut) break;  // every remaining factor is exactly 1
       const int Bq = nb[kb];
       if (Bq == C) continue;
-      // FP32 screen: mu_CB = (r_C - r_B) / R_CB, everything from FP32 coordinates (no table gather: the lanes of
-      // a warp work on different C)
-      const float4 bf = __ldg(atoms_f + Bq);
-      const float bx = pxf - bf.x, by = pyf - bf.y, bz = pzf - bf.z;
-      const float cx = cf.x - bf.x, cy = cf.y - bf.y, cz = cf.z - bf.z;
-      const float muf = (rCf - sqrtf(bx * bx + by * by + bz * bz)) * rsqrtf(cx * cx + cy * cy + cz * cz);
-      if (muf <= -screen_hi) continue;              // factor exactly 1
-      if (muf >= screen_hi) { Pc = 0.; break; }     // factor exactly 0
-      // FP64 path, host operand order
       const double rB = dist(Bq);
       const double Rinv = rabC[Bq];
       if (Bq < C) {
@@ -164,47 +150,6 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
         Pc *= 1. - gq;
       }
     }
-    return Pc;
-  };
-
-  // Pass 1 (cheap, per lane): the candidates C that the nearest atom does not already zero.  Pass 2 walks each
-  // lane's OWN list, so all lanes of a warp sit in the pair loop together -- with one shared candidate index
-  // per warp iteration only ~6 of 32 lanes had work (ncu: 6.5 active threads per instruction), because each
-  // point keeps a different ~15 % of the candidates.
-  double sum = 0., p_par = 0.;
-  int cnt = 0;
-  const double c_lim = kappa * rmin + r_anc;  // candidates: R(anchor, C) < c_lim
-  for (int kc = 0; kc < natoms; ++kc) {
-    if (nd[kc] >= c_lim) break;  // every remaining C has P_C == 0
-    const int C = nb[kc];
-    if (C != imin) {
-      // mu(C, nearest) >= 0.64  =>  P_C == 0: decided in FP32 unless too close to the threshold
-      const float muf = (dist_f(C) - rminf) * __ldg(rab_inv_f + (size_t)C * natoms + imin);
-      if (muf >= screen_hi) continue;
-      if (muf > screen_lo) {
-        const double rC = dist(C);
-        const double Rinv = rab_inv[(size_t)C * natoms + imin];
-        // host evaluates this pair as (iA,jA) = (max,min); mu is exactly antisymmetric
-        const double mu = (C > imin) ? (rC - rmin) * Rinv : -((rmin - rC) * Rinv);
-        if (mu >= magic_ssf) continue;  // P_C == 0
-      }
-    }
-    if (cnt < SSF_MAXC) {
-      s_cand[cnt++][i] = C;
-    } else {  // list full (rare): evaluate in place, same order of the sum
-      for (int j = 0; j < cnt; ++j) {
-        const int Cj = s_cand[j][i];
-        const double Pc = partition_function(Cj);
-        sum += Pc;
-        if (Cj == par) p_par = Pc;
-      }
-      cnt = 0;
-      s_cand[cnt++][i] = C;
-    }
-  }
-  for (int j = 0; j < cnt; ++j) {
-    const int C = s_cand[j][i];
-    const double Pc = partition_function(C);
     sum += Pc;
     if (C == par) p_par = Pc;
   }
@@ -214,12 +159,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
 }  // namespace
 
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const float* atoms_f4, const double* rab_inv, const float* rab_inv_f,
-                        const double* dist_nearest, const int* nbr_idx, const double* nbr_dist, int natoms,
-                        cudaStream_t s) {
+                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
+                        const double* nbr_dist, int natoms, cudaStream_t s) {
   if (ntiles <= 0) return;
-  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, reinterpret_cast<const float4*>(atoms_f4), rab_inv, rab_inv_f,
-                                   dist_nearest, nbr_idx, nbr_dist, natoms);
+  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab_inv, dist_nearest, nbr_idx, nbr_dist, natoms);
 }
 
 }  // namespace gxb

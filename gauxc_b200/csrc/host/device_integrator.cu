@@ -103,7 +103,6 @@ struct DevicePlan {
   DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
   DevBuf<double> d_px, d_py, d_pz, d_w;
   DevBuf<double> d_atoms, d_rab, d_dist_nearest, d_nbr_dist;
-  DevBuf<float> d_atoms_f4, d_rab_f;  // FP32 copies for the SSF screen
   DevBuf<int> d_nbr_idx;  // per atom: all atoms sorted by distance from it (SSF loop cut-offs)
   double f_dense = 0., sum_nbe_npts = 0.;
   std::map<int, std::shared_ptr<Schedule>> schedules;  // key: nmat
@@ -285,13 +284,6 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
     std::vector<double> rab_inv(meta.rab.size());
     for (size_t q = 0; q < rab_inv.size(); ++q) rab_inv[q] = meta.rab[q] > 0. ? 1. / meta.rab[q] : 0.;
     plan->d_rab.upload(rab_inv);
-    std::vector<float> rab_inv_f(rab_inv.begin(), rab_inv.end());
-    plan->d_rab_f.upload(rab_inv_f);
-    std::vector<float> atoms_f4(4 * mol.size(), 0.f);
-    for (size_t a = 0; a < mol.size(); ++a) {
-      atoms_f4[4 * a] = (float)mol[a].x; atoms_f4[4 * a + 1] = (float)mol[a].y; atoms_f4[4 * a + 2] = (float)mol[a].z;
-    }
-    plan->d_atoms_f4.upload(atoms_f4);
   }
   plan->d_dist_nearest.upload(meta.dist_nearest);
   {
@@ -610,8 +602,8 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, 0));
   gxb::launch_ssf_weights(plan->view(), plan->d_tiles.p, (int)plan->tiles.size(), plan->d_atoms.p,
-                          plan->d_atoms_f4.p, plan->d_rab.p, plan->d_rab_f.p, plan->d_dist_nearest.p,
-                          plan->d_nbr_idx.p, plan->d_nbr_dist.p, plan->natoms, 0);
+                          plan->d_rab.p, plan->d_dist_nearest.p, plan->d_nbr_idx.p, plan->d_nbr_dist.p,
+                          plan->natoms, 0);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(e1, 0));
   CUDA_CHECK(cudaEventSynchronize(e1));
