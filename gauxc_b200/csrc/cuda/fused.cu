@@ -608,6 +608,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     int s = 0;
     uint32_t ph = 0;
     if (pw == 0 && lane < 4) tma_prefetch_desc(&tmaps.m[lane]);
+    int popped = -2;  // lane 0 of warp 0: the NEXT tile, popped one tile ahead (-2: nothing popped yet)
     for (int it = 0;; ++it) {
       int tile_idx;
       if (pw == 0) {
@@ -615,10 +616,15 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         mbar_wait(&S.tqempty[slot], ((it / TQ) & 1) ^ 1);
         tile_idx = -1;
         if (lane == 0) {
-          tile_idx = atomicAdd(counter, 1);
+          tile_idx = popped == -2 ? atomicAdd(counter, 1) : popped;
           if (tile_idx >= ntiles) tile_idx = -1;
           S.tq[slot] = tile_idx;
           mbar_arrive(&S.tqfull[slot]);
+          // pop the next tile now: the atomic's round trip and the tile record's first touch then overlap this
+          // tile's loads instead of opening the next tile (the producer's lead over the MMA warps is only the
+          // 5-stage ring)
+          popped = tile_idx >= 0 ? atomicAdd(counter, 1) : -1;
+          if (popped >= 0 && popped < ntiles) prefetch_l2(tiles + popped);
         }
         tile_idx = __shfl_sync(0xffffffffu, tile_idx, 0);
       } else {

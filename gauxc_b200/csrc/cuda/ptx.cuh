@@ -111,6 +111,10 @@ __device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 // ---- L2 eviction-priority hints -------------------------------------------------------------------
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;

@@ -302,7 +302,7 @@ GauXCLoadBalancer gauxc_load_balancer_factory_get_instance(GauXCStatus* status,
   GauXCLoadBalancer lb{{GauXC_Type_LoadBalancer}, nullptr};
   C_TRY(status)
   auto* f = checked<LBFactory>(factory.ptr, factory.hdr, GauXC_Type_LoadBalancerFactory, "LoadBalancerFactory");
-  lb.ptr = new LBPtr(std::make_shared<LoadBalancer>(*RT(env), *MOL(mol), *MG(mg), *BAS(basis), f->kernel));
+  lb.ptr = new LBPtr(std::make_shared<LoadBalancer>(*RT(env), *MOL(mol), *MG(mg), *BAS(basis), f->kernel, f->ex));
   C_CATCH(status)
   return lb;
 }

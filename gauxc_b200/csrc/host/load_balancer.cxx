@@ -1,9 +1,11 @@
 #include "load_balancer.hpp"
+#include "../cuda/lb_screen.hpp"
 #include <algorithm>
 #include <cmath>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <numeric>
 
 namespace GauXC {
@@ -21,7 +23,7 @@ bool cube_sphere_intersect(const double* lo, const double* up, const double* cen
 }
 
 LoadBalancer::LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecule& mol,
-                           const MolGrid& mg, const BasisSet& basis, const std::string& kernel)
+                           const MolGrid& mg, const BasisSet& basis, const std::string& kernel, ExecutionSpace ex)
     : runtime_(std::move(rt)),
       mol_(std::make_shared<Molecule>(mol)),
       mg_(std::make_shared<MolGrid>(mg)),
@@ -29,6 +31,8 @@ LoadBalancer::LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecul
       molmeta_(std::make_shared<MolMeta>(mol)),
       basis_map_(std::make_shared<BasisSetMap>(basis, mol)) {
   // src/load_balancer/host/load_balancer_host_factory.cxx:28-40
+  // the fill-in variant changes nbe (hence the deal over the ranks) after the screening: it keeps the host path
+  device_screen_ = ex == ExecutionSpace::Device && kernel != "REPLICATED-FILLIN";
   if (kernel == "REPLICATED-FILLIN") fill_in_ = true;
   else if (kernel != "DEFAULT" && kernel != "REPLICATED" && kernel != "REPLICATED-PETITE")
     GAUXC_GENERIC_EXCEPTION("LoadBalancer Kernel Not Recognized: " + kernel);
@@ -130,6 +134,79 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     cells[((size_t)cell_of(mol[c].x, 0) * ncell[1] + cell_of(mol[c].y, 1)) * ncell[2] + cell_of(mol[c].z, 2)]
         .push_back((int32_t)c);
 
+  // ---- ExecutionSpace::Device: the box/sphere tests and the shell-list compaction run on the GPU
+  //      (cuda/lb_screen.cu; reference: replicated_cuda_load_balancer.cxx:71-323); the deal over the ranks, the
+  //      sort and the merge below are shared with the Host path, so both produce the same task list bit for bit.
+  std::vector<long long> dev_off;       // per atom: first pair; per pair: offset into dev_lists
+  std::vector<long long> dev_atom_first(natoms + 1, 0);
+  std::vector<int> dev_nshell, dev_nbe, dev_lists;
+  if (device_screen_) {
+    const double t_a = tnow();
+    gxb::LbScreenInput in;
+    std::map<int64_t, int> box_first;  // grid type -> first box
+    for (size_t a = 0; a < natoms; ++a) {
+      in.atoms.insert(in.atoms.end(), {mol[a].x, mol[a].y, mol[a].z});
+      const Grid& grid = mg_->get_grid(mol[a].Z);
+      if (!box_first.count(mol[a].Z)) {
+        box_first[mol[a].Z] = (int)(in.box_lo.size() / 3);
+        for (size_t ib = 0; ib < grid.nbatches(); ++ib) {
+          const auto& gb = grid.batch(ib);
+          in.box_lo.insert(in.box_lo.end(), gb.lo.begin(), gb.lo.end());
+          in.box_up.insert(in.box_up.end(), gb.up.begin(), gb.up.end());
+        }
+      }
+      dev_atom_first[a] = (long long)in.pair_atom.size();
+      const int b0 = box_first[mol[a].Z];
+      for (size_t ib = 0; ib < grid.nbatches(); ++ib) {
+        in.pair_atom.push_back((int)a);
+        in.pair_box.push_back(b0 + (int)ib);
+      }
+    }
+    dev_atom_first[natoms] = (long long)in.pair_atom.size();
+    for (size_t sidx = 0; sidx < nsh; ++sidx) {
+      in.shell_xyz.insert(in.shell_xyz.end(), basis[sidx].O.begin(), basis[sidx].O.end());
+      in.shell_rad.push_back(basis[sidx].cutoff_radius);
+      in.shell_size.push_back(basis[sidx].size());
+    }
+    std::unique_ptr<gxb::LbScreen> scr_p;
+    try {
+      scr_p.reset(new gxb::LbScreen(in));
+    } catch (const std::exception& e) {
+      GAUXC_GENERIC_EXCEPTION(std::string("No CUDA device: the Device LoadBalancer has no CPU fallback in this build (") +
+                              e.what() + ")");
+    }
+    gxb::LbScreen& scr = *scr_p;
+    scr.count(dev_nshell, dev_nbe);
+    // the greedy deal below needs nbe of EVERY batch but the shell lists only of this rank's: replay the deal
+    // on the counts to find them
+    const size_t np = in.pair_atom.size();
+    std::vector<unsigned char> want(np, 0);
+    {
+      std::vector<size_t> wl(world_size, 0);
+      for (size_t a = 0; a < natoms; ++a) {
+        const Grid& grid = mg_->get_grid(mol[a].Z);
+        for (size_t ib = 0; ib < grid.nbatches(); ++ib) {
+          const size_t p = (size_t)dev_atom_first[a] + ib;
+          if (grid.batch(ib).points.empty() || dev_nshell[p] == 0) continue;
+          auto min_it = std::min_element(wl.begin(), wl.end());
+          XCTask probe;
+          probe.npts = (int32_t)grid.batch(ib).points.size();
+          probe.bfn_screening.nbe = dev_nbe[p];
+          *min_it += probe.cost(n_deriv, natoms);
+          if ((int32_t)std::distance(wl.begin(), min_it) == world_rank) want[p] = 1;
+        }
+      }
+    }
+    dev_off.assign(np, 0);
+    long long total = 0;
+    for (size_t p = 0; p < np; ++p) {
+      dev_off[p] = total;
+      if (want[p]) total += dev_nshell[p];
+    }
+    scr.fill(want, dev_off, total, dev_lists);
+    t_scr += tnow() - t_a;
+  }
+
   for (size_t iAtom = 0; iAtom < natoms; ++iAtom) {
     const auto& atom = mol[iAtom];
     const Grid& grid = mg_->get_grid(atom.Z);
@@ -142,6 +219,18 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     for (size_t ib = 0; ib < nb; ++ib) {
       const GridBatch& gb = grid.batch(ib);
       if (gb.points.empty()) continue;
+      if (device_screen_) {
+        // lists of batches dealt to other ranks were not fetched: those tasks only carry their cost
+        const size_t p = (size_t)dev_atom_first[iAtom] + ib;
+        if (dev_nshell[p] == 0) continue;
+        XCTask& task = temp[ib];
+        task.iParent = (int32_t)iAtom;
+        task.npts = (int32_t)gb.points.size();
+        task.bfn_screening.nbe = dev_nbe[p];
+        task.dist_nearest = molmeta_->dist_nearest[iAtom];
+        keep[ib] = 2;  // points / weights / shell list are filled in after the deal, for local batches only
+        continue;
+      }
       const double lo[3] = {gb.lo[0] + atom.x, gb.lo[1] + atom.y, gb.lo[2] + atom.z};
       const double up[3] = {gb.up[0] + atom.x, gb.up[1] + atom.y, gb.up[2] + atom.z};
 
@@ -205,7 +294,19 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       auto min_it = std::min_element(global_workload.begin(), global_workload.end());
       const int64_t min_rank = std::distance(global_workload.begin(), min_it);
       global_workload[min_rank] += temp[ib].cost(n_deriv, natoms);
-      if (world_rank == min_rank) local_work.push_back(std::move(temp[ib]));
+      if (world_rank == min_rank) {
+        if (keep[ib] == 2) {  // device screening: materialise the local task now
+          const GridBatch& gb = grid.batch(ib);
+          const size_t p = (size_t)dev_atom_first[iAtom] + ib;
+          XCTask& task = temp[ib];
+          task.points.resize(gb.points.size());
+          for (size_t i = 0; i < gb.points.size(); ++i)
+            task.points[i] = {gb.points[i][0] + atom.x, gb.points[i][1] + atom.y, gb.points[i][2] + atom.z};
+          task.weights = gb.weights;
+          task.bfn_screening.shell_list.assign(dev_lists.begin() + dev_off[p], dev_lists.begin() + dev_off[p] + dev_nshell[p]);
+        }
+        local_work.push_back(std::move(temp[ib]));
+      }
     }
     t_deal += tnow() - t_b;
   }

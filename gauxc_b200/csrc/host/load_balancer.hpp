@@ -63,7 +63,8 @@ class LoadBalancer {
 
   // pending refresh of host-side task data that currently lives on the device (SSF weights)
   std::function<void(std::vector<XCTask>&)> host_sync_;
-  bool fill_in_ = false;  // REPLICATED-FILLIN: contiguous shell range first..last instead of the exact list
+  bool fill_in_ = false;
+  bool device_screen_ = false;  // ExecutionSpace::Device: shell screening on the GPU (cuda/lb_screen.cu)  // REPLICATED-FILLIN: contiguous shell range first..last instead of the exact list
 
   std::vector<XCTask> create_local_tasks_() const;
 
@@ -71,7 +72,8 @@ public:
   // kernel: "DEFAULT" / "REPLICATED" / "REPLICATED-PETITE" (exact shell lists,
   // petite_replicated_load_balancer.cxx:31-65) or "REPLICATED-FILLIN" (fillin_replicated_load_balancer.cxx)
   LoadBalancer(std::shared_ptr<RuntimeEnvironment> rt, const Molecule& mol, const MolGrid& mg,
-               const BasisSet& basis, const std::string& kernel = "DEFAULT");
+               const BasisSet& basis, const std::string& kernel = "DEFAULT",
+               ExecutionSpace ex = ExecutionSpace::Host);
 
   std::vector<XCTask>& get_tasks();
   // install a user supplied task list without generating the default one first

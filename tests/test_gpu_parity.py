@@ -374,6 +374,26 @@ def test_uks_gga_golden_and_oracle(orc, func):
     assert abs(exc0 - exc_r) <= 1e-10 and np.abs(vs0 - vxc_r).max() <= 1e-10 and np.abs(vz0).max() <= 1e-12
 
 
+@pytest.mark.parametrize("workload,grid,size", [("benzene", "UltraFineGrid", 1), ("taxol", "FineGrid", 1),
+                                                ("taxol", "FineGrid", 3)])
+def test_device_load_balancer_is_bit_identical_to_host(workload, grid, size):
+    """LoadBalancerFactory(ExecutionSpace::Device): box/sphere screening and shell-list compaction on the GPU
+    (cuda/lb_screen.cu; reference replicated_cuda_load_balancer.cxx:71-323) must give the host LoadBalancer's task
+    list exactly -- iParent, npts, shell lists, nbe, points, weights -- on every rank (integer / index work: bit-exact,
+    the reference's own criterion in tests/load_balancer_test.cxx:86-157)."""
+    atoms = systems.geometry(workload) if workload != "benzene" else systems.golden_system("benzene_pbe0_cc-pvdz_ufg_ssf")[0]
+    shells = systems.make_basis_shells(atoms, "cc-pvdz" if workload == "benzene" else "def2-svp", tol=1e-10)
+    mol, basis = gx.Molecule(atoms), gx.BasisSet(shells)
+    mg = gx.MolGrid(mol, "Unpruned", 512, "MuraKnowles", grid)
+    for rank in range(size):
+        rt = gx.RuntimeEnvironment(rank=rank, size=size, device=True)
+        th = gx.LoadBalancerFactory("Host", "Replicated").get_instance(rt, mol, mg, basis).export_tasks()
+        td = gx.LoadBalancerFactory("Device", "Replicated").get_instance(rt, mol, mg, basis).export_tasks()
+        assert len(th["npts"]) > 10
+        for k in ("npts", "iParent", "nshells", "nbe", "shell_lists", "points", "weights", "dist_nearest"):
+            assert np.array_equal(th[k], td[k]), (k, rank)
+
+
 def test_empty_task_list_gives_zero():
     atoms = systems.geometry("water")
     shells = systems.make_basis_shells(atoms, "cc-pvdz")
