@@ -140,6 +140,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
   std::vector<long long> dev_off;       // per atom: first pair; per pair: offset into dev_lists
   std::vector<long long> dev_atom_first(natoms + 1, 0);
   std::vector<int> dev_nshell, dev_nbe, dev_lists;
+  std::vector<unsigned char> want;
   if (device_screen_) {
     const double t_a = tnow();
     gxb::LbScreenInput in;
@@ -180,7 +181,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     // the greedy deal below needs nbe of EVERY batch but the shell lists only of this rank's: replay the deal
     // on the counts to find them
     const size_t np = in.pair_atom.size();
-    std::vector<unsigned char> want(np, 0);
+    want.assign(np, 0);
     {
       std::vector<size_t> wl(world_size, 0);
       for (size_t a = 0; a < natoms; ++a) {
@@ -228,7 +229,15 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
         task.npts = (int32_t)gb.points.size();
         task.bfn_screening.nbe = dev_nbe[p];
         task.dist_nearest = molmeta_->dist_nearest[iAtom];
-        keep[ib] = 2;  // points / weights / shell list are filled in after the deal, for local batches only
+        keep[ib] = 1;
+        if (want[p]) {  // this rank's batch (the deal was replayed on the counts): materialise it
+          task.points.resize(gb.points.size());
+          for (size_t i = 0; i < gb.points.size(); ++i)
+            task.points[i] = {gb.points[i][0] + atom.x, gb.points[i][1] + atom.y, gb.points[i][2] + atom.z};
+          task.weights = gb.weights;
+          task.bfn_screening.shell_list.assign(dev_lists.begin() + dev_off[p],
+                                               dev_lists.begin() + dev_off[p] + dev_nshell[p]);
+        }
         continue;
       }
       const double lo[3] = {gb.lo[0] + atom.x, gb.lo[1] + atom.y, gb.lo[2] + atom.z};
@@ -295,16 +304,8 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       const int64_t min_rank = std::distance(global_workload.begin(), min_it);
       global_workload[min_rank] += temp[ib].cost(n_deriv, natoms);
       if (world_rank == min_rank) {
-        if (keep[ib] == 2) {  // device screening: materialise the local task now
-          const GridBatch& gb = grid.batch(ib);
-          const size_t p = (size_t)dev_atom_first[iAtom] + ib;
-          XCTask& task = temp[ib];
-          task.points.resize(gb.points.size());
-          for (size_t i = 0; i < gb.points.size(); ++i)
-            task.points[i] = {gb.points[i][0] + atom.x, gb.points[i][1] + atom.y, gb.points[i][2] + atom.z};
-          task.weights = gb.weights;
-          task.bfn_screening.shell_list.assign(dev_lists.begin() + dev_off[p], dev_lists.begin() + dev_off[p] + dev_nshell[p]);
-        }
+        if (device_screen_ && !want[(size_t)dev_atom_first[iAtom] + ib])
+          GAUXC_GENERIC_EXCEPTION("Device LoadBalancer: replayed deal disagrees with the deal");
         local_work.push_back(std::move(temp[ib]));
       }
     }

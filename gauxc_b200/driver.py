@@ -70,7 +70,9 @@ class System:
         self.nbf = self.basis.nbf()
         self.mg = gx.MolGrid(self.mol, pruning, batch, "MuraKnowles", self.grid)
         self.rt = gx.RuntimeEnvironment(rank=rank, size=size, device=device)
-        self.lb = gx.LoadBalancerFactory("Host", "Replicated").get_instance(self.rt, self.mol, self.mg, self.basis)
+        # Device execution space: shell screening on the GPU (bit-identical task list, tests/test_gpu_parity.py)
+        self.lb = gx.LoadBalancerFactory("Device" if device else "Host", "Replicated") \
+            .get_instance(self.rt, self.mol, self.mg, self.basis)
         self.npts_local = self.lb.total_npts()
         self.t_setup = time.time() - t0
         if P is not None:
