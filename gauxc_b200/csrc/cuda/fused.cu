@@ -35,6 +35,23 @@
 #ifndef GXB_KNOCKOUT
 #define GXB_KNOCKOUT 0
 #endif
+// stages of B^T prefetched into L2 ahead of the ring on the first pass over a tile's rows (0: none)
+#ifndef GXB_FPF
+#define GXB_FPF 0
+#endif
+// GXB_TIMING (diagnostic builds): MMA warp 0 of CTA 0 accumulates the clocks it spends waiting on each barrier
+// and prints them when the launch ends
+#ifndef GXB_TIMING
+#define GXB_TIMING 0
+#endif
+#if GXB_TIMING
+#include <cstdio>
+#define GXB_T0() const long long _t0 = clock64()
+#define GXB_T1(acc) acc += clock64() - _t0
+#else
+#define GXB_T0()
+#define GXB_T1(acc)
+#endif
 
 namespace gxb {
 
@@ -183,9 +200,13 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     // a0 ^ (mi << 3), i.e. a0 + 8*mi for even mi and (a0 ^ 8) + 8*(mi - 1) for odd mi
     const int a_ev_full = (wm * 64 + g) ^ (t << 2), a_ev_short = g ^ (t << 2);
 
+    long long w_tq = 0, w_full = 0, w_full_first = 0, w_xempty = 0, w_store = 0, n_stage = 0, n_tile = 0;
+    const long long t_begin = clock64();
     for (int it = 0;; ++it) {
-      const int tile_idx = next_tile(it);
+      int tile_idx;
+      { GXB_T0(); tile_idx = next_tile(it); GXB_T1(w_tq); }
       if (tile_idx < 0) break;
+      ++n_tile;
       const DevTile tile = tiles[tile_idx];
       const int nbe = tile.nbe;
       const int nk = pad16(nbe) / FK;
@@ -212,7 +233,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
           for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
 
         for (int ks = 0; ks < nkc; ++ks) {
-          mbar_wait(&S.full[s], ph);
+          { GXB_T0(); mbar_wait(&S.full[s], ph); if (ks < FSTAGES) { GXB_T1(w_full_first); } else { GXB_T1(w_full); } }
+          ++n_stage;
           const double* as = &S.A[s][0][0] + t * ap;
           const double* ps = &S.P[s][t][wn * 16 + g];
           if (active) {
@@ -274,7 +296,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
           if (++s == FSTAGES) { s = 0; ph ^= 1; }
         }
         // hand the chunk of X to the density warps
-        mbar_wait(&S.xempty, xph ^ 1);
+        { GXB_T0(); mbar_wait(&S.xempty, xph ^ 1); GXB_T1(w_xempty); }
+        GXB_T0();
         if (!split) {
 #pragma unroll
           for (int mi = 0; mi < 8; ++mi)
@@ -305,8 +328,20 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         }
         mbar_arrive(&S.xfull);
         xph ^= 1;
+        GXB_T1(w_store);
       }
     }
+#if GXB_TIMING
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) {
+      const double tot = (double)(clock64() - t_begin);
+      printf("[fused timing] tiles %lld stages %lld total %.0f clk: wait tile-queue %.1f%% full(first 5 stages of a chunk) %.1f%% "
+             "full(later) %.1f%% xempty %.1f%% X hand-over %.1f%%; per stage %.0f clk\n",
+             n_tile, n_stage, tot, 100. * w_tq / tot, 100. * w_full_first / tot, 100. * w_full / tot, 100. * w_xempty / tot,
+             100. * w_store / tot, tot / (double)(n_stage ? n_stage : 1));
+    }
+#else
+    (void)w_tq; (void)w_full; (void)w_full_first; (void)w_xempty; (void)w_store; (void)n_stage; (void)n_tile; (void)t_begin;
+#endif
   } else if (warp < MMA_WARPS + DEN_WARPS) {
     // ------------------------------------------------------------------ density warps
     reg_inc<DEN_REGS>();
@@ -655,6 +690,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
             const int kn = k0 + FK + kl;
             ao_next = (ks + 1 < nkc && kn < nbe) ? __ldg(ao + kn) : -1;
           }
+          // first pass over the rows of B (chunk 0): they come from HBM, several ring depths of latency away --
+          // pull the box of a later stage into L2 now (TMA prefetch: no shared memory, no completion)
+          if (GXB_FPF > 0 && pw == 0 && lane == 0 && c == 0 && ks + GXB_FPF < nkc)
+            tma_prefetch_2d(&tmaps.m[W / 32 - 1], 0, rowB + k0 + GXB_FPF * FK);
           mbar_wait(&S.empty[s], ph ^ 1);
           if (pw == 0) {
             // B^T: ONE tensor copy of 16 rows x the W columns the tile owns (one descriptor per
