@@ -597,6 +597,87 @@ void collocation(const Basis& B, int nsh, const int32_t* shell_list, int npts, c
   }
 }
 
+
+// values, gradient and Hessian (xx,xy,xz,yy,yz,zz) of one shell at one point: the semantics of gau2grid
+// gg_collocation_deriv2 as called by gau2grid_collocation_hessian
+// (local_work_driver/host/reference/gau2grid_collocation.cxx:118-163).  phi = f(x,y,z) S(r^2):
+//   d_i phi  = f_i S0 + f x_i S1
+//   d_ij phi = f_ij S0 + (f_i x_j + f_j x_i + f delta_ij) S1 + f x_i x_j S2,
+// S0 = sum c e, S1 = sum -2 a c e, S2 = sum 4 a^2 c e.
+void shell_at_point_d2(const Basis& B, int s, const double* p, double* out[10]) {
+  const double r[3] = {p[0] - B.origin[3 * s], p[1] - B.origin[3 * s + 1], p[2] - B.origin[3 * s + 2]};
+  const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  double S0 = 0, S1 = 0, S2 = 0;
+  for (int k = 0; k < B.nprim[s]; ++k) {
+    const double a = B.alpha[32 * s + k];
+    const double e = B.coeff[32 * s + k] * std::exp(-a * r2);
+    S0 += e;
+    S1 += -2. * a * e;
+    S2 += 4. * a * a * e;
+  }
+  const int l = B.l[s];
+  auto mono = [&](int a, int b, int c, double* o) {
+    const int n[3] = {a, b, c};
+    auto fpow = [&](int da, int db, int dc) {  // monomial with exponents lowered by (da, db, dc), times the falling factors
+      const int e[3] = {n[0] - da, n[1] - db, n[2] - dc};
+      if (e[0] < 0 || e[1] < 0 || e[2] < 0) return 0.;
+      double pre = 1.;
+      const int d[3] = {da, db, dc};
+      for (int q = 0; q < 3; ++q)
+        for (int k = 0; k < d[q]; ++k) pre *= double(n[q] - k);
+      return pre * ipow(r[0], e[0]) * ipow(r[1], e[1]) * ipow(r[2], e[2]);
+    };
+    const double f = fpow(0, 0, 0);
+    const double f1[3] = {fpow(1, 0, 0), fpow(0, 1, 0), fpow(0, 0, 1)};
+    o[0] = f * S0;
+    for (int i = 0; i < 3; ++i) o[1 + i] = f1[i] * S0 + f * r[i] * S1;
+    int q = 4;
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j, ++q) {
+        int d[3] = {0, 0, 0};
+        d[i] += 1; d[j] += 1;
+        const double f2 = fpow(d[0], d[1], d[2]);
+        o[q] = f2 * S0 + (f1[i] * r[j] + f1[j] * r[i] + (i == j ? f : 0.)) * S1 + f * r[i] * r[j] * S2;
+      }
+  };
+  if (!B.pure[s]) {
+    int c = 0;
+    for (int a = l; a >= 0; --a)
+      for (int b = l - a; b >= 0; --b, ++c) {
+        double o[10];
+        mono(a, b, l - a - b, o);
+        for (int q = 0; q < 10; ++q) out[q][c] = o[q];
+      }
+  } else {
+    if (l > 4) { std::fprintf(stderr, "oracle: pure l>4 unsupported\n"); std::abort(); }
+    const auto& T = sph_table(l);
+    for (int m = 0; m < 2 * l + 1; ++m) {
+      double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (auto& t : T[m]) {
+        double o[10];
+        mono(t.a, t.b, t.c, o);
+        for (int q = 0; q < 10; ++q) acc[q] += t.f * o[q];
+      }
+      for (int q = 0; q < 10; ++q) out[q][m] = acc[q];
+    }
+  }
+}
+
+// mats[q] + mu + ipt*nbe, q = value, x, y, z, xx, xy, xz, yy, yz, zz
+void collocation_d2(const Basis& B, int nsh, const int32_t* shell_list, int npts, const double* pts, int nbe,
+                    double* const mats[10]) {
+  for (int i = 0; i < npts; ++i) {
+    int off = 0;
+    for (int q = 0; q < nsh; ++q) {
+      const int s = shell_list[q];
+      double* o[10];
+      for (int k = 0; k < 10; ++k) o[k] = mats[k] + (size_t)i * nbe + off;
+      shell_at_point_d2(B, s, pts + 3 * i, o);
+      off += B.size(s);
+    }
+  }
+}
+
 // Neumaier sum
 struct Acc {
   double s = 0, c = 0;
@@ -1092,6 +1173,249 @@ void oracle_functional_pol_lda(int nkern, const int* kern, const double* coeff, 
   f.nkern = nkern; f.is_gga = 0;
   for (int k = 0; k < nkern; ++k) { f.kern[k] = kern[k]; f.coeff[k] = coeff[k]; }
   eval_func_pol_lda(f, npts, rho2, eps, vrho2);
+}
+
+
+void oracle_collocation_d2(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                           const double* alpha, const double* coeff, const double* origin, int nsh,
+                           const int32_t* shell_list, int npts, const double* pts, double* out10) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  int nbe = 0;
+  for (int q = 0; q < nsh; ++q) nbe += B.size(shell_list[q]);
+  double* mats[10];
+  for (int k = 0; k < 10; ++k) mats[k] = out10 + (size_t)k * nbe * npts;
+  collocation_d2(B, nsh, shell_list, npts, pts, nbe, mats);
+}
+
+// reference_ssf_weights_1std_contraction_host (host/reference/weights.cxx:806-984): the SSF weight derivatives
+// contracted with w_times_f = w * eps * rho per point, accumulated into exc_grad_w[3*natoms].
+static void ssf_weights_1std_contraction(int natoms, const double* coords, const std::vector<double>& RAB,
+                                         int iParent, double dist_nearest, int npts, const double* points,
+                                         const double* w_times_f, double* exc_grad_w) {
+  const double magic = 0.64, weight_tol = 1e-13;
+  const double safe_magic_ssf_bound = magic - 1.e-4;
+  const double w_times_f_thresh = 1.e-12;
+  auto gFrisch = [&](double x) {
+    const double s_x = x / magic;
+    const double s_x2 = s_x * s_x, s_x3 = s_x * s_x2, s_x5 = s_x3 * s_x2, s_x7 = s_x5 * s_x2;
+    return (35. * (s_x - s_x3) + 21. * s_x5 - 5. * s_x7) / 16.;
+  };
+  auto tFrisch = [&](double x) {
+    const double s_x = x / magic;
+    const double s_x2 = s_x * s_x, s_x3 = s_x * s_x2;
+    const double numerator = 35. * (s_x3 + 3. * s_x2 + 3. * s_x + 1.);
+    const double denominator = (x - magic) * (5. * s_x3 + 20. * s_x2 + 29. * s_x + 16.);
+    return numerator / denominator;
+  };
+  std::vector<double> part(natoms), dist(natoms);
+  auto X = [&](int a, int k) { return coords[3 * a + k]; };
+  for (int i = 0; i < npts; ++i) {
+    const double wf = w_times_f[i];
+    if (std::fabs(wf) < w_times_f_thresh) continue;
+    const double* point = points + 3 * i;
+    const double dist_cutoff = 0.5 * (1 - magic) * dist_nearest;
+    {
+      const double dx = point[0] - X(iParent, 0), dy = point[1] - X(iParent, 1), dz = point[2] - X(iParent, 2);
+      dist[iParent] = std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    if (dist[iParent] < dist_cutoff) continue;
+    for (int iA = 0; iA < natoms; ++iA) {
+      if (iA == iParent) continue;
+      const double dx = point[0] - X(iA, 0), dy = point[1] - X(iA, 1), dz = point[2] - X(iA, 2);
+      dist[iA] = std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    std::fill(part.begin(), part.end(), 1.);
+    for (int iA = 0; iA < natoms; ++iA)
+      for (int jA = 0; jA < iA; ++jA)
+        if (part[iA] > weight_tol || part[jA] > weight_tol) {
+          const double mu = (dist[iA] - dist[jA]) / RAB[jA + (size_t)iA * natoms];
+          if (mu <= -magic) part[jA] = 0.;
+          else if (mu >= magic) part[iA] = 0.;
+          else {
+            const double g = 0.5 * (1. - gFrisch(mu));
+            part[iA] *= g;
+            part[jA] *= 1. - g;
+          }
+        }
+    double sum = 0.;
+    for (int iA = 0; iA < natoms; ++iA) sum += part[iA];
+    for (int iB = 0; iB < natoms; ++iB) {
+      if (iB == iParent) continue;
+      double gB[3] = {0., 0., 0.};
+      const double rAB = RAB[iB + (size_t)iParent * natoms];
+      const double rAB_inv = 1.0 / rAB;
+      const double mu_AB = (dist[iParent] - dist[iB]) * rAB_inv;
+      if (std::fabs(mu_AB) < safe_magic_ssf_bound) {
+        const double coef1 = tFrisch(mu_AB) / rAB * (part[iParent] - sum) / sum * wf / dist[iB];
+        for (int k = 0; k < 3; ++k) {
+          const double uB = X(iB, k) - point[k], uBA = X(iB, k) - X(iParent, k);
+          gB[k] = coef1 * (uB + mu_AB * uBA * rAB_inv * dist[iB]);
+        }
+      }
+      if (part[iB] > weight_tol) {
+        for (int iC = 0; iC < natoms; ++iC) {
+          if (iB == iC) continue;
+          const double rBC = RAB[iC + (size_t)iB * natoms];
+          const double mu_BC = (dist[iB] - dist[iC]) / rBC;
+          if (std::fabs(mu_BC) < safe_magic_ssf_bound) {
+            const double t_BC = tFrisch(mu_BC);
+            const double coef = part[iB] * t_BC / rBC / sum * wf;
+            for (int k = 0; k < 3; ++k)
+              gB[k] -= coef * ((X(iB, k) - point[k]) / dist[iB] - mu_BC * (X(iB, k) - X(iC, k)) / rBC);
+            if (iC != iParent) {
+              for (int k = 0; k < 3; ++k) {
+                const double Ck = coef * ((X(iC, k) - point[k]) / dist[iC] + mu_BC * (X(iC, k) - X(iB, k)) / rBC);
+#pragma omp atomic
+                exc_grad_w[3 * iC + k] += Ck;
+#pragma omp atomic
+                exc_grad_w[3 * iParent + k] -= Ck;
+              }
+            }
+          }
+        }
+      }
+      for (int k = 0; k < 3; ++k) {
+#pragma omp atomic
+        exc_grad_w[3 * iB + k] += gB[k];
+#pragma omp atomic
+        exc_grad_w[3 * iParent + k] -= gB[k];  // translational invariance
+      }
+    }
+  }
+}
+
+// The EXC gradient host driver for RKS LDA / GGA
+// (reference_replicated_xc_host_integrator_exc_grad.hpp:107-601 with is_rks): collocation gradient / Hessian,
+// X (and X_x, X_y, X_z for GGA) = 2 P_sub [B | dB], eval_uvvar_{lda,gga}_rks, functional, optional SSF weight
+// derivatives (w_times_f = eps * rho * w), per-shell accumulation g_acc -> EXC_GRAD[shell centre] += -2 g_acc;
+// with weight derivatives the shells on the task's parent atom are skipped and the parent receives +2 g_acc
+// (translational invariance).  P is the alpha density (ld = ldp).  out: EXC_GRAD[3*natoms].
+void oracle_exc_grad(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                     const double* alpha, const double* coeff, const double* origin, const int32_t* shell_to_center,
+                     int natoms, const double* coords, int nbf, const double* P, int ldp, int ntasks,
+                     const int32_t* task_npts, const int32_t* task_nshells, const int32_t* shell_lists,
+                     const int32_t* task_iparent, const double* task_dist_nearest, const double* points,
+                     const double* weights, int nkern, const int* kern, const double* kcoeff, int is_gga,
+                     int include_weight_derivatives, double* EXC_GRAD) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  Func func{};
+  func.nkern = nkern; func.is_gga = is_gga;
+  for (int k = 0; k < nkern; ++k) { func.kern[k] = kern[k]; func.coeff[k] = kcoeff[k]; }
+  std::vector<int> first_ao(nshells_total + 1, 0);
+  for (int s = 0; s < nshells_total; ++s) first_ao[s + 1] = first_ao[s] + B.size(s);
+  std::vector<size_t> poff(ntasks + 1, 0), soff(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) {
+    poff[t + 1] = poff[t] + task_npts[t];
+    soff[t + 1] = soff[t] + task_nshells[t];
+  }
+  std::vector<double> RAB((size_t)natoms * natoms, 0.);
+  for (int i = 0; i < natoms; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double dx = coords[3 * i] - coords[3 * j], dy = coords[3 * i + 1] - coords[3 * j + 1],
+                   dz = coords[3 * i + 2] - coords[3 * j + 2];
+      RAB[i + (size_t)j * natoms] = RAB[j + (size_t)i * natoms] = std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  for (int i = 0; i < 3 * natoms; ++i) EXC_GRAD[i] = 0.;
+  const int nmat = is_gga ? 10 : 4, nx = is_gga ? 4 : 1;
+
+#pragma omp parallel
+  {
+    std::vector<double> be, X, Psub, den, ddx, ddy, ddz, gam, eps, vrho, vgam;
+    std::vector<int> ao;
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; ++iT) {
+      const int npts = task_npts[iT];
+      const int nsh = task_nshells[iT];
+      const int32_t* sl = shell_lists + soff[iT];
+      const double* pts = points + 3 * poff[iT];
+      const double* w = weights + poff[iT];
+      const int iParent = task_iparent[iT];
+      ao.clear();
+      for (int q = 0; q < nsh; ++q)
+        for (int a = first_ao[sl[q]]; a < first_ao[sl[q] + 1]; ++a) ao.push_back(a);
+      const int nbe = (int)ao.size();
+      const size_t nn = (size_t)nbe * npts;
+      be.assign(nmat * nn, 0.);
+      X.resize(nx * nn);
+      Psub.resize((size_t)nbe * nbe);
+      den.resize(npts); eps.resize(npts); vrho.resize(npts); gam.assign(npts, 0.);
+      ddx.assign(npts, 0.); ddy.assign(npts, 0.); ddz.assign(npts, 0.); vgam.assign(npts, 0.);
+      double* mats[10];
+      for (int k = 0; k < 10; ++k) mats[k] = k < nmat ? be.data() + k * nn : nullptr;
+      if (is_gga) collocation_d2(B, nsh, sl, npts, pts, nbe, mats);
+      else collocation(B, nsh, sl, npts, pts, nbe, true, mats[0], mats[1], mats[2], mats[3]);
+      // eval_xmat over [B | dBx | dBy | dBz] (xmat_len * npts columns): X = 2 P_sub B
+      for (int j = 0; j < nbe; ++j)
+        for (int i = 0; i < nbe; ++i) Psub[i + (size_t)j * nbe] = P[ao[i] + (size_t)ao[j] * ldp];
+      gemm_nn(nbe, nx * npts, nbe, 2.0, Psub.data(), nbe, be.data(), nbe, X.data(), nbe);
+      const double *xN = X.data(), *xNx = X.data() + nn, *xNy = X.data() + 2 * nn, *xNz = X.data() + 3 * nn;
+      // eval_uvvar_{lda,gga}_rks
+      for (int i = 0; i < npts; ++i) {
+        const double* xi = xN + (size_t)i * nbe;
+        double d = 0;
+        for (int m = 0; m < nbe; ++m) d += mats[0][(size_t)i * nbe + m] * xi[m];
+        den[i] = d;
+        if (is_gga) {
+          double a = 0, b = 0, c = 0;
+          for (int m = 0; m < nbe; ++m) {
+            a += mats[1][(size_t)i * nbe + m] * xi[m];
+            b += mats[2][(size_t)i * nbe + m] * xi[m];
+            c += mats[3][(size_t)i * nbe + m] * xi[m];
+          }
+          ddx[i] = 2. * a; ddy[i] = 2. * b; ddz[i] = 2. * c;
+          gam[i] = ddx[i] * ddx[i] + ddy[i] * ddy[i] + ddz[i] * ddz[i];
+        }
+      }
+      eval_func(func, npts, den.data(), gam.data(), eps.data(), vrho.data(), is_gga ? vgam.data() : nullptr);
+      if (include_weight_derivatives) {
+        for (int i = 0; i < npts; ++i) eps[i] *= den[i] * w[i];
+        ssf_weights_1std_contraction(natoms, coords, RAB, iParent, task_dist_nearest[iT], npts, pts, eps.data(),
+                                     EXC_GRAD);
+      }
+      size_t bf_off = 0;
+      for (int ish = 0; ish < nsh; ++ish) {
+        const int sh_idx = sl[ish];
+        const int sh_sz = B.size(sh_idx);
+        const int iAt = shell_to_center[sh_idx];
+        if (iAt == iParent && include_weight_derivatives) { bf_off += sh_sz; continue; }
+        double g_acc_x = 0, g_acc_y = 0, g_acc_z = 0;
+        for (int ibf = 0, mu = (int)bf_off; ibf < sh_sz; ++ibf, ++mu)
+          for (int ipt = 0; ipt < npts; ++ipt) {
+            const size_t mu_i = mu + (size_t)ipt * nbe;
+            const double vrhop_ipt = w[ipt] * vrho[ipt];
+            const double xn = xN[mu_i];
+            const double dbx = mats[1][mu_i], dby = mats[2][mu_i], dbz = mats[3][mu_i];
+            g_acc_x += vrhop_ipt * xn * dbx;
+            g_acc_y += vrhop_ipt * xn * dby;
+            g_acc_z += vrhop_ipt * xn * dbz;
+            if (is_gga) {
+              const double vgammapp_ipt = w[ipt] * vgam[ipt];
+              const double ddenn_x = ddx[ipt], ddenn_y = ddy[ipt], ddenn_z = ddz[ipt];
+              const double xnx = xNx[mu_i], xny = xNy[mu_i], xnz = xNz[mu_i];
+              const double d2bxx = mats[4][mu_i], d2bxy = mats[5][mu_i], d2bxz = mats[6][mu_i],
+                           d2byy = mats[7][mu_i], d2byz = mats[8][mu_i], d2bzz = mats[9][mu_i];
+              const double d2_term_x = d2bxx * ddenn_x + d2bxy * ddenn_y + d2bxz * ddenn_z;
+              const double d2_term_y = d2bxy * ddenn_x + d2byy * ddenn_y + d2byz * ddenn_z;
+              const double d2_term_z = d2bxz * ddenn_x + d2byz * ddenn_y + d2bzz * ddenn_z;
+              const double d11_xmat_term = ddenn_x * xnx + ddenn_y * xny + ddenn_z * xnz;
+              g_acc_x += 2 * vgammapp_ipt * (xn * d2_term_x + dbx * d11_xmat_term);
+              g_acc_y += 2 * vgammapp_ipt * (xn * d2_term_y + dby * d11_xmat_term);
+              g_acc_z += 2 * vgammapp_ipt * (xn * d2_term_z + dbz * d11_xmat_term);
+            }
+          }
+        const double g[3] = {g_acc_x, g_acc_y, g_acc_z};
+        for (int k = 0; k < 3; ++k) {
+#pragma omp atomic
+          EXC_GRAD[3 * iAt + k] += -2 * g[k];
+          if (include_weight_derivatives) {
+#pragma omp atomic
+            EXC_GRAD[3 * iParent + k] -= -2 * g[k];
+          }
+        }
+        bf_off += sh_sz;
+      }
+    }
+  }
 }
 
 }  // extern "C"

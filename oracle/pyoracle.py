@@ -108,6 +108,40 @@ def collocation(flat_basis, shell_list, points, gradient=False):
     return (ev, dx, dy, dz) if gradient else ev
 
 
+def collocation_d2(flat_basis, shell_list, points):
+    """value, gradient (x, y, z) and Hessian (xx, xy, xz, yy, yz, zz): ten [npts][nbe] arrays."""
+    l, pure, nprim, alpha, coeff, origin = flat_basis
+    sl = np.ascontiguousarray(shell_list, np.int32)
+    pts = np.ascontiguousarray(points, np.float64)
+    nbe = int(sum((2 * l[s] + 1) if pure[s] else (l[s] + 1) * (l[s] + 2) // 2 for s in sl))
+    n = len(pts)
+    out = np.zeros((10, n, nbe))
+    lib().oracle_collocation_d2(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), len(sl),
+                                _i(sl), n, _d(pts), _d(out))
+    return out
+
+
+def exc_grad(flat_basis, shell_to_center, coords, nbf, P, tasks, func_name, include_weight_derivatives=True):
+    """RKS EXC gradient [natoms][3]; tasks as LoadBalancer.export_tasks() (with SSF-modified weights)."""
+    l, pure, nprim, alpha, coeff, origin = flat_basis
+    gga, nk, kern, coef = _func(func_name)
+    Pf = np.asfortranarray(np.asarray(P, np.float64))
+    s2c = np.ascontiguousarray(shell_to_center, np.int32)
+    xyz = np.ascontiguousarray(coords, np.float64)
+    tn = np.ascontiguousarray(tasks["npts"], np.int32)
+    ts = np.ascontiguousarray(tasks["nshells"], np.int32)
+    sl = np.ascontiguousarray(tasks["shell_lists"], np.int32)
+    ip = np.ascontiguousarray(tasks["iParent"], np.int32)
+    dn = np.ascontiguousarray(tasks["dist_nearest"], np.float64)
+    pts = np.ascontiguousarray(tasks["points"], np.float64)
+    w = np.ascontiguousarray(tasks["weights"], np.float64)
+    g = np.zeros((len(xyz), 3))
+    lib().oracle_exc_grad(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), _i(s2c), len(xyz),
+                          _d(xyz), nbf, _d(Pf), Pf.shape[0], len(tn), _i(tn), _i(ts), _i(sl), _i(ip), _d(dn), _d(pts),
+                          _d(w), nk, kern, coef, int(gga), int(bool(include_weight_derivatives)), _d(g))
+    return g
+
+
 def ssf_weights(coords, task_npts, task_iparent, task_dist_nearest, points, weights):
     coords = np.ascontiguousarray(coords, np.float64)
     tn = np.ascontiguousarray(task_npts, np.int32)
@@ -212,3 +246,24 @@ def gau2grid_collocation(flat_basis, shell_list, points, gradient=False):
             outs.append((ph,))
     res = [np.concatenate([o[k] for o in outs], axis=0).T.copy() for k in range(4 if gradient else 1)]
     return tuple(res) if gradient else res[0]
+
+
+def gau2grid_collocation_d2(flat_basis, shell_list, points):
+    """gg_collocation_deriv2 as called by gau2grid_collocation_hessian
+    (local_work_driver/host/reference/gau2grid_collocation.cxx:153-200): ten [npts][nbe] arrays."""
+    g = gau2grid()
+    l, pure, nprim, alpha, coeff, origin = flat_basis
+    pts = np.ascontiguousarray(points, np.float64)
+    n = len(pts)
+    outs = []
+    for s in shell_list:
+        nf = (2 * l[s] + 1) if pure[s] else (l[s] + 1) * (l[s] + 2) // 2
+        order = 300 if pure[s] else 400
+        c = np.ascontiguousarray(coeff[s, :nprim[s]])
+        a = np.ascontiguousarray(alpha[s, :nprim[s]])
+        o = np.ascontiguousarray(origin[s])
+        m = [np.zeros((nf, n)) for _ in range(10)]
+        g.gg_collocation_deriv2(C.c_int(int(l[s])), C.c_ulong(n), _d(pts), C.c_ulong(3), C.c_int(int(nprim[s])),
+                                _d(c), _d(a), _d(o), C.c_int(order), *[_d(x) for x in m])
+        outs.append(m)
+    return np.stack([np.concatenate([o[k] for o in outs], axis=0).T for k in range(10)])

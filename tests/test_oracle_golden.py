@@ -1,6 +1,8 @@
 """CPU: the oracle (oracle/oracle.cxx) against every golden vector the reference's own tests
 hold for this path, plus the pieces of the product's host layer the goldens pin (grid
 generation, batching/screening through the full EXC/VXC integrals)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -323,3 +325,57 @@ def test_functional_thresholds(orc):
             for a in ev:
                 assert np.all(np.isfinite(a))
             assert ev[0][0] == 0 and ev[1][0] == 0 and ev[0][3] == 0
+
+
+def test_collocation_hessian_vs_gau2grid(orc):
+    """Second derivatives of the oracle's collocation against the reference's own gau2grid
+    (gg_collocation_deriv2, the call of gau2grid_collocation_hessian) for l <= 4, cartesian and pure."""
+    import gauxc_b200 as gx
+    if orc.gau2grid() is None:
+        pytest.skip("oracle/_ref/libgau2grid.so not built (reference tree absent)")
+    shells = [dict(l=l, pure=p, exps=[1.3, 0.4], coefs=[0.6, 0.5], origin=(0.1, -0.2, 0.3))
+              for l in range(5) for p in (False, True)]
+    basis = gx.BasisSet(shells, normalize=True)
+    fb = basis.flat()
+    pts = np.random.default_rng(2).standard_normal((64, 3))
+    sl = np.arange(len(shells), dtype=np.int32)
+    a, b = orc.collocation_d2(fb, sl, pts), orc.gau2grid_collocation_d2(fb, sl, pts)
+    assert np.abs(a - b).max() < 2e-14
+    # value + gradient agree with the first-derivative path
+    for q, c in enumerate(orc.collocation(fb, sl, pts, True)):
+        assert np.abs(a[q] - c).max() < 1e-15
+
+
+def shell_centers(atoms, basis):
+    """BasisSetMap::shell_to_center (include/gauxc/basisset_map.hpp): the atom a shell sits on."""
+    xyz = np.array([a[1:] for a in atoms])
+    O = basis.flat()[5]
+    d = np.linalg.norm(O[:, None, :] - xyz[None, :, :], axis=2)
+    assert d.min(1).max() < 1e-12
+    return d.argmin(1).astype(np.int32)
+
+
+@pytest.mark.parametrize("name,func,pruning", [
+    ("benzene_svwn5_cc-pvdz_ufg_ssf", "SVWN5", "Unpruned"),
+    ("benzene_pbe0_cc-pvdz_ufg_ssf", "PBE0", "Unpruned"),
+    ("benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "SVWN5", "Robust"),
+])
+def test_exc_grad_golden(orc, benzene_golden, name, func, pruning):
+    """reference: tests/xc_integrator.cxx:276-297 over /EXC_GRAD_FULL (include_weight_derivatives = true)
+    and /EXC_GRAD_HELLFEY (false): |diff|_F / sqrt(3 natoms) < 1e-8 there; the oracle meets 1e-10."""
+    atoms, shells, P, VXC, EXC = benzene_golden(name, pruning)
+    mol, basis, lb = make_lb(atoms, shells, "UltraFineGrid", pruning, normalize=False)
+    tasks = lb.export_tasks()
+    coords = np.array([a[1:] for a in atoms])
+    tasks["weights"] = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"],
+                                       tasks["points"], tasks["weights"])
+    s2c = shell_centers(atoms, basis)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "benzene_exc_grad.npz"))
+    for key, wd in (("EXC_GRAD_HELLFEY", False), ("EXC_GRAD_FULL", True)):
+        g = orc.exc_grad(basis.flat(), s2c, coords, basis.nbf(), P, tasks, func, include_weight_derivatives=wd)
+        ref = gold[f"{name}:{key}"]
+        rms = np.linalg.norm(g - ref) / np.sqrt(3 * len(atoms))
+        print(name, key, "rms", rms, "max", np.abs(g - ref).max())
+        assert rms < 1e-10
+        if wd:  # translational invariance of the full gradient
+            assert np.abs(g.sum(0)).max() < 1e-10

@@ -10,6 +10,8 @@ Sources (all under /root/reference/tests/):
       consumed by tests/xc_integrator.cxx:405-426       -> benzene_*.npz
   ref_data/cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks.hdf5
       consumed by tests/xc_integrator.cxx:455-459 (UKS LDA)  -> cytosine_svwn5_..._uks.npz
+  ref_data/benzene_*.hdf5 /EXC_GRAD_HELLFEY, /EXC_GRAD_FULL
+      consumed by tests/xc_integrator.cxx:276-297       -> benzene_exc_grad.npz
   ref_data/water_cc-pVDZ_collocation.hdf5
       consumed by tests/collocation.cxx:45-91           -> water_collocation.npz
   ref_data/benzene_weights_ssf.hdf5
@@ -76,6 +78,19 @@ def conv_xc_uks(name):
         o[k] = f.array("/" + k)
     np.savez_compressed(f"{OUT}/{name}.npz", **o)
     print(name, "EXC", o["EXC"], "nbf", o["DENSITY_SCALAR"].shape)
+
+
+def conv_grad():
+    """EXC gradients (tests/xc_integrator.cxx:117-150, 276-297): /EXC_GRAD_HELLFEY (include_weight_derivatives
+    = false) and /EXC_GRAD_FULL (true), natoms x 3 row-major, for the RKS benzene fixtures."""
+    o = {}
+    for name in ("benzene_svwn5_cc-pvdz_ufg_ssf", "benzene_pbe0_cc-pvdz_ufg_ssf",
+                 "benzene_svwn5_cc-pvdz_ufg_ssf_robust_prune", "benzene_svwn5_cc-pvdz_ufg_ssf_treutler_prune"):
+        f = H5File(f"{REF}/ref_data/{name}.hdf5")
+        for k in ("EXC_GRAD_HELLFEY", "EXC_GRAD_FULL"):
+            o[f"{name}:{k}"] = np.asarray(f.array("/" + k), dtype=np.float64).reshape(-1, 3)
+        print(name, "grad", o[f"{name}:EXC_GRAD_FULL"].shape, np.abs(o[f"{name}:EXC_GRAD_FULL"]).max())
+    np.savez_compressed(f"{OUT}/benzene_exc_grad.npz", **o)
 
 
 def conv_basis_only(name, out):
@@ -192,6 +207,7 @@ if __name__ == "__main__":
         conv_xc(n)
     conv_xc_uks("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks")
     conv_xc_uks("cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks")
+    conv_grad()
     conv_basis_only("benzene_m062x_def2-svp_ufg_ssf", "benzene_def2-svp_basis")
     conv_collocation()
     conv_weights()
