@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-Wall,
 SOURCES = [
     "host/core.cxx", "host/grid.cxx", "host/load_balancer.cxx", "host/hdf5_io.cxx", "host/c_api.cxx",
     "host/device_integrator.cu",
-    "cuda/collocation.cu", "cuda/fused.cu", "cuda/vxc.cu", "cuda/ssf_weights.cu", "cuda/probe.cu", "cuda/lb_screen.cu",
+    "cuda/collocation.cu", "cuda/fused.cu", "cuda/vxc.cu", "cuda/ssf_weights.cu", "cuda/probe.cu", "cuda/lb_screen.cu", "cuda/exc_grad.cu",
 ]
 
 

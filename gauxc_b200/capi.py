@@ -106,6 +106,8 @@ def lib():
         "gauxc_integrator_eval_exc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
         "gauxc_integrator_eval_exc_vxc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, _dp, C.c_int64]),
         "gauxc_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
+        "gauxc_b200_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp,
+                                                             C.c_int]),
         "gauxc_integrator_eval_exc_vxc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
                                                      _dp, _dp, C.c_int64, _dp, C.c_int64]),
         "gauxc_integrator_eval_exc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp]),
@@ -144,6 +146,8 @@ def lib():
         "gauxc_b200_lebedev": (C.c_int64, [S, C.c_int, _dp, _dp]),
         "gauxc_b200_radial": (None, [S, C.c_int, C.c_int, C.c_double, _dp, _dp]),
         "gauxc_b200_eval_collocation": (None, [S, _Handle, C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
+        "gauxc_b200_eval_collocation_hessian": (None, [S, _Handle, C.c_int64, _ip, C.c_int64, _dp, _dp, _dp, _dp, _dp,
+                                                         _dp]),
         "gauxc_b200_functional_eval_host": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host_pol": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
         "gauxc_b200_functional_eval_host_pol_full": (None, [S, _Handle, C.c_int64, _dp, _dp, _dp, _dp, _dp]),
@@ -545,13 +549,18 @@ class XCIntegrator(_Obj):
         _call("gauxc_integrator_eval_exc_uks", self.h, m, n, _d(Psf), max(m, 1), _d(Pzf), max(m, 1), C.byref(exc))
         return exc.value
 
-    def eval_exc_grad(self, P, natoms):
-        """RKS EXC gradient (3 * natoms)."""
+    def eval_exc_grad(self, P, natoms, include_weight_derivatives=None):
+        """RKS EXC gradient [natoms][3].  include_weight_derivatives None: the reference's C entry point (default
+        settings = full gradient); True / False: IntegratorSettingsEXC_GRAD through the extension."""
         Pf = np.asfortranarray(np.asarray(P, dtype=np.float64))
         m, n = Pf.shape
         g = np.zeros(3 * natoms)
-        _call("gauxc_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g))
-        return g
+        if include_weight_derivatives is None:
+            _call("gauxc_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g))
+        else:
+            _call("gauxc_b200_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g),
+                  int(bool(include_weight_derivatives)))
+        return g.reshape(natoms, 3)
 
     def eval_exc_vxc_raw(self, m, n, P, ldp, vxc, ldv):
         exc = C.c_double(0.)
@@ -635,6 +644,22 @@ def radial(rq, n, R):
     r, w = np.zeros(n), np.zeros(n)
     _call("gauxc_b200_radial", RadialQuad[rq], n, R, _d(r), _d(w))
     return r, w
+
+
+def eval_collocation_hessian(basis, shell_list, points):
+    """Device collocation with first and second derivatives: ten [npts][nbe] arrays (value, x, y, z, xx, xy, xz, yy,
+    yz, zz) -- test hook of the EXC gradient's Hessian collocation kernel."""
+    sl = np.ascontiguousarray(shell_list, dtype=np.int32)
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    npts = len(pts)
+    nbe = 0
+    for q in sl:
+        d = basis.get_shell(int(q))
+        nbe += (2 * d["l"] + 1) if d["pure"] else (d["l"] + 1) * (d["l"] + 2) // 2
+    out = np.zeros((10, npts, nbe))
+    _call("gauxc_b200_eval_collocation_hessian", basis.h, len(sl), _i(sl), npts, _d(pts), _d(out[0]), _d(out[1]),
+          _d(out[2]), _d(out[3]), _d(out[4:]))
+    return out
 
 
 def eval_collocation(basis, shell_list, points, gradient=False):

@@ -1,0 +1,546 @@
+// EXC gradient kernels: Hessian collocation, the gradient assembly and the SSF weight
+// derivatives.  Host semantics followed:
+//   * gau2grid_collocation_hessian (local_work_driver/host/reference/gau2grid_collocation.cxx:153-216)
+//   * the shell / point loops of reference_replicated_xc_host_integrator_exc_grad.hpp:404-590 (RKS)
+//   * reference_ssf_weights_1std_contraction_host (host/reference/weights.cxx:806-984)
+// replacing the reference device kernels increment_exc_grad_{lda,gga} (kernels/increment_exc_grad.cu) and
+// eval_weight_1st_deriv_contracted_ssf_kernel_1d (kernels/cuda_ssf_1d.cu:146-350).
+//
+// Per batch of tiles the integrator runs: collocation (gradient for LDA, Hessian for GGA) -> the fused DMMA kernel
+// in XOUT mode once per needed X = 2 A P_sub (A = B; GGA also dB/dx, dB/dy, dB/dz) -> exc_grad_kernel.  Tile
+// matrices ([pad16(nbe)][TP], swizzled as everywhere, device_plan.hpp): LDA  B dx dy dz | X;  GGA  B dx dy dz xx xy
+// xz yy yz zz | X Xx Xy Xz.
+#include <algorithm>
+#include <initializer_list>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "xc_functionals.cuh"
+#include "xc_functionals_pol_gga.cuh"
+
+namespace gxb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Hessian collocation: thread = point, ten output matrices.  phi = f(x,y,z) S(r^2), f a monomial:
+//   d_i phi  = f_i S0 + f x_i S1
+//   d_ij phi = f_ij S0 + (f_i x_j + f_j x_i + f delta_ij) S1 + f x_i x_j S2
+// with S0 = sum c e, S1 = sum -2 a c e, S2 = sum 4 a^2 c e.  Pure shells: sparse real solid harmonics (CCA order
+// m = -l..l, gau2grid normalisation) as combinations of monomials.
+// ------------------------------------------------------------------------------------------------
+struct SphTerm { signed char a, b, c, n; double f; };  // n: terms in this row (stored in the row's first entry)
+__constant__ SphTerm c_sph[5][9][6];
+
+template <int NM>
+__device__ __forceinline__ void store_n(double* __restrict__ B, size_t ms, int row, int i, bool ok, const double (&o)[10]) {
+  const size_t off = (size_t)row * TP + swz(row, i);
+#pragma unroll
+  for (int q = 0; q < NM; ++q) B[off + q * ms] = ok ? o[q] : 0.;
+}
+
+__global__ void __launch_bounds__(TP) collocation_hessian_kernel(PlanView pv, const DevTile* __restrict__ tiles,
+                                                                 double* __restrict__ ws) {
+  const DevTile tile = tiles[blockIdx.x];
+  const DevTask task = pv.tasks[tile.task];
+  const int i = threadIdx.x;
+  if (i >= tile_width(tile.npts)) return;
+  const bool ok = i < tile.npts;
+  const int ip = tile.pt_off + (ok ? i : 0);
+  const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];
+  double* __restrict__ B = ws + tile.ws_off;
+  const int nbp = pad16(task.nbe);
+  const size_t ms = (size_t)nbp * TP;
+  {
+    const double zero[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = task.nbe; r < nbp; ++r) store_n<10>(B, ms, r, i, false, zero);
+  }
+  for (int s = 0; s < task.nshells; ++s) {
+    const DevShell sh = pv.shells[pv.task_shells[task.shell_off + s]];
+    const int bf = pv.task_shell_bf[task.shell_off + s];
+    const double r[3] = {px - sh.x, py - sh.y, pz - sh.z};
+    const double r2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double S0 = 0., S1 = 0., S2 = 0.;
+    const double* __restrict__ al = pv.prim_alpha + sh.prim_off;
+    const double* __restrict__ co = pv.prim_coeff + sh.prim_off;
+    for (int k = 0; k < sh.nprim; ++k) {
+      const double a = __ldg(al + k);
+      const double e = __ldg(co + k) * exp(-a * r2);
+      S0 += e;
+      S1 += -2. * a * e;
+      S2 += 4. * a * a * e;
+    }
+    double pw[3][5];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      pw[d][0] = 1.;
+#pragma unroll
+      for (int k = 1; k <= 4; ++k) pw[d][k] = pw[d][k - 1] * r[d];
+    }
+    // monomial x^n0 y^n1 z^n2 with the exponents lowered by (d0, d1, d2), times the falling factors
+    auto fpow = [&](const int (&n)[3], int d0, int d1, int d2) {
+      const int e0 = n[0] - d0, e1 = n[1] - d1, e2 = n[2] - d2;
+      if (e0 < 0 || e1 < 0 || e2 < 0) return 0.;
+      double pre = 1.;
+      for (int k = 0; k < d0; ++k) pre *= double(n[0] - k);
+      for (int k = 0; k < d1; ++k) pre *= double(n[1] - k);
+      for (int k = 0; k < d2; ++k) pre *= double(n[2] - k);
+      return pre * pw[0][e0] * pw[1][e1] * pw[2][e2];
+    };
+    auto mono = [&](int a, int b, int c, double (&o)[10]) {
+      const int n[3] = {a, b, c};
+      const double f = fpow(n, 0, 0, 0);
+      const double f1[3] = {fpow(n, 1, 0, 0), fpow(n, 0, 1, 0), fpow(n, 0, 0, 1)};
+      o[0] = f * S0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) o[1 + d] = f1[d] * S0 + f * r[d] * S1;
+      o[4] = fpow(n, 2, 0, 0) * S0 + (2. * f1[0] * r[0] + f) * S1 + f * r[0] * r[0] * S2;
+      o[5] = fpow(n, 1, 1, 0) * S0 + (f1[0] * r[1] + f1[1] * r[0]) * S1 + f * r[0] * r[1] * S2;
+      o[6] = fpow(n, 1, 0, 1) * S0 + (f1[0] * r[2] + f1[2] * r[0]) * S1 + f * r[0] * r[2] * S2;
+      o[7] = fpow(n, 0, 2, 0) * S0 + (2. * f1[1] * r[1] + f) * S1 + f * r[1] * r[1] * S2;
+      o[8] = fpow(n, 0, 1, 1) * S0 + (f1[1] * r[2] + f1[2] * r[1]) * S1 + f * r[1] * r[2] * S2;
+      o[9] = fpow(n, 0, 0, 2) * S0 + (2. * f1[2] * r[2] + f) * S1 + f * r[2] * r[2] * S2;
+    };
+    const int l = sh.l;
+    if (!sh.pure) {
+      int c = 0;
+      for (int a = l; a >= 0; --a)
+        for (int b = l - a; b >= 0; --b, ++c) {
+          double o[10];
+          mono(a, b, l - a - b, o);
+          store_n<10>(B, ms, bf + c, i, ok, o);
+        }
+    } else {
+      for (int m = 0; m < 2 * l + 1; ++m) {
+        double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int nt = c_sph[l][m][0].n;
+        for (int t = 0; t < nt; ++t) {
+          const SphTerm tt = c_sph[l][m][t];
+          double o[10];
+          mono(tt.a, tt.b, tt.c, o);
+#pragma unroll
+          for (int q = 0; q < 10; ++q) acc[q] += tt.f * o[q];
+        }
+        store_n<10>(B, ms, bf + m, i, ok, acc);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient assembly.  Persistent CTAs of 256 threads pull tiles from *counter; thread (p, h) = point p of the tile,
+// basis rows mu = h (mod 2).  Phase A: rho = sum B X, grad rho = 2 sum dB X (eval_uvvar_{lda,gga}_rks), functional,
+// weights.  Phase B: per shell of the task, rows of the shell
+//   g += w vrho X dB  [+ 2 w vgamma (X (H grad rho) + dB (grad rho . X_grad))]
+// summed over the rows of consecutive shells on the same atom, reduced over the points by warp shuffles and added as
+// -2 g to the atom (with weight derivatives: shells on the parent atom are skipped and the parent receives +2 g;
+// :404-410, 575-590).  Atom sums accumulate in shared memory (3 natoms doubles per CTA) and reach HBM once per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int EG_THREADS = 256;
+
+template <bool GGA>
+__global__ void __launch_bounds__(EG_THREADS)
+exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
+                const double* __restrict__ ws, FunctionalDesc func, const int* __restrict__ shell_atom, int natoms,
+                int include_wd, double* __restrict__ wf_out, double* __restrict__ grad, int smem_acc) {
+  extern __shared__ double eg_dyn[];  // smem_acc: 3 natoms accumulators
+  __shared__ double part[2][4][TP];
+  __shared__ int s_tile;
+  const int tid = threadIdx.x, p = tid & (TP - 1), h = tid >> 7, lane = tid & 31;
+  constexpr int NB = GGA ? 10 : 4;  // basis matrices ahead of X
+  if (smem_acc)
+    for (int q = tid; q < 3 * natoms; q += EG_THREADS) eg_dyn[q] = 0.;
+  __syncthreads();
+  auto add_atom = [&](int atom, int c, double v) {
+    if (smem_acc) atomicAdd(&eg_dyn[3 * atom + c], v);
+    else atomicAdd(&grad[3 * atom + c], v);
+  };
+
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(counter, 1);
+    __syncthreads();
+    const int tile_idx = s_tile;
+    if (tile_idx >= ntiles) break;
+    const DevTile tile = tiles[tile_idx];
+    const DevTask task = pv.tasks[tile.task];
+    const int nbe = tile.nbe;
+    const size_t ms = (size_t)pad16(nbe) * TP;
+    const double* __restrict__ M = ws + tile.ws_off;
+    const bool ok = p < tile.npts;
+    // element (mu, p) of matrix q: M[q * ms + mu * TP + (p ^ ((mu & 3) << 2))]
+    auto at = [&](int q, int mu) { return M[(size_t)q * ms + (size_t)mu * TP + swz(mu, p)]; };
+
+    // ---- phase A
+    double r0 = 0., r1 = 0., r2 = 0., r3 = 0.;
+    if (ok) {
+#pragma unroll 4
+      for (int mu = h; mu < nbe; mu += 2) {
+        const double x = at(NB, mu);
+        r0 = fma(at(0, mu), x, r0);
+        if (GGA) {
+          r1 = fma(at(1, mu), x, r1);
+          r2 = fma(at(2, mu), x, r2);
+          r3 = fma(at(3, mu), x, r3);
+        }
+      }
+    }
+    part[h][0][p] = r0;
+    if (GGA) { part[h][1][p] = r1; part[h][2][p] = r2; part[h][3][p] = r3; }
+    __syncthreads();
+    const double rho = part[0][0][p] + part[1][0][p];
+    double dx = 0., dy = 0., dz = 0.;
+    if (GGA) {
+      dx = 2. * (part[0][1][p] + part[1][1][p]);
+      dy = 2. * (part[0][2][p] + part[1][2][p]);
+      dz = 2. * (part[0][3][p] + part[1][3][p]);
+    }
+    double wv = 0., wg = 0.;
+    if (ok) {
+      const double w = pv.w[tile.pt_off + p];
+      const XcOut xc = eval_functional(func, rho, GGA ? dx * dx + dy * dy + dz * dz : 0.);
+      wv = w * xc.vrho;
+      wg = w * xc.vsigma;
+      if (include_wd && h == 0) wf_out[tile.pt_off + p] = xc.eps * (rho * w);  // eps *= den * w (:396-399)
+    }
+
+    // ---- phase B
+    double acc[3] = {0., 0., 0.}, par[3] = {0., 0., 0.};
+    int cur_atom = -1;
+    auto flush = [&]() {
+      if (cur_atom < 0) return;
+      double v[3] = {acc[0], acc[1], acc[2]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          add_atom(cur_atom, c, -2. * v[c]);
+          par[c] += 2. * v[c];
+        }
+      }
+      acc[0] = acc[1] = acc[2] = 0.;
+    };
+    for (int s = 0; s < task.nshells; ++s) {
+      const int atom = __ldg(shell_atom + __ldg(pv.task_shells + task.shell_off + s));
+      if (include_wd && atom == task.iParent) continue;
+      if (atom != cur_atom) {
+        flush();
+        cur_atom = atom;
+      }
+      if (!ok) continue;
+      const int bf0 = __ldg(pv.task_shell_bf + task.shell_off + s);
+      const int bf1 = s + 1 < task.nshells ? __ldg(pv.task_shell_bf + task.shell_off + s + 1) : nbe;
+      for (int mu = bf0 + ((bf0 ^ h) & 1); mu < bf1; mu += 2) {
+        const double xn = at(NB, mu);
+        const double dbx = at(1, mu), dby = at(2, mu), dbz = at(3, mu);
+        const double a = wv * xn;
+        acc[0] = fma(a, dbx, acc[0]);
+        acc[1] = fma(a, dby, acc[1]);
+        acc[2] = fma(a, dbz, acc[2]);
+        if (GGA) {
+          const double xx = at(4, mu), xy = at(5, mu), xz = at(6, mu), yy = at(7, mu), yz = at(8, mu), zz = at(9, mu);
+          const double d2x = xx * dx + xy * dy + xz * dz;
+          const double d2y = xy * dx + yy * dy + yz * dz;
+          const double d2z = xz * dx + yz * dy + zz * dz;
+          const double d11 = dx * at(NB + 1, mu) + dy * at(NB + 2, mu) + dz * at(NB + 3, mu);
+          const double g2 = 2. * wg;
+          acc[0] += g2 * (xn * d2x + dbx * d11);
+          acc[1] += g2 * (xn * d2y + dby * d11);
+          acc[2] += g2 * (xn * d2z + dbz * d11);
+        }
+      }
+    }
+    flush();
+    if (include_wd && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (par[c] != 0.) add_atom(task.iParent, c, par[c]);
+    }
+    __syncthreads();  // part[] and s_tile are reused by the next tile
+  }
+  if (smem_acc) {
+    __syncthreads();
+    for (int q = tid; q < 3 * natoms; q += EG_THREADS) {
+      const double v = eg_dyn[q];
+      if (v != 0.) atomicAdd(&grad[q], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSF weight derivatives contracted with wf = w eps rho.  One warp per grid point, lanes over atoms.  With
+// kappa = (1 + 0.64)/(1 - 0.64) and r_min the distance to the nearest atom (the bounds of ssf_weights.cu):
+//   * P_A = 0 exactly unless r_A < kappa r_min                                   (list0)
+//   * atom B changes P_A (s(mu_AB) != 1) only if r_B < kappa r_A < kappa^2 r_min  (list1)
+//   * the derivative terms need |mu_BC| < 0.64 - 1e-4 with P_B > 1e-13, or |mu_parent,B| < 0.64 - 1e-4 with
+//     P_parent > 0 (wf = 0 otherwise): all inside list1.
+// So every loop of the host function runs over list1 (compacted into shared memory with coordinates and distances)
+// instead of all atoms, with identical terms.  The host's pair loop skips pairs whose two partial products are both
+// <= 1e-13; here P_A is the full product (differences below 1e-13 of the sum).  R_AB is recomputed from the
+// coordinates.  Atom sums accumulate in shared memory per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr double magic_ssf = 0.64;
+
+__device__ __forceinline__ double g_frisch_d(double x) {
+  const double s = x / magic_ssf;
+  const double s2 = s * s, s3 = s * s2, s5 = s3 * s2, s7 = s5 * s2;
+  return (35. * (s - s3) + 21. * s5 - 5. * s7) / 16.;
+}
+__device__ __forceinline__ double t_frisch_d(double x) {
+  const double s = x / magic_ssf;
+  const double s2 = s * s, s3 = s * s2;
+  const double num = 35. * (s3 + 3. * s2 + 3. * s + 1.);
+  const double den = (x - magic_ssf) * (5. * s3 + 20. * s2 + 29. * s + 16.);
+  return num / den;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+__global__ void ssf_weight_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles,
+                                       int* __restrict__ counter, const double* __restrict__ atoms,
+                                       const double* __restrict__ dist_nearest, int natoms,
+                                       const double* __restrict__ wf, double* __restrict__ grad) {
+  extern __shared__ double wg_dyn[];
+  __shared__ int s_tile;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* g_s = wg_dyn;                                        // [3 natoms] CTA accumulators
+  double* base = wg_dyn + 3 * natoms + (size_t)warp * 5 * natoms;  // per warp
+  double *ld = base, *lx = base + natoms, *ly = base + 2 * natoms, *lz = base + 3 * natoms, *lp = base + 4 * natoms;
+  int* li = reinterpret_cast<int*>(wg_dyn + 3 * natoms + (size_t)nwarps * 5 * natoms) + (size_t)warp * natoms;
+  for (int q = threadIdx.x; q < 3 * natoms; q += blockDim.x) g_s[q] = 0.;
+  __syncthreads();
+  const double kappa = (1. + magic_ssf) / (1. - magic_ssf) * (1. + 1e-9);
+  const double bound = magic_ssf - 1.e-4, weight_tol = 1e-13, wf_thresh = 1.e-12;
+
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
+    __syncthreads();
+    const int tile_idx = s_tile;
+    __syncthreads();
+    if (tile_idx >= ntiles) break;
+    const DevTile tile = tiles[tile_idx];
+    const int par = pv.tasks[tile.task].iParent;
+    const double dist_cutoff = 0.5 * (1. - magic_ssf) * dist_nearest[par];
+    const double ax = atoms[3 * par], ay = atoms[3 * par + 1], az = atoms[3 * par + 2];
+    for (int i = warp; i < tile.npts; i += nwarps) {
+      const int ip = tile.pt_off + i;
+      const double wfi = wf[ip];
+      if (fabs(wfi) < wf_thresh) continue;
+      const double px = pv.px[ip], py = pv.py[ip], pz = pv.pz[ip];
+      const double d_par = sqrt((px - ax) * (px - ax) + (py - ay) * (py - ay) + (pz - az) * (pz - az));
+      if (d_par < dist_cutoff) continue;
+      // nearest atom
+      double dmin = d_par;
+      for (int a = lane; a < natoms; a += 32) {
+        const double dx = px - atoms[3 * a], dy = py - atoms[3 * a + 1], dz = pz - atoms[3 * a + 2];
+        dmin = fmin(dmin, sqrt(dx * dx + dy * dy + dz * dz));
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+      // list1: atoms with r < kappa^2 r_min, compacted in index order
+      const double r1 = kappa * kappa * dmin, r0 = kappa * dmin;
+      int n1 = 0, kpar = -1;
+      __syncwarp();
+      for (int a0 = 0; a0 < natoms; a0 += 32) {
+        const int a = a0 + lane;
+        double x = 0., y = 0., z = 0., d = 1e300;
+        if (a < natoms) {
+          x = atoms[3 * a]; y = atoms[3 * a + 1]; z = atoms[3 * a + 2];
+          d = a == par ? d_par : sqrt((px - x) * (px - x) + (py - y) * (py - y) + (pz - z) * (pz - z));
+        }
+        const bool keep = a < natoms && (d < r1 || a == par);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = n1 + __popc(m & ((1u << lane) - 1u));
+        if (keep) { li[pos] = a; ld[pos] = d; lx[pos] = x; ly[pos] = y; lz[pos] = z; }
+        const unsigned mp = __ballot_sync(0xffffffffu, keep && a == par);
+        if (mp) kpar = n1 + __popc(m & ((1u << (__ffs(mp) - 1)) - 1u));
+        n1 += __popc(m);
+      }
+      __syncwarp();
+      // partition products over list1
+      double psum = 0.;
+      for (int k = lane; k < n1; k += 32) {
+        double P = 0.;
+        const double dk = ld[k];
+        if (dk < r0) {
+          P = 1.;
+          const double xk = lx[k], yk = ly[k], zk = lz[k];
+          for (int j = 0; j < n1; ++j) {
+            if (j == k) continue;
+            const double ex = xk - lx[j], ey = yk - ly[j], ez = zk - lz[j];
+            const double mu = (dk - ld[j]) / sqrt(ex * ex + ey * ey + ez * ez);
+            if (mu >= magic_ssf) { P = 0.; break; }
+            if (mu > -magic_ssf) P *= 0.5 * (1. - g_frisch_d(mu));
+          }
+        }
+        lp[k] = P;
+        psum += P;
+      }
+      const double sum = warp_sum(psum);
+      __syncwarp();
+      const double P_par = lp[kpar];
+      double pa[3] = {0., 0., 0.};  // lane-local share of what the parent receives (translational invariance)
+      // first term: - coef1 nabla_B mu_BA, B != parent
+      for (int k = lane; k < n1; k += 32) {
+        if (k == kpar) continue;
+        const double ux = lx[k] - ax, uy = ly[k] - ay, uz = lz[k] - az;
+        const double rAB = sqrt(ux * ux + uy * uy + uz * uz), rAB_inv = 1. / rAB;
+        const double dB = ld[k];
+        const double mu_AB = (d_par - dB) * rAB_inv;
+        if (fabs(mu_AB) < bound) {
+          const double coef1 = t_frisch_d(mu_AB) / rAB * (P_par - sum) / sum * wfi / dB;
+          const double gx = coef1 * ((lx[k] - px) + mu_AB * ux * rAB_inv * dB);
+          const double gy = coef1 * ((ly[k] - py) + mu_AB * uy * rAB_inv * dB);
+          const double gz = coef1 * ((lz[k] - pz) + mu_AB * uz * rAB_inv * dB);
+          atomicAdd(&g_s[3 * li[k]], gx); atomicAdd(&g_s[3 * li[k] + 1], gy); atomicAdd(&g_s[3 * li[k] + 2], gz);
+          pa[0] -= gx; pa[1] -= gy; pa[2] -= gz;
+        }
+      }
+      // second term: B with P_B > tol, C over list1
+      for (int kb = 0; kb < n1; ++kb) {
+        const double PB = lp[kb];
+        if (!(PB > weight_tol) || kb == kpar) continue;
+        const double xb = lx[kb], yb = ly[kb], zb = lz[kb], dB = ld[kb];
+        double gb[3] = {0., 0., 0.};
+        for (int kc = lane; kc < n1; kc += 32) {
+          if (kc == kb) continue;
+          const double ex = xb - lx[kc], ey = yb - ly[kc], ez = zb - lz[kc];
+          const double rBC = sqrt(ex * ex + ey * ey + ez * ez);
+          const double dC = ld[kc];
+          const double mu_BC = (dB - dC) / rBC;
+          if (fabs(mu_BC) < bound) {
+            const double coef = PB * t_frisch_d(mu_BC) / rBC / sum * wfi;
+            gb[0] -= coef * ((xb - px) / dB - mu_BC * ex / rBC);
+            gb[1] -= coef * ((yb - py) / dB - mu_BC * ey / rBC);
+            gb[2] -= coef * ((zb - pz) / dB - mu_BC * ez / rBC);
+            if (kc != kpar) {
+              const double cx = coef * ((lx[kc] - px) / dC - mu_BC * ex / rBC);
+              const double cy = coef * ((ly[kc] - py) / dC - mu_BC * ey / rBC);
+              const double cz = coef * ((lz[kc] - pz) / dC - mu_BC * ez / rBC);
+              atomicAdd(&g_s[3 * li[kc]], cx); atomicAdd(&g_s[3 * li[kc] + 1], cy); atomicAdd(&g_s[3 * li[kc] + 2], cz);
+              pa[0] -= cx; pa[1] -= cy; pa[2] -= cz;
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double v = warp_sum(gb[c]);
+          if (lane == 0) {
+            atomicAdd(&g_s[3 * li[kb] + c], v);
+            pa[c] -= v;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = warp_sum(pa[c]);
+        if (lane == 0 && v != 0.) atomicAdd(&g_s[3 * par + c], v);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 3 * natoms; q += blockDim.x) {
+    const double v = g_s[q];
+    if (v != 0.) atomicAdd(&grad[q], v);
+  }
+}
+
+bool g_sph_ready[64] = {};
+
+void upload_sph_table() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && g_sph_ready[dev]) return;
+  static SphTerm T[5][9][6];
+  auto row = [&](int l, int m, std::initializer_list<SphTerm> ts) {
+    int k = 0;
+    for (auto t : ts) T[l][m][k++] = t;
+    T[l][m][0].n = (signed char)ts.size();
+  };
+  for (auto& a : T) for (auto& b : a) for (auto& c : b) c = SphTerm{0, 0, 0, 0, 0.};
+  const double s3 = 1.7320508075688772935;
+  row(0, 0, {{0, 0, 0, 0, 1.}});
+  row(1, 0, {{0, 1, 0, 0, 1.}}); row(1, 1, {{0, 0, 1, 0, 1.}}); row(1, 2, {{1, 0, 0, 0, 1.}});
+  row(2, 0, {{1, 1, 0, 0, s3}});
+  row(2, 1, {{0, 1, 1, 0, s3}});
+  row(2, 2, {{0, 0, 2, 0, 1.}, {2, 0, 0, 0, -0.5}, {0, 2, 0, 0, -0.5}});
+  row(2, 3, {{1, 0, 1, 0, s3}});
+  row(2, 4, {{2, 0, 0, 0, 0.5 * s3}, {0, 2, 0, 0, -0.5 * s3}});
+  const double s10 = 0.79056941504209483300, s15 = 3.8729833462074168852, s6 = 0.61237243569579452455,
+               s15h = 1.9364916731037084426;
+  row(3, 0, {{2, 1, 0, 0, 3 * s10}, {0, 3, 0, 0, -s10}});
+  row(3, 1, {{1, 1, 1, 0, s15}});
+  row(3, 2, {{0, 1, 2, 0, 4 * s6}, {2, 1, 0, 0, -s6}, {0, 3, 0, 0, -s6}});
+  row(3, 3, {{0, 0, 3, 0, 1.0}, {2, 0, 1, 0, -1.5}, {0, 2, 1, 0, -1.5}});
+  row(3, 4, {{1, 0, 2, 0, 4 * s6}, {3, 0, 0, 0, -s6}, {1, 2, 0, 0, -s6}});
+  row(3, 5, {{2, 0, 1, 0, s15h}, {0, 2, 1, 0, -s15h}});
+  row(3, 6, {{3, 0, 0, 0, s10}, {1, 2, 0, 0, -3 * s10}});
+  const double s35h = 2.9580398915498080213, s70q = 2.0916500663351888699, s5h = 1.1180339887498948482,
+               s10q = 0.79056941504209483300, s5q = 0.55901699437494742410, s35e = 0.73950997288745200532;
+  row(4, 0, {{3, 1, 0, 0, s35h}, {1, 3, 0, 0, -s35h}});
+  row(4, 1, {{2, 1, 1, 0, 3 * s70q}, {0, 3, 1, 0, -s70q}});
+  row(4, 2, {{1, 1, 2, 0, 6 * s5h}, {3, 1, 0, 0, -s5h}, {1, 3, 0, 0, -s5h}});
+  row(4, 3, {{0, 1, 3, 0, 4 * s10q}, {2, 1, 1, 0, -3 * s10q}, {0, 3, 1, 0, -3 * s10q}});
+  row(4, 4, {{0, 0, 4, 0, 1.0}, {2, 0, 2, 0, -3.0}, {0, 2, 2, 0, -3.0}, {4, 0, 0, 0, 0.375}, {2, 2, 0, 0, 0.75},
+             {0, 4, 0, 0, 0.375}});
+  row(4, 5, {{1, 0, 3, 0, 4 * s10q}, {3, 0, 1, 0, -3 * s10q}, {1, 2, 1, 0, -3 * s10q}});
+  row(4, 6, {{2, 0, 2, 0, 6 * s5q}, {0, 2, 2, 0, -6 * s5q}, {4, 0, 0, 0, -s5q}, {0, 4, 0, 0, s5q}});
+  row(4, 7, {{3, 0, 1, 0, s70q}, {1, 2, 1, 0, -3 * s70q}});
+  row(4, 8, {{4, 0, 0, 0, s35e}, {2, 2, 0, 0, -6 * s35e}, {0, 4, 0, 0, s35e}});
+  cudaMemcpyToSymbol(c_sph, T, sizeof(T));
+  if (dev >= 0 && dev < 64) g_sph_ready[dev] = true;
+}
+
+}  // namespace
+
+void launch_collocation_hessian(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws, cudaStream_t s) {
+  if (ntiles <= 0) return;
+  upload_sph_table();
+  collocation_hessian_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, ws);
+}
+
+cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
+                            const double* ws, FunctionalDesc func, bool gga, const int* shell_atom, int natoms,
+                            bool include_wd, double* wf_out, double* grad, cudaStream_t s) {
+  if (ntiles <= 0) return cudaSuccess;
+  const size_t dyn = (size_t)3 * natoms * sizeof(double);
+  const bool smem_acc = dyn <= 160 * 1024;
+  const int ncta = std::min(ntiles, std::max(1, nsm) * (smem_acc && dyn > 64 * 1024 ? 1 : 3));
+  auto launch = [&](auto kern) {
+    if (smem_acc && dyn > 32 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<ncta, EG_THREADS, smem_acc ? dyn : 0, s>>>(pv, tiles, ntiles, counter, ws, func, shell_atom, natoms,
+                                                      include_wd ? 1 : 0, wf_out, grad, smem_acc ? 1 : 0);
+    return cudaGetLastError();
+  };
+  return gga ? launch(exc_grad_kernel<true>) : launch(exc_grad_kernel<false>);
+}
+
+cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
+                                   const double* atoms, const double* dist_nearest, int natoms, const double* wf,
+                                   double* grad, cudaStream_t s) {
+  if (ntiles <= 0) return cudaSuccess;
+  // shared memory: 3 natoms (CTA sums) + per warp 5 natoms doubles + natoms ints
+  auto bytes = [&](int nw) { return (size_t)natoms * (3 * 8 + (size_t)nw * (5 * 8 + 4)) + 16; };
+  int nw = 8;
+  while (nw > 1 && bytes(nw) > 200 * 1024) nw >>= 1;
+  const size_t dyn = bytes(nw);
+  if (dyn > 227 * 1024) return cudaErrorInvalidConfiguration;  // > ~3400 atoms: the caller reports NYI
+  cudaError_t e = cudaFuncSetAttribute(ssf_weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / dyn));
+  const int ncta = std::min(ntiles, std::max(1, nsm) * per_sm);
+  ssf_weight_grad_kernel<<<ncta, nw * 32, dyn, s>>>(pv, tiles, ntiles, counter, atoms, dist_nearest, natoms, wf, grad);
+  return cudaGetLastError();
+}
+
+}  // namespace gxb

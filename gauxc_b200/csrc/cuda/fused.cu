@@ -147,7 +147,11 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
 // func.nkern == 0: density only (integrate_den): no functional, no Z pass.
 // DUAL: the functional contains kernels evaluated with dual numbers (B88, LYP; every polarised GGA) -- kept out
 // of the instantiations that do not need them (xc_functionals.cuh)
-template <bool GGA, int SPIN, bool DUAL>
+// XOUT (EXC gradient, eval_xmat of reference_replicated_xc_host_integrator_exc_grad.hpp:370-373): the kernel only
+// forms X = 2 A P_sub for ONE matrix A of the tile (B or one of dB/dx, dB/dy, dB/dz) and the density warps write it
+// to another matrix slot of the tile instead of contracting it -- the gradient kernel (exc_grad.cu) needs X itself.
+// The two slots travel in uks_stride (unused for SPIN == 0): low 16 bits = A, next 16 bits = X slot.
+template <bool GGA, int SPIN, bool DUAL, bool XOUT = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
                            const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
@@ -362,6 +366,24 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       double r0[4] = {0., 0., 0., 0.}, r1[4] = {0., 0., 0., 0.}, r2[4] = {0., 0., 0., 0.},
              r3[4] = {0., 0., 0., 0.};
       const bool lane_on = p4 < tile_width(tile.npts);  // columns beyond the tile width do not exist
+      if (XOUT) {
+        double* __restrict__ Xo = ws + tile.ws_off + (size_t)((uks_stride >> 16) & 0xffff) * ms + cofs;
+        for (int c = 0; c < nn; ++c) {
+          const int n0 = c * FN;
+          const int ncols = lane_on ? min(FN, nbe - n0) : 0;
+          mbar_wait(&S.xfull, xph);
+          for (int n = dw; n < ncols; n += 4) {
+            double x[4];
+            lds4(x, &S.X[n][p4]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] *= 2.;  // eval_xmat fac = 2 (RKS)
+            stg256(Xo + (size_t)(n0 + n) * TP, x);
+          }
+          mbar_arrive(&S.xempty);
+          xph ^= 1;
+        }
+        continue;
+      }
       for (int c = 0; c < nn; ++c) {
         const int n0 = c * FN;
         const int ncols = lane_on ? min(FN, nbe - n0) : 0;
@@ -447,6 +469,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     for (int it = 0;; ++it) {
       const int tile_idx = next_tile(it);
       if (tile_idx < 0) break;
+      if (XOUT) continue;  // X is written by the density warps; no functional, no Z
       const DevTile tile = tiles[tile_idx];
       const int nbe = tile.nbe;
       const int nbp = pad16(nbe);
@@ -671,7 +694,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
       const int* __restrict__ ao = pv.task_ao + tile.ao_off;
-      const int rowB = (int)(tile.ws_off / TP);
+      const int rowB = (int)(tile.ws_off / TP) + (XOUT ? (int)(uks_stride & 0xffff) * pad16(nbe) : 0);
       const int W = tile_width(tile.npts);
       for (int c = 0; c < nn; ++c) {
         // lane -> columns (lane, lane + 32): each warp-wide LDGSTS covers 32 consecutive local AOs
@@ -739,6 +762,7 @@ cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile
                                                        exc_part, nel_part, part_off, uks_den, uks_stride);
     return cudaGetLastError();
   };
+  if (spin == 3) return launch(fused_xmat_den_zmat_kernel<true, 0, false, true>);  // XOUT
   if (spin == 1 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 1, false>);
   if (spin == 2 && func.is_gga) return launch(fused_xmat_den_zmat_kernel<true, 2, true>);
   if (spin == 1) return launch(fused_xmat_den_zmat_kernel<false, 1, false>);

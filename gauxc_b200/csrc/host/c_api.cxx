@@ -14,7 +14,7 @@ using namespace GauXC;
 namespace GauXC {
 void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& shell_list,
                              int64_t npts, const double* points, double* eval, double* dx,
-                             double* dy, double* dz);
+                             double* dy, double* dz, double* hess6 = nullptr);
 double device_probe_peak(int which);
 int device_count();
 void device_set(int dev);
@@ -483,6 +483,13 @@ void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrat
   INTG(integrator)->eval_exc_grad(m, n, P, ldp, exc_grad);
   C_CATCH(status)
 }
+void gauxc_b200_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                             const int64_t n, const double* P, const int64_t ldp, double* exc_grad,
+                                             int include_weight_derivatives) {
+  C_TRY(status)
+  INTG(integrator)->eval_exc_grad(m, n, P, ldp, exc_grad, include_weight_derivatives != 0);
+  C_CATCH(status)
+}
 void gauxc_integrator_eval_exc_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
                                    const int64_t n, const double* Ps, const int64_t ldps, const double* Pz,
                                    const int64_t ldpz, double* exc) {
@@ -793,6 +800,14 @@ void gauxc_b200_eval_collocation(GauXCStatus* status, const GauXCBasisSet basis,
   C_TRY(status)
   std::vector<int32_t> sl(shell_list, shell_list + nshells);
   device_eval_collocation(*BAS(basis), sl, npts, points, eval, dx, dy, dz);
+  C_CATCH(status)
+}
+void gauxc_b200_eval_collocation_hessian(GauXCStatus* status, const GauXCBasisSet basis, int64_t nshells,
+                                         const int32_t* shell_list, int64_t npts, const double* points, double* eval,
+                                         double* dx, double* dy, double* dz, double* hess6) {
+  C_TRY(status)
+  std::vector<int32_t> sl(shell_list, shell_list + nshells);
+  device_eval_collocation(*BAS(basis), sl, npts, points, eval, dx, dy, dz, hess6);
   C_CATCH(status)
 }
 double gauxc_b200_probe_peak(GauXCStatus* status, int which) {

@@ -101,6 +101,7 @@ struct DevicePlan {
   DevBuf<gxb::DevTask> d_tasks;
   DevBuf<gxb::DevTile> d_tiles;
   DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
+  DevBuf<int> d_shell_center;  // shell -> atom (BasisSetMap::shell_to_center), EXC gradient
   DevBuf<double> d_px, d_py, d_pz, d_w;
   DevBuf<double> d_atoms, d_rab, d_dist_nearest, d_nbr_dist;
   DevBuf<int> d_nbr_idx;  // per atom: all atoms sorted by distance from it (SSF loop cut-offs)
@@ -274,6 +275,10 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
   plan->d_task_shells.upload(task_shells);
   plan->d_task_shell_bf.upload(task_shell_bf);
   plan->d_task_ao.upload(task_ao);
+  {
+    std::vector<int> sc(bmap.shell_to_center.begin(), bmap.shell_to_center.end());
+    plan->d_shell_center.upload(sc);
+  }
   plan->d_px.upload(px);
   plan->d_py.upload(py);
   plan->d_pz.upload(pz);
@@ -649,6 +654,7 @@ struct XCIntegrator::Impl {
   bool p_pending = false;  // set by the host-buffer entry points: wait for e_p_ready before P is read
   DevBuf<double> dP, dPtri, dVXC, d_ws, d_exc_part, d_nel_part, d_out2, d_pack;
   DevBuf<double> dPz, dPtri_z, dVXCz, d_uks_den;  // UKS: z density / potential, densities per point
+  DevBuf<double> d_grad, d_wf;  // EXC gradient: 3 natoms sums, w eps rho per point (weight derivatives)
   gxb::TmapSet tmapA{};  // TMA views of d_ws: 16 rows x (32..128) points
   CUtensorMap tmapV{}, tmapZ{};  // 128 / 64 rows x 16 points
   int ncta = 0;
@@ -1164,8 +1170,78 @@ void XCIntegrator::eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t 
   eval_uks_(m, n, Ps, ldps, Pz, ldpz, nullptr, 0, nullptr, 0, EXC, false);
 }
 
-void XCIntegrator::eval_exc_grad(int64_t, int64_t, const double*, int64_t, double*) {
-  GAUXC_GENERIC_EXCEPTION("EXC Gradient NYI in B200 path");
+// EXC gradient, RKS LDA / GGA (incore_replicated_xc_device_integrator_exc_grad.hpp:21-72, 134-270; host semantics
+// reference_replicated_xc_host_integrator_exc_grad.hpp:107-601).  Per batch: collocation gradient (LDA) / Hessian
+// (GGA) -> X = 2 P_sub A on the DMMA pipe for A = B (GGA: and the three dB) -> gradient assembly (densities,
+// functional, per-atom sums); with weight derivatives (the default, IntegratorSettingsEXC_GRAD) one more kernel
+// contracts the SSF weight derivatives with w eps rho over all local points.  The 3 natoms sums are reduced over the
+// ranks on the device (the reference refuses a device reduction here: "Device Reduction + EXC Grad NYI").
+void XCIntegrator::eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD,
+                                 bool include_weight_derivatives) {
+  check_dims(*lb_, m, n, ldp, 0, false);
+  if (func_->polarized) GAUXC_GENERIC_EXCEPTION("RKS Evaluation Requires An Unpolarized Functional");
+  if (!lb_->state().modified_weights_are_stored) GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
+  if (include_weight_derivatives && lb_->state().weight_alg != XCWeightAlg::SSF)
+    GAUXC_GENERIC_EXCEPTION("Weight Alg Not Supported");
+  auto& I = *impl_;
+  const size_t nbf = (size_t)m;
+  cudaStream_t s = I.stream;
+  const bool gga = func_->is_gga();
+  const int nb = gga ? 10 : 4, nx = gga ? 4 : 1, nmat = nb + nx;
+  I.ensure_matrices(nbf, red_->comm_size(), false);
+  CUDA_CHECK(cudaEventRecord(I.e_begin, s));
+  CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
+  upload_density_(P, ldp, I.dP.p, nbf);
+  CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
+  I.prepare(*lb_, nmat, false);
+  auto& plan = *I.plan;
+  auto& sc = *I.sched;
+  const gxb::PlanView pv = plan.view();
+  const int inbf = plan.nbf, natoms = plan.natoms;
+  if (I.d_grad.n != (size_t)3 * natoms) I.d_grad.alloc((size_t)3 * natoms);
+  if (include_weight_derivatives && I.d_wf.n < plan.npts) I.d_wf.alloc(std::max<size_t>(1, plan.npts));
+  CUDA_CHECK(cudaMemsetAsync(I.d_grad.p, 0, sizeof(double) * 3 * natoms, s));
+  CUDA_CHECK(cudaMemsetAsync(sc.d_counters.p, 0, sizeof(int) * sc.d_counters.n, s));
+  CUDA_CHECK(cudaEventRecord(I.e_lw0, s));
+  const size_t nbatch = sc.batches.size();
+  long long launches = 0;
+  size_t ib = 0;
+  for (auto& b : sc.batches) {
+    const int nt = b.tile_end - b.tile_begin;
+    const gxb::DevTile* tl = sc.d_tiles.p + b.tile_begin;
+    if (gga) gxb::launch_collocation_hessian(pv, tl, nt, I.d_ws.p, s);
+    else gxb::launch_collocation(pv, tl, nt, I.d_ws.p, true, s);
+    if (ib == 0) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));  // the upload of P hides behind the collocation
+    for (int k = 0; k < nx; ++k)
+      CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + k * nbatch + ib, sc.ncta, I.d_ws.p, I.dP.p,
+                                   inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 3, nullptr,
+                                   (size_t)k | ((size_t)(nb + k) << 16)));
+    CUDA_CHECK(gxb::launch_exc_grad(pv, tl, nt, sc.d_counters.p + 4 * nbatch + ib, sc.ncta, I.d_ws.p, func_->desc, gga,
+                                    plan.d_shell_center.p, natoms, include_weight_derivatives,
+                                    include_weight_derivatives ? I.d_wf.p : nullptr, I.d_grad.p, s));
+    launches += 2 + nx;
+    ++ib;
+  }
+  if (sc.batches.empty()) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
+  if (include_weight_derivatives && !plan.tiles.empty()) {
+    const cudaError_t e = gxb::launch_ssf_weight_grad(pv, plan.d_tiles.p, (int)plan.tiles.size(),
+                                                      sc.d_counters.p + 5 * nbatch, sc.ncta, plan.d_atoms.p,
+                                                      plan.d_dist_nearest.p, natoms, I.d_wf.p, I.d_grad.p, s);
+    if (e == cudaErrorInvalidConfiguration)
+      GAUXC_GENERIC_EXCEPTION("SSF Weight Derivatives NYI in B200 path for this many atoms");
+    CUDA_CHECK(e);
+    ++launches;
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(I.e_lw1, s));
+  if (red_->comm_size() > 1) red_->allreduce_inplace(I.d_grad.p, (size_t)3 * natoms, ReductionOp::Sum, s);
+  CUDA_CHECK(cudaMemcpyAsync(EXC_GRAD, I.d_grad.p, sizeof(double) * 3 * natoms, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, I.e_lw0, I.e_lw1);
+  stats_.last_local_work_ms = ms;
+  timer_.add("XCIntegrator.LocalWork_EXC_GRAD", ms);
+  stats_.kernel_launches = launches;
 }
 
 }  // namespace GauXC
@@ -1211,9 +1287,10 @@ void device_allreduce(double* dptr, size_t n) {
 // eval[ipt*nbe + mu] of gau2grid_collocation.cxx.
 void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& shell_list,
                              int64_t npts, const double* points, double* eval, double* dx,
-                             double* dy, double* dz) {
+                             double* dy, double* dz, double* hess6) {
   require_device();
   const bool grad = dx != nullptr;
+  const bool hess = hess6 != nullptr;  // six more [npts][nbe] arrays: xx, xy, xz, yy, yz, zz
   Molecule mol;  // centres are irrelevant here
   BasisSetMap bmap(basis, mol);
   std::vector<gxb::DevShell> shells(basis.size());
@@ -1241,7 +1318,7 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   task.nbe = nbe;
   task.npts = (int)npts;
   std::vector<gxb::DevTile> tiles;
-  const int nmat = grad ? 4 : 1;
+  const int nmat = hess ? 10 : (grad ? 4 : 1);
   for (int p0 = 0; p0 < npts; p0 += gxb::TP) {
     gxb::DevTile t{};
     t.task = 0; t.pt_off = p0; t.npts = (int)std::min<int64_t>(gxb::TP, npts - p0);
@@ -1262,7 +1339,8 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
   gxb::PlanView pv{};
   pv.shells = d_sh.p; pv.prim_alpha = d_a.p; pv.prim_coeff = d_c.p; pv.tasks = d_task.p;
   pv.task_shells = d_tsh.p; pv.task_shell_bf = d_tbf.p; pv.px = d_px.p; pv.py = d_py.p; pv.pz = d_pz.p;
-  gxb::launch_collocation(pv, d_tiles.p, (int)tiles.size(), d_ws.p, grad, 0);
+  if (hess) gxb::launch_collocation_hessian(pv, d_tiles.p, (int)tiles.size(), d_ws.p, 0);
+  else gxb::launch_collocation(pv, d_tiles.p, (int)tiles.size(), d_ws.p, grad, 0);
   CUDA_CHECK(cudaGetLastError());
   std::vector<double> h(wsn);
   CUDA_CHECK(cudaMemcpy(h.data(), d_ws.p, wsn * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1274,6 +1352,8 @@ void device_eval_collocation(const BasisSet& basis, const std::vector<int32_t>& 
         const size_t dst = (size_t)(tiles[t].pt_off + i) * nbe + mu;
         eval[dst] = h[src];
         if (grad) { dx[dst] = h[src + ms]; dy[dst] = h[src + 2 * ms]; dz[dst] = h[src + 3 * ms]; }
+        if (hess)
+          for (int q = 0; q < 6; ++q) hess6[(size_t)q * npts * nbe + dst] = h[src + (4 + q) * ms];
       }
 }
 

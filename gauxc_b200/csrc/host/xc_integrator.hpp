@@ -123,8 +123,11 @@ public:
   void eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
                     double* EXC);
   void eval_exc(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC);
-  // EXC gradient w.r.t. the nuclear coordinates (3 * natoms), RKS
-  void eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD);
+  // EXC gradient w.r.t. the nuclear coordinates (3 * natoms, atom-major), RKS.  include_weight_derivatives:
+  // IntegratorSettingsEXC_GRAD (include/gauxc/xc_integrator_settings.hpp:28-30), default true = full gradient with
+  // the grid-weight contribution and translational invariance; false = Hellmann-Feynman-like gradient
+  void eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD,
+                     bool include_weight_derivatives = true);
   void integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL);
   // device-resident variant: dP (nbf x nbf, ld nbf) and dVXC live in HBM, out2 = {EXC, N_EL}
   // device scalars; no host<->device traffic in the call.

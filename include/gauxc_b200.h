@@ -358,6 +358,12 @@ void gauxc_b200_load_balancer_set_tasks(GauXCStatus* status, GauXCLoadBalancer l
 /* stats of the last eval call: out[0..15] = {local_work_ms, total_ms, k_colloc_ms, k_xmat_ms,
  * k_zmat_ms, k_vxc_ms, launches, f_dense, sum_nbe_npts, npts, ntiles, nbatches, nitems, n_el,
  * 0, 0}; per-kernel ms are only filled in profile mode */
+/* EXC gradient with the reference's IntegratorSettingsEXC_GRAD::include_weight_derivatives
+ * (include/gauxc/xc_integrator_settings.hpp:28-30; the C entry point gauxc_integrator_eval_exc_grad_rks has no
+ * settings argument and uses the default, true).  exc_grad: 3 * natoms doubles, atom-major. */
+void gauxc_b200_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                             const int64_t n, const double* density_matrix, const int64_t ldp,
+                                             double* exc_grad, int include_weight_derivatives);
 void gauxc_b200_integrator_stats(GauXCStatus* status, const GauXCIntegrator integrator, double* out16);
 void gauxc_b200_integrator_set_profile(GauXCStatus* status, const GauXCIntegrator integrator, int on);
 /* extension: only rank 0 copies VXC back to host memory (default off = the reference's replicated result) */
@@ -371,6 +377,11 @@ void gauxc_b200_radial(GauXCStatus* status, enum GauXC_RadialQuad rq, int n, dou
 void gauxc_b200_eval_collocation(GauXCStatus* status, const GauXCBasisSet basis, int64_t nshells,
                                  const int32_t* shell_list, int64_t npts, const double* points,
                                  double* eval, double* deval_x, double* deval_y, double* deval_z);
+/* the same with second derivatives (the EXC gradient's collocation): hess6 = six more [npts][nbe] arrays
+ * xx, xy, xz, yy, yz, zz (gau2grid_collocation_hessian, .../host/reference/gau2grid_collocation.cxx:153-216) */
+void gauxc_b200_eval_collocation_hessian(GauXCStatus* status, const GauXCBasisSet basis, int64_t nshells,
+                                         const int32_t* shell_list, int64_t npts, const double* points, double* eval,
+                                         double* dx, double* dy, double* dz, double* hess6);
 /* product functional evaluated on the HOST for unit tests of the formulas only (never used
  * by the integrator): out = {eps, vrho, vsigma} per point */
 void gauxc_b200_functional_eval_host(GauXCStatus* status, const GauXCFunctional functional, int64_t npts,

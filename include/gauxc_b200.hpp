@@ -545,6 +545,14 @@ public:
 };
 
 // ---- XC integrator ----------------------------------------------------------------------------------------
+// include/gauxc/xc_integrator_settings.hpp:14-30
+struct IntegratorSettingsXC {
+  virtual ~IntegratorSettingsXC() noexcept = default;
+};
+struct IntegratorSettingsEXC_GRAD : public IntegratorSettingsXC {
+  bool include_weight_derivatives = true;  // grid-weight contribution + translational invariance; false: Hellmann-Feynman
+};
+
 template <typename MatrixType>
 class XCIntegrator {
 public:
@@ -605,6 +613,15 @@ public:
     detail::StatusGuard g;
     gauxc_integrator_eval_exc_grad_rks(&g.st, *h_, (int64_t)P.rows(), (int64_t)P.cols(), P.data(), (int64_t)P.rows(),
                                        grad.data());
+    g.check();
+    return grad;
+  }
+  // with IntegratorSettingsEXC_GRAD (include/gauxc/xc_integrator_settings.hpp:28-30)
+  std::vector<value_type> eval_exc_grad(const MatrixType& P, size_t natoms, const IntegratorSettingsEXC_GRAD& settings) {
+    std::vector<value_type> grad(3 * natoms, 0);
+    detail::StatusGuard g;
+    gauxc_b200_integrator_eval_exc_grad_rks(&g.st, *h_, (int64_t)P.rows(), (int64_t)P.cols(), P.data(),
+                                            (int64_t)P.rows(), grad.data(), settings.include_weight_derivatives ? 1 : 0);
     g.check();
     return grad;
   }

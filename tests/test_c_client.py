@@ -112,3 +112,34 @@ def test_c_client_matches_the_python_binding(client):
     assert abs(exc - exc_c) <= 1e-12 * max(1.0, abs(exc))
     assert np.abs(vxc - vxc_c).max() <= 1e-12
     assert abs(nel_c - integ.stats()["n_el"]) <= 1e-10
+
+
+SRC_ADAPTOR = os.path.join(ROOT, "tests", "c_client", "b200_integrator_adaptor.cpp")
+
+
+@pytest.fixture(scope="module")
+def adaptor(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("adaptor") / "b200_integrator_adaptor")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC_ADAPTOR,
+           "-o", exe, "-L", LIBDIR, "-lgauxc_b200", "-Wl,-rpath," + LIBDIR]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_reference_side_adaptor_compiles_and_fails_loudly_without_a_gpu(adaptor):
+    """INTEGRATION.md 2b: the ReplicatedXCDeviceIntegrator<double>::eval_exc_vxc_ hook implemented over the
+    C ABI (the binding a GauXC maintainer would add), compiled -Werror; no CPU fallback behind it."""
+    if capi.device_count() > 0:
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([adaptor], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "No CUDA device" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_side_adaptor_matches_the_direct_call(adaptor):
+    """The adaptor hands the 'reference' task list (points, SSF weights, shell lists) to the device path through
+    gauxc_b200_load_balancer_set_tasks and must reproduce the direct integrator to 1e-12."""
+    r = subprocess.run([adaptor], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("EXC direct"), r.stdout
