@@ -12,6 +12,7 @@ import gauxc_b200 as gx
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
+SSF_TOL = 1e-10
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -42,7 +43,14 @@ def raw_weights_in_device_order(raw, tasks):
 def ssf_err(w_oracle, w_device, w_raw):
     """SSF weight error, absolute for quadrature weights up to 1 and relative to the UNMODIFIED weight above
     (SuperFine / UltraFine outer radial shells carry raw weights of 1e2-1e3; the device kernel multiplies by a
-    precomputed 1 / R_AB where the host divides, an ulp-level change of mu)."""
+    precomputed 1 / R_AB where the host divides, an ulp-level change of mu).
+
+    Tolerance SSF_TOL = 1e-10, the path's own (BASELINE north_star); the reference's weights test compares with
+    Catch2 Approx (1.2e-5 relative, tests/weights.cxx:58-77).  The weight fraction P_parent / sum_A P_A is
+    ill-conditioned at points far outside the molecule, where ~all atoms compete (|mu_AB| < 0.64 for most pairs):
+    d ln w ~ sum_B s'(mu)/s(mu) d mu with d mu ~ ulp(r) / R_AB ~ 1e-15 over ~1e2 atoms and s'/s up to ~1e2, i.e.
+    1e-11 from a one-ulp difference in the distances (FMA contraction) alone -- measured 1.1e-11 on taxol's
+    SuperFine grid over 171 824 sampled points, 4e-13 typical."""
     return (np.abs(w_oracle - w_device) / np.maximum(1.0, np.abs(w_raw))).max()
 
 
@@ -164,7 +172,7 @@ def test_exc_vxc_golden_and_oracle(orc, benzene_golden, name, func, pruning):
     atoms, shells, P, VXC, EXC = benzene_golden(name, pruning)
     _, basis, lb = make_lb(atoms, shells, "UltraFineGrid", pruning, normalize=False, device=True)
     res = device_run(lb, func, P, orc, atoms)
-    assert res["ssf_err"] < 1e-11
+    assert res["ssf_err"] < SSF_TOL
     assert abs(res["exc"] - EXC) <= TOL
     assert np.abs(res["vxc"] - VXC).max() <= TOL
     assert np.linalg.norm(res["vxc"] - VXC) / basis.nbf() <= TOL
@@ -190,7 +198,7 @@ def test_exc_vxc_configs_vs_oracle(orc, workload, func, grid):
     from gauxc_b200.driver import System
     s = System(workload, device=True, func=func, grid=grid)
     res = device_run(s.lb, func, s.P, orc, s.atoms)
-    assert res["ssf_err"] < 1e-11
+    assert res["ssf_err"] < SSF_TOL
     ref = check_against_oracle(orc, s.basis, s.P, res, func)
     nel = sum(a[0] for a in s.atoms)
     if workload == "benzene":
@@ -206,7 +214,7 @@ def test_taxol_full_grid_vs_oracle(orc):
     raw = s.lb.export_tasks()
     res = device_run(s.lb, s.func_name, s.P)
     err, npts = ssf_sample_error(orc, s.atoms, raw, res["tasks"], 300)
-    assert npts > 10000 and err < 1e-11
+    assert npts > 10000 and err < SSF_TOL
     check_against_oracle(orc, s.basis, s.P, res, s.func_name)
     assert abs(res["nel"] - sum(a[0] for a in s.atoms)) < 0.5  # the synthetic density carries ~Z electrons
 
@@ -223,7 +231,7 @@ def test_large_config_task_sample_vs_oracle(orc, workload, stride, nssf):
     gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(s.lb)
     full = s.lb.export_tasks()
     err, npts = ssf_sample_error(orc, s.atoms, raw, full, nssf)
-    assert npts > 1000 and err < 1e-11
+    assert npts > 1000 and err < SSF_TOL
     del raw
     nt = len(full["npts"])
     pick = np.arange(0, nt, stride)
