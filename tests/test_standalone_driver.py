@@ -22,6 +22,9 @@ def write_fixture(name, path):
     capi.hdf5_write_dataset(path, "/DENSITY", P)
     capi.hdf5_write_dataset(path, "/VXC", VXC)
     capi.hdf5_write_dataset(path, "/EXC", np.array([EXC]))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "benzene_exc_grad.npz"))
+    if f"{name}:EXC_GRAD_FULL" in gold.files:
+        capi.hdf5_write_dataset(path, "/EXC_GRAD_FULL", gold[f"{name}:EXC_GRAD_FULL"])
 
 
 def deck(tmp_path, ref, func, extra=""):
@@ -72,3 +75,18 @@ def test_driver_reproduces_the_reference_fixture(tmp_path, name, func):
     assert abs(nel - 21.0) < 1e-3  # integrate_den of the alpha density: 42 electrons / 2
     m = gx.Molecule.from_hdf5(str(tmp_path / "out.hdf5"))
     assert m.natoms() == 12
+
+
+@pytest.mark.gpu
+def test_driver_exc_gradient_matches_the_reference_fixture(tmp_path):
+    """integrate_exc_grad = TRUE (reference tests/standalone_driver.cxx:495-514, 715-737): the default settings
+    include the weight derivatives, compared with the fixture's /EXC_GRAD_FULL."""
+    name = "benzene_pbe0_cc-pvdz_ufg_ssf"
+    ref = str(tmp_path / "ref.hdf5")
+    write_fixture(name, ref)
+    r = subprocess.run([EXE, deck(tmp_path, ref, "pbe0", "integrate_exc_grad = TRUE")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "| EXC_GRAD (diff) |" in r.stdout
+    g = capi.hdf5_read_dataset(str(tmp_path / "out.hdf5"), "/EXC_GRAD")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "benzene_exc_grad.npz"))[f"{name}:EXC_GRAD_FULL"]
+    assert np.abs(np.asarray(g).reshape(-1, 3) - gold).max() < 1e-10

@@ -300,6 +300,28 @@ int main(int argc, char** argv) {
       std::cout << "EXC Gradient:\n";
       for (size_t a = 0; a < natoms; ++a)
         std::printf("  %4zu %20.12e %20.12e %20.12e\n", a, grad[3 * a], grad[3 * a + 1], grad[3 * a + 2]);
+      // reference (:715-737): norms of /EXC_GRAD and of the difference.  The default IntegratorSettingsEXC_GRAD
+      // includes the weight derivatives, which the fixtures hold as /EXC_GRAD_FULL (tests/xc_integrator.cxx:117-150)
+      const char* gname = has_dataset(ref_file, "/EXC_GRAD_FULL") ? "/EXC_GRAD_FULL"
+                                                                  : (has_dataset(ref_file, "/EXC_GRAD") ? "/EXC_GRAD" : nullptr);
+      if (gname) {
+        detail::StatusGuard gg;
+        int64_t dims[4] = {0, 0, 0, 0};
+        int rank = 0;
+        const int64_t n = gauxc_b200_hdf5_dataset_size(&gg.st, ref_file.c_str(), gname, dims, &rank);
+        gg.check();
+        if (n != (int64_t)(3 * natoms)) throw std::runtime_error("Incorrect dims for EXC_GRAD");
+        std::vector<double> gref((size_t)n);
+        gauxc_b200_hdf5_read_dataset(&gg.st, ref_file.c_str(), gname, gref.data(), n);
+        gg.check();
+        double nr = 0., nc = 0., nd = 0.;
+        for (size_t i = 0; i < gref.size(); ++i) {
+          nr += gref[i] * gref[i]; nc += grad[i] * grad[i]; nd += (gref[i] - grad[i]) * (gref[i] - grad[i]);
+        }
+        std::cout << "| EXC_GRAD (ref)  | = " << std::sqrt(nr) << "\n| EXC_GRAD (calc) | = " << std::sqrt(nc)
+                  << "\n| EXC_GRAD (diff) | = " << std::sqrt(nd) << "   (" << gname << ")\n";
+        if (!(std::sqrt(nd / (3. * natoms)) < 1e-8)) rc = 1;  // tests/xc_integrator.cxx:285
+      }
     }
 
     // ---- OUTFILE (:768-851) ----
@@ -322,6 +344,11 @@ int main(int argc, char** argv) {
         if (uks) write_matrix(out, "/VXC_Z", VXCz);
         const int64_t one[1] = {1};
         gauxc_b200_hdf5_write_dataset(&g.st, out.c_str(), "/EXC", &EXC, one, 1);
+        g.check();
+      }
+      if (!grad.empty()) {
+        const int64_t gd[2] = {(int64_t)natoms, 3};
+        gauxc_b200_hdf5_write_dataset(&g.st, out.c_str(), "/EXC_GRAD", grad.data(), gd, 2);
         g.check();
       }
       if (integrate_den) {
