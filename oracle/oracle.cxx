@@ -1418,4 +1418,156 @@ void oracle_exc_grad(int nshells_total, const int32_t* l, const int32_t* pure, c
   }
 }
 
+
+// UKS EXC gradient (reference_replicated_xc_host_integrator_exc_grad.hpp:107-601 with is_uks): Ps = P_alpha + P_beta,
+// Pz = P_alpha - P_beta, X factor 1.0 (:367), eval_uvvar_{lda,gga}_uks, polarised functional, w_times_f = eps (rho_+ +
+// rho_-) w, the vrhon / vrhoz and four vgamma combinations of :424-436, 482-513.
+void oracle_exc_grad_uks(int nshells_total, const int32_t* l, const int32_t* pure, const int32_t* nprim,
+                         const double* alpha, const double* coeff, const double* origin, const int32_t* shell_to_center,
+                         int natoms, const double* coords, int nbf, const double* Ps, const double* Pz, int ldp,
+                         int ntasks, const int32_t* task_npts, const int32_t* task_nshells, const int32_t* shell_lists,
+                         const int32_t* task_iparent, const double* task_dist_nearest, const double* points,
+                         const double* weights, int nkern, const int* kern, const double* kcoeff, int is_gga,
+                         int include_weight_derivatives, double* EXC_GRAD) {
+  Basis B{nshells_total, l, pure, nprim, alpha, coeff, origin};
+  Func func{};
+  func.nkern = nkern; func.is_gga = is_gga;
+  for (int k = 0; k < nkern; ++k) { func.kern[k] = kern[k]; func.coeff[k] = kcoeff[k]; }
+  std::vector<int> first_ao(nshells_total + 1, 0);
+  for (int s = 0; s < nshells_total; ++s) first_ao[s + 1] = first_ao[s] + B.size(s);
+  std::vector<size_t> poff(ntasks + 1, 0), soff(ntasks + 1, 0);
+  for (int t = 0; t < ntasks; ++t) {
+    poff[t + 1] = poff[t] + task_npts[t];
+    soff[t + 1] = soff[t] + task_nshells[t];
+  }
+  std::vector<double> RAB((size_t)natoms * natoms, 0.);
+  for (int i = 0; i < natoms; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double dx = coords[3 * i] - coords[3 * j], dy = coords[3 * i + 1] - coords[3 * j + 1],
+                   dz = coords[3 * i + 2] - coords[3 * j + 2];
+      RAB[i + (size_t)j * natoms] = RAB[j + (size_t)i * natoms] = std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  for (int i = 0; i < 3 * natoms; ++i) EXC_GRAD[i] = 0.;
+  const int nmat = is_gga ? 10 : 4, nx = is_gga ? 4 : 1;
+  sph_table(0);
+
+#pragma omp parallel
+  {
+    std::vector<double> be, XN, XZ, Psub, den2, gam3, eps, vrho2, vgam3, dd[3];
+    std::vector<int> ao;
+#pragma omp for schedule(dynamic)
+    for (int iT = 0; iT < ntasks; ++iT) {
+      const int npts = task_npts[iT];
+      const int nsh = task_nshells[iT];
+      const int32_t* sl = shell_lists + soff[iT];
+      const double* pts = points + 3 * poff[iT];
+      const double* w = weights + poff[iT];
+      const int iParent = task_iparent[iT];
+      ao.clear();
+      for (int q = 0; q < nsh; ++q)
+        for (int a = first_ao[sl[q]]; a < first_ao[sl[q] + 1]; ++a) ao.push_back(a);
+      const int nbe = (int)ao.size();
+      const size_t nn = (size_t)nbe * npts;
+      be.assign(nmat * nn, 0.);
+      XN.resize(nx * nn); XZ.resize(nx * nn);
+      Psub.resize((size_t)nbe * nbe);
+      den2.assign(2 * (size_t)npts, 0.); gam3.assign(3 * (size_t)npts, 0.); eps.resize(npts);
+      vrho2.assign(2 * (size_t)npts, 0.); vgam3.assign(3 * (size_t)npts, 0.);
+      for (auto& v : dd) v.assign(2 * (size_t)npts, 0.);
+      double* mats[10];
+      for (int k = 0; k < 10; ++k) mats[k] = k < nmat ? be.data() + k * nn : nullptr;
+      if (is_gga) collocation_d2(B, nsh, sl, npts, pts, nbe, mats);
+      else collocation(B, nsh, sl, npts, pts, nbe, true, mats[0], mats[1], mats[2], mats[3]);
+      for (int pass = 0; pass < 2; ++pass) {
+        const double* P = pass == 0 ? Ps : Pz;
+        for (int j = 0; j < nbe; ++j)
+          for (int i = 0; i < nbe; ++i) Psub[i + (size_t)j * nbe] = P[ao[i] + (size_t)ao[j] * ldp];
+        gemm_nn(nbe, nx * npts, nbe, 1.0, Psub.data(), nbe, be.data(), nbe, (pass == 0 ? XN : XZ).data(), nbe);
+      }
+      // eval_uvvar_{lda,gga}_uks
+      for (int i = 0; i < npts; ++i) {
+        const size_t o = (size_t)i * nbe;
+        double rs = 0, rz = 0;
+        for (int m = 0; m < nbe; ++m) { rs += mats[0][o + m] * XN[o + m]; rz += mats[0][o + m] * XZ[o + m]; }
+        den2[2 * i] = 0.5 * (rs + rz);
+        den2[2 * i + 1] = 0.5 * (rs - rz);
+        if (is_gga) {
+          double dn[3], dm[3];
+          for (int c = 0; c < 3; ++c) {
+            double a = 0, b = 0;
+            for (int m = 0; m < nbe; ++m) { a += mats[1 + c][o + m] * XN[o + m]; b += mats[1 + c][o + m] * XZ[o + m]; }
+            dn[c] = 2. * a; dm[c] = 2. * b;
+            dd[c][2 * i] = dn[c]; dd[c][2 * i + 1] = dm[c];
+          }
+          const double dn_sq = dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2];
+          const double dm_sq = dm[0] * dm[0] + dm[1] * dm[1] + dm[2] * dm[2];
+          const double dn_dm = dn[0] * dm[0] + dn[1] * dm[1] + dn[2] * dm[2];
+          gam3[3 * i] = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm;
+          gam3[3 * i + 1] = 0.25 * (dn_sq - dm_sq);
+          gam3[3 * i + 2] = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
+        }
+      }
+      if (is_gga) eval_func_pol_gga(func, npts, den2.data(), gam3.data(), eps.data(), vrho2.data(), vgam3.data());
+      else eval_func_pol_lda(func, npts, den2.data(), eps.data(), vrho2.data());
+      if (include_weight_derivatives) {
+        for (int i = 0; i < npts; ++i) eps[i] *= (den2[2 * i] + den2[2 * i + 1]) * w[i];
+        ssf_weights_1std_contraction(natoms, coords, RAB, iParent, task_dist_nearest[iT], npts, pts, eps.data(),
+                                     EXC_GRAD);
+      }
+      size_t bf_off = 0;
+      for (int ish = 0; ish < nsh; ++ish) {
+        const int sh_idx = sl[ish];
+        const int sh_sz = B.size(sh_idx);
+        const int iAt = shell_to_center[sh_idx];
+        if (iAt == iParent && include_weight_derivatives) { bf_off += sh_sz; continue; }
+        double g[3] = {0, 0, 0};
+        for (int ibf = 0, mu = (int)bf_off; ibf < sh_sz; ++ibf, ++mu)
+          for (int ipt = 0; ipt < npts; ++ipt) {
+            const size_t mu_i = mu + (size_t)ipt * nbe;
+            const double vrhop_ipt = w[ipt] * vrho2[2 * ipt], vrhom_ipt = w[ipt] * vrho2[2 * ipt + 1];
+            const double xN = XN[mu_i], xZ = XZ[mu_i];
+            const double db[3] = {mats[1][mu_i], mats[2][mu_i], mats[3][mu_i]};
+            const double vrhon_ipt = vrhop_ipt + vrhom_ipt, vrhoz_ipt = vrhop_ipt - vrhom_ipt;
+            for (int c = 0; c < 3; ++c) {
+              g[c] += 0.5 * vrhon_ipt * xN * db[c];
+              g[c] += 0.5 * vrhoz_ipt * xZ * db[c];
+            }
+            if (is_gga) {
+              const double vpp = w[ipt] * vgam3[3 * ipt], vpm = w[ipt] * vgam3[3 * ipt + 1],
+                           vmm = w[ipt] * vgam3[3 * ipt + 2];
+              const double dn[3] = {dd[0][2 * ipt], dd[1][2 * ipt], dd[2][2 * ipt]};
+              const double dz[3] = {dd[0][2 * ipt + 1], dd[1][2 * ipt + 1], dd[2][2 * ipt + 1]};
+              const double xNg[3] = {XN[nn + mu_i], XN[2 * nn + mu_i], XN[3 * nn + mu_i]};
+              const double xZg[3] = {XZ[nn + mu_i], XZ[2 * nn + mu_i], XZ[3 * nn + mu_i]};
+              const double H[3][3] = {{mats[4][mu_i], mats[5][mu_i], mats[6][mu_i]},
+                                      {mats[5][mu_i], mats[7][mu_i], mats[8][mu_i]},
+                                      {mats[6][mu_i], mats[8][mu_i], mats[9][mu_i]}};
+              const double d11nn = dn[0] * xNg[0] + dn[1] * xNg[1] + dn[2] * xNg[2];
+              const double d11nz = dn[0] * xZg[0] + dn[1] * xZg[1] + dn[2] * xZg[2];
+              const double d11zn = dz[0] * xNg[0] + dz[1] * xNg[1] + dz[2] * xNg[2];
+              const double d11zz = dz[0] * xZg[0] + dz[1] * xZg[1] + dz[2] * xZg[2];
+              for (int c = 0; c < 3; ++c) {
+                const double d2n = H[c][0] * dn[0] + H[c][1] * dn[1] + H[c][2] * dn[2];
+                const double d2z = H[c][0] * dz[0] + H[c][1] * dz[1] + H[c][2] * dz[2];
+                g[c] += 0.5 * (vpp + vpm + vmm) * (d2n * xN + d11nn * db[c]);
+                g[c] += 0.5 * (vpp - vmm) * (d2z * xN + d11zn * db[c]);
+                g[c] += 0.5 * (vpp - vmm) * (d2n * xZ + d11nz * db[c]);
+                g[c] += 0.5 * (vpp - vpm + vmm) * (d2z * xZ + d11zz * db[c]);
+              }
+            }
+          }
+        for (int k = 0; k < 3; ++k) {
+#pragma omp atomic
+          EXC_GRAD[3 * iAt + k] += -2 * g[k];
+          if (include_weight_derivatives) {
+#pragma omp atomic
+            EXC_GRAD[3 * iParent + k] -= -2 * g[k];
+          }
+        }
+        bf_off += sh_sz;
+      }
+    }
+  }
+}
+
 }  // extern "C"

@@ -142,6 +142,29 @@ def exc_grad(flat_basis, shell_to_center, coords, nbf, P, tasks, func_name, incl
     return g
 
 
+def exc_grad_uks(flat_basis, shell_to_center, coords, nbf, Ps, Pz, tasks, func_name, include_weight_derivatives=True):
+    """UKS EXC gradient [natoms][3], (Ps, Pz) = (P_alpha + P_beta, P_alpha - P_beta)."""
+    l, pure, nprim, alpha, coeff, origin = flat_basis
+    gga, nk, kern, coef = _func(func_name)
+    Psf = np.asfortranarray(np.asarray(Ps, np.float64))
+    Pzf = np.asfortranarray(np.asarray(Pz, np.float64))
+    s2c = np.ascontiguousarray(shell_to_center, np.int32)
+    xyz = np.ascontiguousarray(coords, np.float64)
+    tn = np.ascontiguousarray(tasks["npts"], np.int32)
+    ts = np.ascontiguousarray(tasks["nshells"], np.int32)
+    sl = np.ascontiguousarray(tasks["shell_lists"], np.int32)
+    ip = np.ascontiguousarray(tasks["iParent"], np.int32)
+    dn = np.ascontiguousarray(tasks["dist_nearest"], np.float64)
+    pts = np.ascontiguousarray(tasks["points"], np.float64)
+    w = np.ascontiguousarray(tasks["weights"], np.float64)
+    g = np.zeros((len(xyz), 3))
+    lib().oracle_exc_grad_uks(len(l), _i(l), _i(pure), _i(nprim), _d(alpha), _d(coeff), _d(origin), _i(s2c), len(xyz),
+                              _d(xyz), nbf, _d(Psf), _d(Pzf), Psf.shape[0], len(tn), _i(tn), _i(ts), _i(sl), _i(ip),
+                              _d(dn), _d(pts), _d(w), nk, kern, coef, int(gga), int(bool(include_weight_derivatives)),
+                              _d(g))
+    return g
+
+
 def ssf_weights(coords, task_npts, task_iparent, task_dist_nearest, points, weights):
     coords = np.ascontiguousarray(coords, np.float64)
     tn = np.ascontiguousarray(task_npts, np.int32)

@@ -91,6 +91,13 @@ def conv_grad():
             o[f"{name}:{k}"] = np.asarray(f.array("/" + k), dtype=np.float64).reshape(-1, 3)
         print(name, "grad", o[f"{name}:EXC_GRAD_FULL"].shape, np.abs(o[f"{name}:EXC_GRAD_FULL"]).max())
     np.savez_compressed(f"{OUT}/benzene_exc_grad.npz", **o)
+    o = {}
+    for name in ("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks", "cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks"):
+        f = H5File(f"{REF}/ref_data/{name}.hdf5")
+        for k in ("EXC_GRAD_HELLFEY", "EXC_GRAD_FULL"):
+            o[f"{name}:{k}"] = np.asarray(f.array("/" + k), dtype=np.float64).reshape(-1, 3)
+        print(name, "grad", o[f"{name}:EXC_GRAD_FULL"].shape, np.abs(o[f"{name}:EXC_GRAD_FULL"]).max())
+    np.savez_compressed(f"{OUT}/cytosine_uks_exc_grad.npz", **o)
 
 
 def conv_basis_only(name, out):
