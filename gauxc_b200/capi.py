@@ -106,6 +106,8 @@ def lib():
         "gauxc_integrator_eval_exc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
         "gauxc_integrator_eval_exc_vxc_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, _dp, C.c_int64]),
         "gauxc_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp]),
+        "gauxc_b200_integrator_eval_exc_grad_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
+                                                             _dp, C.c_int]),
         "gauxc_b200_integrator_eval_exc_grad_rks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp,
                                                              C.c_int]),
         "gauxc_integrator_eval_exc_vxc_uks": (None, [S, _Handle, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64,
@@ -559,6 +561,19 @@ class XCIntegrator(_Obj):
             _call("gauxc_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g))
         else:
             _call("gauxc_b200_integrator_eval_exc_grad_rks", self.h, m, n, _d(Pf), m, _d(g),
+                  int(bool(include_weight_derivatives)))
+        return g.reshape(natoms, 3)
+
+    def eval_exc_grad_uks(self, Ps, Pz, natoms, include_weight_derivatives=None):
+        """UKS EXC gradient [natoms][3], (Ps, Pz) = (P_alpha + P_beta, P_alpha - P_beta)."""
+        Psf = np.asfortranarray(np.asarray(Ps, dtype=np.float64))
+        Pzf = np.asfortranarray(np.asarray(Pz, dtype=np.float64))
+        m, n = Psf.shape
+        g = np.zeros(3 * natoms)
+        if include_weight_derivatives is None:
+            _call("gauxc_integrator_eval_exc_grad_uks", self.h, m, n, _d(Psf), m, _d(Pzf), m, _d(g))
+        else:
+            _call("gauxc_b200_integrator_eval_exc_grad_uks", self.h, m, n, _d(Psf), m, _d(Pzf), m, _d(g),
                   int(bool(include_weight_derivatives)))
         return g.reshape(natoms, 3)
 

@@ -138,16 +138,17 @@ __global__ void __launch_bounds__(TP) collocation_hessian_kernel(PlanView pv, co
 // ------------------------------------------------------------------------------------------------
 constexpr int EG_THREADS = 256;
 
-template <bool GGA>
+template <bool GGA, bool UKS>
 __global__ void __launch_bounds__(EG_THREADS)
 exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
                 const double* __restrict__ ws, FunctionalDesc func, const int* __restrict__ shell_atom, int natoms,
                 int include_wd, double* __restrict__ wf_out, double* __restrict__ grad, int smem_acc) {
   extern __shared__ double eg_dyn[];  // smem_acc: 3 natoms accumulators
-  __shared__ double part[2][4][TP];
+  __shared__ double part[2][UKS ? 8 : 4][TP];
   __shared__ int s_tile;
   const int tid = threadIdx.x, p = tid & (TP - 1), h = tid >> 7, lane = tid & 31;
   constexpr int NB = GGA ? 10 : 4;  // basis matrices ahead of X
+  constexpr int NX = GGA ? 4 : 1;   // X matrices per density (UKS: XN block, then XZ block)
   if (smem_acc)
     for (int q = tid; q < 3 * natoms; q += EG_THREADS) eg_dyn[q] = 0.;
   __syncthreads();
@@ -172,20 +173,37 @@ exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int*
 
     // ---- phase A
     double r0 = 0., r1 = 0., r2 = 0., r3 = 0.;
+    double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;  // UKS: the same sums with X of Pz
     if (ok) {
 #pragma unroll 4
       for (int mu = h; mu < nbe; mu += 2) {
         const double x = at(NB, mu);
-        r0 = fma(at(0, mu), x, r0);
+        const double b0 = at(0, mu);
+        r0 = fma(b0, x, r0);
+        double b1 = 0., b2 = 0., b3 = 0.;
         if (GGA) {
-          r1 = fma(at(1, mu), x, r1);
-          r2 = fma(at(2, mu), x, r2);
-          r3 = fma(at(3, mu), x, r3);
+          b1 = at(1, mu); b2 = at(2, mu); b3 = at(3, mu);
+          r1 = fma(b1, x, r1);
+          r2 = fma(b2, x, r2);
+          r3 = fma(b3, x, r3);
+        }
+        if (UKS) {
+          const double xz = at(NB + NX, mu);
+          q0 = fma(b0, xz, q0);
+          if (GGA) {
+            q1 = fma(b1, xz, q1);
+            q2 = fma(b2, xz, q2);
+            q3 = fma(b3, xz, q3);
+          }
         }
       }
     }
     part[h][0][p] = r0;
     if (GGA) { part[h][1][p] = r1; part[h][2][p] = r2; part[h][3][p] = r3; }
+    if (UKS) {
+      part[h][4][p] = q0;
+      if (GGA) { part[h][5][p] = q1; part[h][6][p] = q2; part[h][7][p] = q3; }
+    }
     __syncthreads();
     const double rho = part[0][0][p] + part[1][0][p];
     double dx = 0., dy = 0., dz = 0.;
@@ -194,13 +212,48 @@ exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int*
       dy = 2. * (part[0][2][p] + part[1][2][p]);
       dz = 2. * (part[0][3][p] + part[1][3][p]);
     }
-    double wv = 0., wg = 0.;
+    double rho_z = 0., mx = 0., my = 0., mz = 0.;  // UKS: rho = rho_s, (dx, dy, dz) = grad n, (mx, my, mz) = grad M_z
+    if (UKS) {
+      rho_z = part[0][4][p] + part[1][4][p];
+      if (GGA) {
+        mx = 2. * (part[0][5][p] + part[1][5][p]);
+        my = 2. * (part[0][6][p] + part[1][6][p]);
+        mz = 2. * (part[0][7][p] + part[1][7][p]);
+      }
+    }
+    // RKS: wv = w vrho, wg = w vgamma.  UKS (:424-436, 482-513): wv = 1/2 w (v+ + v-), wvz = 1/2 w (v+ - v-),
+    // c1 = 1/2 w (v++ + v+- + v--), c2 = 1/2 w (v++ - v--), c3 = 1/2 w (v++ - v+- + v--)
+    double wv = 0., wg = 0., wvz = 0., c2 = 0., c3 = 0.;
     if (ok) {
       const double w = pv.w[tile.pt_off + p];
-      const XcOut xc = eval_functional(func, rho, GGA ? dx * dx + dy * dy + dz * dz : 0.);
-      wv = w * xc.vrho;
-      wg = w * xc.vsigma;
-      if (include_wd && h == 0) wf_out[tile.pt_off + p] = xc.eps * (rho * w);  // eps *= den * w (:396-399)
+      double eps;
+      if (!UKS) {
+        const XcOut xc = eval_functional(func, rho, GGA ? dx * dx + dy * dy + dz * dz : 0.);
+        wv = w * xc.vrho;
+        wg = w * xc.vsigma;
+        eps = xc.eps;
+      } else if (GGA) {
+        const double dn_sq = dx * dx + dy * dy + dz * dz, dm_sq = mx * mx + my * my + mz * mz,
+                     dn_dm = dx * mx + dy * my + dz * mz;
+        const double gpp = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm, gpm = 0.25 * (dn_sq - dm_sq),
+                     gmm = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
+        const XcOutPolGga xc = eval_functional_pol(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z), gpp, gpm, gmm);
+        const double vp = w * xc.va, vm = w * xc.vb;
+        wv = 0.5 * (vp + vm);
+        wvz = 0.5 * (vp - vm);
+        const double vpp = w * xc.vaa, vpm = w * xc.vab, vmm = w * xc.vbb;
+        wg = 0.5 * (vpp + vpm + vmm);
+        c2 = 0.5 * (vpp - vmm);
+        c3 = 0.5 * (vpp - vpm + vmm);
+        eps = xc.eps;
+      } else {
+        const XcOutPol xc = eval_functional_pol_lda(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z));
+        const double vp = w * xc.va, vm = w * xc.vb;
+        wv = 0.5 * (vp + vm);
+        wvz = 0.5 * (vp - vm);
+        eps = xc.eps;
+      }
+      if (include_wd && h == 0) wf_out[tile.pt_off + p] = eps * (rho * w);  // eps *= den * w (:396-399)
     }
 
     // ---- phase B
@@ -235,21 +288,39 @@ exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int*
       const int bf1 = s + 1 < task.nshells ? __ldg(pv.task_shell_bf + task.shell_off + s + 1) : nbe;
       for (int mu = bf0 + ((bf0 ^ h) & 1); mu < bf1; mu += 2) {
         const double xn = at(NB, mu);
+        const double xz = UKS ? at(NB + NX, mu) : 0.;
         const double dbx = at(1, mu), dby = at(2, mu), dbz = at(3, mu);
-        const double a = wv * xn;
+        const double a = UKS ? wv * xn + wvz * xz : wv * xn;
         acc[0] = fma(a, dbx, acc[0]);
         acc[1] = fma(a, dby, acc[1]);
         acc[2] = fma(a, dbz, acc[2]);
         if (GGA) {
-          const double xx = at(4, mu), xy = at(5, mu), xz = at(6, mu), yy = at(7, mu), yz = at(8, mu), zz = at(9, mu);
-          const double d2x = xx * dx + xy * dy + xz * dz;
+          const double xx = at(4, mu), xy = at(5, mu), xzz = at(6, mu), yy = at(7, mu), yz = at(8, mu), zz = at(9, mu);
+          const double d2x = xx * dx + xy * dy + xzz * dz;
           const double d2y = xy * dx + yy * dy + yz * dz;
-          const double d2z = xz * dx + yz * dy + zz * dz;
-          const double d11 = dx * at(NB + 1, mu) + dy * at(NB + 2, mu) + dz * at(NB + 3, mu);
-          const double g2 = 2. * wg;
-          acc[0] += g2 * (xn * d2x + dbx * d11);
-          acc[1] += g2 * (xn * d2y + dby * d11);
-          acc[2] += g2 * (xn * d2z + dbz * d11);
+          const double d2z = xzz * dx + yz * dy + zz * dz;
+          const double xnx = at(NB + 1, mu), xny = at(NB + 2, mu), xnz = at(NB + 3, mu);
+          const double d11 = dx * xnx + dy * xny + dz * xnz;
+          if (!UKS) {
+            const double g2 = 2. * wg;
+            acc[0] += g2 * (xn * d2x + dbx * d11);
+            acc[1] += g2 * (xn * d2y + dby * d11);
+            acc[2] += g2 * (xn * d2z + dbz * d11);
+          } else {
+            const double e2x = xx * mx + xy * my + xzz * mz;  // H grad M_z
+            const double e2y = xy * mx + yy * my + yz * mz;
+            const double e2z = xzz * mx + yz * my + zz * mz;
+            const double xzx = at(NB + NX + 1, mu), xzy = at(NB + NX + 2, mu), xzz_ = at(NB + NX + 3, mu);
+            const double d11nz = dx * xzx + dy * xzy + dz * xzz_;
+            const double d11zn = mx * xnx + my * xny + mz * xnz;
+            const double d11zz = mx * xzx + my * xzy + mz * xzz_;
+            // c1 (d2n xN + d11nn db) + c2 (d2z xN + d11zn db) + c2 (d2n xZ + d11nz db) + c3 (d2z xZ + d11zz db)
+            const double sx = wg * xn + c2 * xz, tx = c2 * xn + c3 * xz;  // multiply d2n resp. d2z
+            const double sd = wg * d11 + c2 * (d11zn + d11nz) + c3 * d11zz;
+            acc[0] += sx * d2x + tx * e2x + sd * dbx;
+            acc[1] += sx * d2y + tx * e2y + sd * dby;
+            acc[2] += sx * d2z + tx * e2z + sd * dbz;
+          }
         }
       }
     }
@@ -507,8 +578,8 @@ void launch_collocation_hessian(const PlanView& pv, const DevTile* tiles, int nt
 }
 
 cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                            const double* ws, FunctionalDesc func, bool gga, const int* shell_atom, int natoms,
-                            bool include_wd, double* wf_out, double* grad, cudaStream_t s) {
+                            const double* ws, FunctionalDesc func, bool gga, bool uks, const int* shell_atom,
+                            int natoms, bool include_wd, double* wf_out, double* grad, cudaStream_t s) {
   if (ntiles <= 0) return cudaSuccess;
   const size_t dyn = (size_t)3 * natoms * sizeof(double);
   const bool smem_acc = dyn <= 160 * 1024;
@@ -522,7 +593,8 @@ cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles
                                                       include_wd ? 1 : 0, wf_out, grad, smem_acc ? 1 : 0);
     return cudaGetLastError();
   };
-  return gga ? launch(exc_grad_kernel<true>) : launch(exc_grad_kernel<false>);
+  if (uks) return gga ? launch(exc_grad_kernel<true, true>) : launch(exc_grad_kernel<false, true>);
+  return gga ? launch(exc_grad_kernel<true, false>) : launch(exc_grad_kernel<false, false>);
 }
 
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,

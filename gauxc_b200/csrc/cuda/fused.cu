@@ -150,7 +150,8 @@ __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* 
 // XOUT (EXC gradient, eval_xmat of reference_replicated_xc_host_integrator_exc_grad.hpp:370-373): the kernel only
 // forms X = 2 A P_sub for ONE matrix A of the tile (B or one of dB/dx, dB/dy, dB/dz) and the density warps write it
 // to another matrix slot of the tile instead of contracting it -- the gradient kernel (exc_grad.cu) needs X itself.
-// The two slots travel in uks_stride (unused for SPIN == 0): low 16 bits = A, next 16 bits = X slot.
+// The two slots travel in uks_stride (unused for SPIN == 0): low 16 bits = A, next 16 bits = X slot, bit 32 set = UKS
+// (eval_xmat factor 1.0 instead of the RKS 2.0).
 template <bool GGA, int SPIN, bool DUAL, bool XOUT = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
@@ -368,6 +369,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       const bool lane_on = p4 < tile_width(tile.npts);  // columns beyond the tile width do not exist
       if (XOUT) {
         double* __restrict__ Xo = ws + tile.ws_off + (size_t)((uks_stride >> 16) & 0xffff) * ms + cofs;
+        const double xfac = ((uks_stride >> 32) & 1) ? 1. : 2.;  // eval_xmat fac: RKS 2, UKS 1
         for (int c = 0; c < nn; ++c) {
           const int n0 = c * FN;
           const int ncols = lane_on ? min(FN, nbe - n0) : 0;
@@ -376,7 +378,7 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
             double x[4];
             lds4(x, &S.X[n][p4]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] *= 2.;  // eval_xmat fac = 2 (RKS)
+            for (int j = 0; j < 4; ++j) x[j] *= xfac;
             stg256(Xo + (size_t)(n0 + n) * TP, x);
           }
           mbar_arrive(&S.xempty);

@@ -21,7 +21,8 @@ void launch_collocation(const PlanView& pv, const DevTile* tiles, int ntiles, do
 //      func.nkern == 0: density only (integrate_den).  spin 1 / 2: the two UKS passes (Ps then Pz),
 //      uks_den: 1 (LDA) or 4 (GGA) arrays of uks_stride doubles carried between them.
 //      spin 3 (EXC gradient): X = 2 A P_sub only, A = matrix (uks_stride & 0xffff) of the tile, written to matrix
-//      ((uks_stride >> 16) & 0xffff) of the tile; no density, functional or Z.
+//      ((uks_stride >> 16) & 0xffff) of the tile (bit 32 of uks_stride: factor 1 instead of 2, UKS); no density,
+//      functional or Z.
 cudaError_t launch_fused(const TmapSet& tmapA, const PlanView& pv, const DevTile* tiles, int ntiles,
                          int* counter, int ncta, double* ws, const double* P, int ldp,
                          FunctionalDesc func, double* exc_part, double* nel_part, int part_off,
@@ -42,9 +43,10 @@ void launch_collocation_hessian(const PlanView& pv, const DevTile* tiles, int nt
 //   gradient assembly over tiles holding [B dx dy dz | X] (LDA) or [B dx dy dz xx xy xz yy yz zz | X Xx Xy Xz] (GGA);
 //   shell_atom: shell -> atom; include_wd: skip the parent atom's shells, give the parent the opposite sum and
 //   write wf_out[point] = w eps rho for the weight-derivative kernel; grad: 3 natoms, accumulated
+//   uks: tiles hold [.. | XN .. | XZ ..] (X of Ps and of Pz, factor 1) and func is a polarised functional
 cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                            const double* ws, FunctionalDesc func, bool gga, const int* shell_atom, int natoms,
-                            bool include_wd, double* wf_out, double* grad, cudaStream_t s);
+                            const double* ws, FunctionalDesc func, bool gga, bool uks, const int* shell_atom,
+                            int natoms, bool include_wd, double* wf_out, double* grad, cudaStream_t s);
 //   SSF weight derivatives contracted with wf, accumulated into grad (cudaErrorInvalidConfiguration: too many atoms
 //   for the shared-memory lists)
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,

@@ -514,9 +514,19 @@ void gauxc_integrator_eval_exc_vxc_gks(GauXCStatus* status, const GauXCIntegrato
                                        double*, const int64_t, double*, const int64_t, double*, const int64_t) {
   GAUXC_B200_NYI("GKS EXC/VXC")
 }
-void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
-                                        const double*, const int64_t, const double*, const int64_t, double*) {
-  GAUXC_B200_NYI("UKS EXC Gradient")
+void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                        const int64_t n, const double* Ps, const int64_t ldps, const double* Pz,
+                                        const int64_t ldpz, double* exc_grad) {
+  C_TRY(status)
+  INTG(integrator)->eval_exc_grad_uks(m, n, Ps, ldps, Pz, ldpz, exc_grad);
+  C_CATCH(status)
+}
+void gauxc_b200_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                             const int64_t n, const double* Ps, const int64_t ldps, const double* Pz,
+                                             const int64_t ldpz, double* exc_grad, int include_weight_derivatives) {
+  C_TRY(status)
+  INTG(integrator)->eval_exc_grad_uks(m, n, Ps, ldps, Pz, ldpz, exc_grad, include_weight_derivatives != 0);
+  C_CATCH(status)
 }
 void gauxc_integrator_eval_exx_rks(GauXCStatus* status, const GauXCIntegrator, const int64_t, const int64_t,
                                    const double*, const int64_t, double*, const int64_t) {

@@ -413,7 +413,7 @@ static std::shared_ptr<Schedule> build_schedule(DevicePlan& plan, int nmat, size
   sc->ws_doubles = ws_max;
   sc->d_tiles.upload(sc->tiles);
   sc->d_items.upload(sc->items);
-  sc->d_counters.alloc(std::max<size_t>(1, 8 * sc->batches.size()));  // queue heads: fused, vxc (UKS: several each)
+  sc->d_counters.alloc(std::max<size_t>(1, 12 * sc->batches.size()));  // queue heads: fused, vxc (UKS: several each); EXC gradient: up to 8 X passes + 2
   CUDA_CHECK(cudaDeviceSynchronize());
   return sc;
 }
@@ -1178,8 +1178,21 @@ void XCIntegrator::eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t 
 // ranks on the device (the reference refuses a device reduction here: "Device Reduction + EXC Grad NYI").
 void XCIntegrator::eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD,
                                  bool include_weight_derivatives) {
-  check_dims(*lb_, m, n, ldp, 0, false);
   if (func_->polarized) GAUXC_GENERIC_EXCEPTION("RKS Evaluation Requires An Unpolarized Functional");
+  eval_exc_grad_(m, n, P, ldp, nullptr, 0, EXC_GRAD, include_weight_derivatives);
+}
+// UKS: Ps = P_alpha + P_beta, Pz = P_alpha - P_beta (the (Ps, Pz) overload of eval_exc_grad_, :75-131); X of both
+// densities with factor 1, the polarised functional, the vrho_n / vrho_z and four vgamma combinations of the host loop
+void XCIntegrator::eval_exc_grad_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz,
+                                     int64_t ldpz, double* EXC_GRAD, bool include_weight_derivatives) {
+  if (!func_->polarized) GAUXC_GENERIC_EXCEPTION("UKS Evaluation Requires A Polarized Functional");
+  if (!Pz) GAUXC_GENERIC_EXCEPTION("Invalid LDPZ");
+  check_dims(*lb_, m, n, ldpz, 0, false);
+  eval_exc_grad_(m, n, Ps, ldps, Pz, ldpz, EXC_GRAD, include_weight_derivatives);
+}
+void XCIntegrator::eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t ldp, const double* Pz, int64_t ldpz,
+                                  double* EXC_GRAD, bool include_weight_derivatives) {
+  check_dims(*lb_, m, n, ldp, 0, false);
   if (!lb_->state().modified_weights_are_stored) GAUXC_GENERIC_EXCEPTION("Weights Have Not Been Modified");
   if (include_weight_derivatives && lb_->state().weight_alg != XCWeightAlg::SSF)
     GAUXC_GENERIC_EXCEPTION("Weight Alg Not Supported");
@@ -1187,11 +1200,13 @@ void XCIntegrator::eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t 
   const size_t nbf = (size_t)m;
   cudaStream_t s = I.stream;
   const bool gga = func_->is_gga();
-  const int nb = gga ? 10 : 4, nx = gga ? 4 : 1, nmat = nb + nx;
-  I.ensure_matrices(nbf, red_->comm_size(), false);
+  const bool uks = Pz != nullptr;
+  const int nb = gga ? 10 : 4, nx = gga ? 4 : 1, nden = uks ? 2 : 1, nmat = nb + nden * nx;
+  I.ensure_matrices(nbf, red_->comm_size(), uks);
   CUDA_CHECK(cudaEventRecord(I.e_begin, s));
   CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
   upload_density_(P, ldp, I.dP.p, nbf);
+  if (uks) upload_density_(Pz, ldpz, I.dPz.p, nbf);
   CUDA_CHECK(cudaEventRecord(I.e_p_ready, I.copy_stream));
   I.prepare(*lb_, nmat, false);
   auto& plan = *I.plan;
@@ -1212,20 +1227,24 @@ void XCIntegrator::eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t 
     if (gga) gxb::launch_collocation_hessian(pv, tl, nt, I.d_ws.p, s);
     else gxb::launch_collocation(pv, tl, nt, I.d_ws.p, true, s);
     if (ib == 0) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));  // the upload of P hides behind the collocation
-    for (int k = 0; k < nx; ++k)
-      CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + k * nbatch + ib, sc.ncta, I.d_ws.p, I.dP.p,
-                                   inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p, b.tile_begin, s, 3, nullptr,
-                                   (size_t)k | ((size_t)(nb + k) << 16)));
-    CUDA_CHECK(gxb::launch_exc_grad(pv, tl, nt, sc.d_counters.p + 4 * nbatch + ib, sc.ncta, I.d_ws.p, func_->desc, gga,
-                                    plan.d_shell_center.p, natoms, include_weight_derivatives,
+    for (int d = 0; d < nden; ++d)
+      for (int k = 0; k < nx; ++k) {
+        const int q = d * nx + k;  // X slot nb + q; queue head q of this batch
+        CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + q * nbatch + ib, sc.ncta, I.d_ws.p,
+                                     d == 0 ? I.dP.p : I.dPz.p, inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p,
+                                     b.tile_begin, s, 3, nullptr,
+                                     (size_t)k | ((size_t)(nb + q) << 16) | ((size_t)(uks ? 1 : 0) << 32)));
+      }
+    CUDA_CHECK(gxb::launch_exc_grad(pv, tl, nt, sc.d_counters.p + 8 * nbatch + ib, sc.ncta, I.d_ws.p, func_->desc, gga,
+                                    uks, plan.d_shell_center.p, natoms, include_weight_derivatives,
                                     include_weight_derivatives ? I.d_wf.p : nullptr, I.d_grad.p, s));
-    launches += 2 + nx;
+    launches += 2 + nden * nx;
     ++ib;
   }
   if (sc.batches.empty()) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
   if (include_weight_derivatives && !plan.tiles.empty()) {
     const cudaError_t e = gxb::launch_ssf_weight_grad(pv, plan.d_tiles.p, (int)plan.tiles.size(),
-                                                      sc.d_counters.p + 5 * nbatch, sc.ncta, plan.d_atoms.p,
+                                                      sc.d_counters.p + 9 * nbatch, sc.ncta, plan.d_atoms.p,
                                                       plan.d_dist_nearest.p, natoms, I.d_wf.p, I.d_grad.p, s);
     if (e == cudaErrorInvalidConfiguration)
       GAUXC_GENERIC_EXCEPTION("SSF Weight Derivatives NYI in B200 path for this many atoms");

@@ -105,6 +105,8 @@ class XCIntegrator {
 
   void reduce_and_symmetrize_(double* dV, double* dVz, double* d_out2, int nbf, bool do_vxc);
   void upload_density_(const double* P, int64_t ldp, double* dP, size_t nbf);
+  void eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t ldp, const double* Pz, int64_t ldpz,
+                      double* EXC_GRAD, bool include_weight_derivatives);
   void eval_uks_(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
                  double* VXCs, int64_t ldvxcs, double* VXCz, int64_t ldvxcz, double* EXC, bool do_vxc);
 
@@ -128,6 +130,8 @@ public:
   // the grid-weight contribution and translational invariance; false = Hellmann-Feynman-like gradient
   void eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD,
                      bool include_weight_derivatives = true);
+  void eval_exc_grad_uks(int64_t m, int64_t n, const double* Ps, int64_t ldps, const double* Pz, int64_t ldpz,
+                         double* EXC_GRAD, bool include_weight_derivatives = true);
   void integrate_den(int64_t m, int64_t n, const double* P, int64_t ldp, double* N_EL);
   // device-resident variant: dP (nbf x nbf, ld nbf) and dVXC live in HBM, out2 = {EXC, N_EL}
   // device scalars; no host<->device traffic in the call.

@@ -364,6 +364,10 @@ void gauxc_b200_load_balancer_set_tasks(GauXCStatus* status, GauXCLoadBalancer l
 void gauxc_b200_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
                                              const int64_t n, const double* density_matrix, const int64_t ldp,
                                              double* exc_grad, int include_weight_derivatives);
+void gauxc_b200_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                             const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                             const double* density_matrix_z, const int64_t ldp_z, double* exc_grad,
+                                             int include_weight_derivatives);
 void gauxc_b200_integrator_stats(GauXCStatus* status, const GauXCIntegrator integrator, double* out16);
 void gauxc_b200_integrator_set_profile(GauXCStatus* status, const GauXCIntegrator integrator, int on);
 /* extension: only rank 0 copies VXC back to host memory (default off = the reference's replicated result) */

@@ -616,6 +616,17 @@ public:
     g.check();
     return grad;
   }
+  // UKS (include/gauxc/xc_integrator.hpp eval_exc_grad(Ps, Pz))
+  std::vector<value_type> eval_exc_grad(const MatrixType& Ps, const MatrixType& Pz, size_t natoms,
+                                        const IntegratorSettingsEXC_GRAD& settings = IntegratorSettingsEXC_GRAD{}) {
+    std::vector<value_type> grad(3 * natoms, 0);
+    detail::StatusGuard g;
+    gauxc_b200_integrator_eval_exc_grad_uks(&g.st, *h_, (int64_t)Ps.rows(), (int64_t)Ps.cols(), Ps.data(),
+                                            (int64_t)Ps.rows(), Pz.data(), (int64_t)Pz.rows(), grad.data(),
+                                            settings.include_weight_derivatives ? 1 : 0);
+    g.check();
+    return grad;
+  }
   // with IntegratorSettingsEXC_GRAD (include/gauxc/xc_integrator_settings.hpp:28-30)
   std::vector<value_type> eval_exc_grad(const MatrixType& P, size_t natoms, const IntegratorSettingsEXC_GRAD& settings) {
     std::vector<value_type> grad(3 * natoms, 0);

@@ -216,7 +216,9 @@ def test_taxol_full_grid_vs_oracle(orc):
     err, npts = ssf_sample_error(orc, s.atoms, raw, res["tasks"], 300)
     assert npts > 10000 and err < SSF_TOL
     check_against_oracle(orc, s.basis, s.P, res, s.func_name)
-    assert abs(res["nel"] - sum(a[0] for a in s.atoms)) < 0.5  # the synthetic density carries ~Z electrons
+    # the synthetic SAD-like density is not normalised: it carries Z electrons to ~10 % (489.86 of 446 on this grid);
+    # N_el itself is compared with the oracle at 1e-10 above
+    assert abs(res["nel"] / sum(a[0] for a in s.atoms) - 1.0) < 0.2
 
 
 @pytest.mark.parametrize("workload,stride,nssf", [("ubiquitin", 20, 100), ("water833", 50, 40)])
@@ -601,3 +603,43 @@ def test_exc_grad_taxol_sample_vs_oracle(orc):
                          include_weight_derivatives=wd)
         print("taxol sample grad wd", wd, "max diff", np.abs(g - o).max(), "max", np.abs(o).max())
         assert np.abs(g - o).max() < TOL
+
+
+@pytest.mark.parametrize("name,func", [("cytosine_svwn5_cc-pvdz_ufg_ssf_robust_uks", "SVWN5"),
+                                        ("cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks", "BLYP")])
+def test_exc_grad_uks_golden_and_oracle(orc, name, func):
+    """UKS EXC gradient (reference tests/xc_integrator.cxx:276-297 with (Ps, Pz)) on the cytosine fixtures: Device
+    against the oracle on the same tasks (1e-10) and against /EXC_GRAD_FULL (1e-10; the fixtures' Hellmann-Feynman
+    vectors sit 2.8e-9 from the oracle for both functionals, inside the reference's 1e-8 -- tests/test_oracle_golden.py)."""
+    import os
+    d = systems.golden(name)
+    atoms = [(int(Z), *xyz) for Z, xyz in zip(d["mol_Z"], d["mol_xyz"])]
+    shells = []
+    for i in range(len(d["sh_l"])):
+        n = int(d["sh_nprim"][i])
+        shells.append(dict(l=int(d["sh_l"][i]), pure=bool(d["sh_pure"][i]), exps=list(d["sh_alpha"][i, :n]),
+                           coefs=list(d["sh_coeff"][i, :n]), origin=tuple(d["sh_O"][i]), tol=np.finfo(float).eps))
+    _, basis, lb = make_lb(atoms, shells, "UltraFineGrid", "Robust", normalize=False, device=True)
+    gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(lb)
+    tasks = lb.export_tasks()
+    integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func, polarized=True), lb)
+    Ps, Pz = d["DENSITY_SCALAR"], d["DENSITY_Z"]
+    coords = np.array([a[1:] for a in atoms])
+    s2c = shell_centers(atoms, basis)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cytosine_uks_exc_grad.npz"))
+    na = len(atoms)
+    for key, wd in (("EXC_GRAD_HELLFEY", False), ("EXC_GRAD_FULL", True)):
+        g = integ.eval_exc_grad_uks(Ps, Pz, na, include_weight_derivatives=wd)
+        o = orc.exc_grad_uks(basis.flat(), s2c, coords, basis.nbf(), Ps, Pz, tasks, func, include_weight_derivatives=wd)
+        ref = gold[f"{name}:{key}"]
+        print(name, key, "vs fixture", np.abs(g - ref).max(), "vs oracle", np.abs(g - o).max())
+        assert np.abs(g - o).max() < TOL
+        assert np.linalg.norm(g - ref) / np.sqrt(3 * na) < (TOL if wd else 1e-8)
+    assert np.abs(integ.eval_exc_grad_uks(Ps, Pz, na) - g).max() < 1e-12  # the reference's C entry point: full gradient
+    # spin-unpolarised limit: Pz = 0 reproduces the RKS gradient of Ps / 2
+    g0 = integ.eval_exc_grad_uks(Ps, np.zeros_like(Pz), na, include_weight_derivatives=True)
+    rks = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func), lb)
+    gr = rks.eval_exc_grad(0.5 * Ps, na, include_weight_derivatives=True)
+    assert np.abs(g0 - gr).max() < TOL
+    with pytest.raises(gx.GauXCError, match="Requires A Polarized Functional"):
+        rks.eval_exc_grad_uks(Ps, Pz, na)

@@ -267,7 +267,7 @@ int main(int argc, char** argv) {
     }
     std::vector<double> grad;
     if (integrate_exc_grad) {
-      if (uks) std::cout << "  (UKS EXC gradient is NYI: skipped)\n";
+      if (uks) grad = integrator.eval_exc_grad(P, Pz, natoms);
       else grad = integrator.eval_exc_grad(P, natoms);
     }
 
