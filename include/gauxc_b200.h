@@ -255,6 +255,10 @@ void gauxc_integrator_eval_exc_grad_rks(GauXCStatus* status, const GauXCIntegrat
 void gauxc_integrator_eval_exc_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
                                    const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
                                    const double* density_matrix_z, const int64_t ldp_z, double* exc);
+/* include/gauxc/c/xc_integrator.h:304-314: UKS EXC gradient (default settings: weight derivatives included) */
+void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
+                                        const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
+                                        const double* density_matrix_z, const int64_t ldp_z, double* exc_grad);
 /* include/gauxc/c/xc_integrator.h:124-365, outside the LDA/GGA RKS/UKS path: exported for link
  * compatibility, every call returns status code 1 with a "... NYI in B200 path" message. */
 void gauxc_integrator_eval_exc_gks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
@@ -270,9 +274,6 @@ void gauxc_integrator_eval_exc_vxc_gks(GauXCStatus* status, const GauXCIntegrato
                                        double* vxc_matrix_s, const int64_t vxc_ld_s, double* vxc_matrix_z,
                                        const int64_t vxc_ld_z, double* vxc_matrix_y, const int64_t vxc_ld_y,
                                        double* vxc_matrix_x, const int64_t vxc_ld_x);
-void gauxc_integrator_eval_exc_grad_uks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
-                                        const int64_t n, const double* density_matrix_s, const int64_t ldp_s,
-                                        const double* density_matrix_z, const int64_t ldp_z, double* exc_grad);
 void gauxc_integrator_eval_exx_rks(GauXCStatus* status, const GauXCIntegrator integrator, const int64_t m,
                                    const int64_t n, const double* density_matrix, const int64_t ldp, double* K,
                                    const int64_t ldk);

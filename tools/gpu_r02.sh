@@ -37,6 +37,9 @@ for ST in "$@"; do
     lib)   # bench:<workload> with the diagnostic library variant <B>
       GAUXC_B200_LIB=$PWD/gauxc_b200/libgauxc_b200_$B.so timeout 900 python bench.py --workload $A --steps 3 --warmup 2 --others "" --no-cpu-baseline --parity-seconds 1 > gpurun_out/${TAG}_lib${B}_${A}.json 2> gpurun_out/${TAG}_lib${B}_${A}.err
       echo "lib $B $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_lib${B}_${A}.json | head -3 ;;
+    fast)  # bench:<workload>[:steps] without the CPU baseline and with a 2 s parity sample
+      timeout 900 python bench.py --workload $A --steps ${B:-3} --warmup 3 --others "" --no-cpu-baseline --parity-seconds 2 > gpurun_out/${TAG}_fast_${A}.json 2> gpurun_out/${TAG}_fast_${A}.err
+      echo "fast $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_fast_${A}.json | head -4; tail -3 gpurun_out/${TAG}_fast_${A}.err ;;
     grad)
       timeout 900 python tools/grad_report.py > gpurun_out/${TAG}_exc_grad.txt 2>&1; echo "grad exit $?"; cat gpurun_out/${TAG}_exc_grad.txt ;;
     *) echo "unknown stage $ST" ;;
