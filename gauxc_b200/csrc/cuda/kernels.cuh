@@ -64,10 +64,10 @@ void launch_unpack_tril_sym(const double* in, double* A, int n, int ld, cudaStre
 void launch_sym_half(const double* P, int ldp, double* out, int nbf, cudaStream_t s);
 
 // SSF weights (in place on pv.w)
-//   rab_inv [natoms][natoms]: 1 / R_AB (0 on the diagonal);
+//   rab / rab_inv [natoms][natoms]: R_AB and 1 / R_AB (0 on the diagonal);
 //   nbr_idx / nbr_dist [natoms][natoms]: per atom, all atoms sorted by distance from it (itself first)
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
+                        const double* rab, const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
                         const double* nbr_dist, int natoms, cudaStream_t s);
 
 // FP64 peak probes (DMMA m8n8k4 and DFMA), return achieved TFLOP/s

@@ -50,8 +50,14 @@ __device__ __forceinline__ double g_frisch(double mu) {
   return (35. * (s - s3) + 21. * s5 - 5. * s7) / 16.;
 }
 
+// Margin of the squared-distance pre-test of the pair loop: a pair is skipped only when (r_B - r_C) / R_CB exceeds 0.64
+// by more than 1e-10 relative -- eight orders above the rounding of either evaluation -- so the host's own test
+// (mu <= -0.64 resp. mu >= 0.64 on its rounded mu) takes the same branch and the factor is exactly 1 on both sides.
+constexpr double skip_fac = magic_ssf * (1. + 1e-10);
+
 __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __restrict__ tiles,
                                                   const double* __restrict__ atoms,
+                                                  const double* __restrict__ rab,
                                                   const double* __restrict__ rab_inv,
                                                   const double* __restrict__ dist_nearest,
                                                   const int* __restrict__ nbr_idx,
@@ -130,12 +136,19 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
     }
     double Pc = 1.;
     const double* __restrict__ rabC = rab_inv + (size_t)C * natoms;
+    const double* __restrict__ rabR = rab + (size_t)C * natoms;
     const double b_cut = kappa * rC;
     for (int kb = 0; kb < natoms; ++kb) {
       if (nd[kb] - r_anc >= b_cut) break;  // every remaining factor is exactly 1
       const int Bq = nb[kb];
       if (Bq == C) continue;
-      const double rB = dist(Bq);
+      // Most B inside the cut-off sphere still give a factor of exactly 1 (r_B - r_C >= 0.64 R_CB): decide that on
+      // squared distances -- no square root, no reciprocal -- and evaluate mu only for the pairs that compete.
+      const double bx = px - atoms[3 * Bq], by = py - atoms[3 * Bq + 1], bz = pz - atoms[3 * Bq + 2];
+      const double rB2 = bx * bx + by * by + bz * bz;
+      const double T = fma(skip_fac, rabR[Bq], rC);
+      if (rB2 >= T * T) continue;
+      const double rB = sqrt(rB2);
       const double Rinv = rabC[Bq];
       if (Bq < C) {
         const double mu = (rC - rB) * Rinv;
@@ -159,10 +172,10 @@ __global__ void __launch_bounds__(TP) ssf_kernel(PlanView pv, const DevTile* __r
 }  // namespace
 
 void launch_ssf_weights(const PlanView& pv, const DevTile* tiles, int ntiles, const double* atoms,
-                        const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
+                        const double* rab, const double* rab_inv, const double* dist_nearest, const int* nbr_idx,
                         const double* nbr_dist, int natoms, cudaStream_t s) {
   if (ntiles <= 0) return;
-  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab_inv, dist_nearest, nbr_idx, nbr_dist, natoms);
+  ssf_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, atoms, rab, rab_inv, dist_nearest, nbr_idx, nbr_dist, natoms);
 }
 
 }  // namespace gxb

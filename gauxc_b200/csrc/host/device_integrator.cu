@@ -103,7 +103,7 @@ struct DevicePlan {
   DevBuf<int> d_task_shells, d_task_shell_bf, d_task_ao;
   DevBuf<int> d_shell_center;  // shell -> atom (BasisSetMap::shell_to_center), EXC gradient
   DevBuf<double> d_px, d_py, d_pz, d_w;
-  DevBuf<double> d_atoms, d_rab, d_dist_nearest, d_nbr_dist;
+  DevBuf<double> d_atoms, d_rab, d_rab_dist, d_dist_nearest, d_nbr_dist;  // d_rab: 1 / R_AB, d_rab_dist: R_AB
   DevBuf<int> d_nbr_idx;  // per atom: all atoms sorted by distance from it (SSF loop cut-offs)
   double f_dense = 0., sum_nbe_npts = 0.;
   std::map<int, std::shared_ptr<Schedule>> schedules;  // key: nmat
@@ -289,6 +289,7 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
     std::vector<double> rab_inv(meta.rab.size());
     for (size_t q = 0; q < rab_inv.size(); ++q) rab_inv[q] = meta.rab[q] > 0. ? 1. / meta.rab[q] : 0.;
     plan->d_rab.upload(rab_inv);
+    plan->d_rab_dist.upload(meta.rab);
   }
   plan->d_dist_nearest.upload(meta.dist_nearest);
   {
@@ -607,7 +608,7 @@ void MolecularWeights::modify_weights(LoadBalancer& lb) {
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, 0));
   gxb::launch_ssf_weights(plan->view(), plan->d_tiles.p, (int)plan->tiles.size(), plan->d_atoms.p,
-                          plan->d_rab.p, plan->d_dist_nearest.p, plan->d_nbr_idx.p, plan->d_nbr_dist.p,
+                          plan->d_rab_dist.p, plan->d_rab.p, plan->d_dist_nearest.p, plan->d_nbr_idx.p, plan->d_nbr_dist.p,
                           plan->natoms, 0);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(e1, 0));
