@@ -36,6 +36,15 @@
 // candidates, so all lanes sit in the pair loop together) were 5-7x SLOWER (ubiquitin 7.4 s, (H2O)833 32 s): a
 // candidate is competitive for all points of a tile or for none, so the shared-candidate loop is long for ~8
 // candidates per warp, the per-lane one for every list position; and 1 / R_CB becomes a 32-row gather.
+//
+// Round 2, later: (3) a squared-distance pre-test of the pair loop (no square root / reciprocal for the pairs whose factor
+// is exactly 1; identical weights) is in: taxol 52.1 -> 49.2 ms, ubiquitin 1097 -> 974 ms, (H2O)833 6378 -> 5556 ms.
+// (4) A warp-per-point kernel for the points far from every nucleus (nearest atom as the anchor, the kappa^2 r_min
+// neighbourhood staged in shared memory with its distances, 32 lanes over the atoms B of one candidate at a time, lane
+// products multiplied by shuffles) was built and swept over the hand-over radius (gpurun_out/r02v_ssf_sweep.log): same
+// weights, but slower at every radius -- taxol 73 ms with all points, ubiquitin 1103 ms, (H2O)833 14.5 s (2 warps per CTA:
+// 30 KB of lists per warp for 2499 atoms) -- the thread-per-point loop visits fewer pairs per point than its 6.5 active
+// lanes suggest, because dead candidates die on their first few B and the warp's union of live (C, B) pairs is small.
 #include "kernels.cuh"
 
 namespace gxb {

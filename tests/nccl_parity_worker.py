@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_parity.py::test_two_rank_nccl_result_matches_oracle (one process per GPU under
 torchrun): every rank evaluates its share of the grid batches on its GPU, the library's NCCL reduction driver
-sums VXC / EXC / N_el, and EVERY rank checks the reduced result against the oracle on the undivided task list."""
+sums VXC / EXC / N_el (and the EXC gradient), and EVERY rank checks the reduced result against the oracle on the
+undivided task list."""
 import os
 import sys
 
@@ -43,6 +44,17 @@ def main():
         assert 0 < s.npts_local < s1.npts_local
         assert max(d) <= TOL, d
         assert np.array_equal(vxc, vxc.T)
+        # EXC gradient: the 3 natoms sums are reduced on the device (the reference refuses a device reduction here)
+        na = len(s.atoms)
+        xyz = np.array([a[1:] for a in s.atoms])
+        s2c = np.linalg.norm(s1.basis.flat()[5][:, None, :] - xyz[None, :, :], axis=2).argmin(1).astype(np.int32)
+        for wd in (False, True):
+            g = integ.eval_exc_grad(s.P, na, include_weight_derivatives=wd)
+            go = orc.exc_grad(s1.basis.flat(), s2c, xyz, s1.nbf, s1.P, s1.lb.export_tasks(), func,
+                              include_weight_derivatives=wd)
+            dg = float(np.abs(g - go).max())
+            print(f"[rank {rank}] {workload} {func}: EXC gradient (weight derivatives {wd}) max|dg| {dg:.2e}", flush=True)
+            assert dg <= TOL, dg
         del integ, s, s1
     dist.barrier()
     if rank == 0:
