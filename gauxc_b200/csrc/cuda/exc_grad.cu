@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(TP) collocation_hessian_kernel(PlanView pv, co
 // ------------------------------------------------------------------------------------------------
 constexpr int EG_THREADS = 256;
 
+// RKS: two CTAs per SM (128 registers; the GGA instantiation spills 104 bytes around the functional) -- the kernel streams
+// 5 / 14 matrices and wants the occupancy; the UKS GGA instantiation would spill 640 bytes and keeps one.
 template <bool GGA, bool UKS>
-__global__ void __launch_bounds__(EG_THREADS)
+__global__ void __launch_bounds__(EG_THREADS, UKS ? 1 : 2)
 exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
                 const double* __restrict__ ws, FunctionalDesc func, const int* __restrict__ shell_atom, int natoms,
                 int include_wd, double* __restrict__ wf_out, double* __restrict__ grad, int smem_acc) {
@@ -350,8 +352,8 @@ exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int*
 //     P_parent > 0 (wf = 0 otherwise): all inside list1.
 // So every loop of the host function runs over list1 (compacted into shared memory with coordinates and distances)
 // instead of all atoms, with identical terms.  The host's pair loop skips pairs whose two partial products are both
-// <= 1e-13; here P_A is the full product (differences below 1e-13 of the sum).  R_AB is recomputed from the
-// coordinates.  Atom sums accumulate in shared memory per CTA.
+// <= 1e-13; here P_A is the full product (differences below 1e-13 of the sum).  1 / R_AB comes from the plan's table
+// (the SSF weights kernel's), so the pair loops hold no square root or division by R.  Atom sums accumulate in warp-private shared memory (no atomics) and reach HBM once per warp.
 // ------------------------------------------------------------------------------------------------
 constexpr double magic_ssf = 0.64;
 
@@ -375,19 +377,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void ssf_weight_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles,
                                        int* __restrict__ counter, const double* __restrict__ atoms,
+                                       const double* __restrict__ rab_inv,
                                        const double* __restrict__ dist_nearest, int natoms,
                                        const double* __restrict__ wf, double* __restrict__ grad) {
+  // per warp: ld, lp (list distances / partition products), gw (3 natoms PRIVATE atom sums: within a warp every list entry
+  // -- hence every atom -- is owned by one lane, so the sums need no atomics; shared-memory FP64 atomics are CAS loops) and
+  // li (list -> atom); coordinates are read through li from the (L1-resident) atom array
   extern __shared__ double wg_dyn[];
   __shared__ int s_tile;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* g_s = wg_dyn;                                        // [3 natoms] CTA accumulators
-  double* base = wg_dyn + 3 * natoms + (size_t)warp * 5 * natoms;  // per warp
-  double *ld = base, *lx = base + natoms, *ly = base + 2 * natoms, *lz = base + 3 * natoms, *lp = base + 4 * natoms;
-  int* li = reinterpret_cast<int*>(wg_dyn + 3 * natoms + (size_t)nwarps * 5 * natoms) + (size_t)warp * natoms;
-  for (int q = threadIdx.x; q < 3 * natoms; q += blockDim.x) g_s[q] = 0.;
+  double* base = wg_dyn + (size_t)warp * 5 * natoms;
+  double *ld = base, *lp = base + natoms, *gw = base + 2 * natoms;
+  int* li = reinterpret_cast<int*>(wg_dyn + (size_t)nwarps * 5 * natoms) + (size_t)warp * natoms;
+  for (int q = lane; q < 3 * natoms; q += 32) gw[q] = 0.;
   __syncthreads();
   const double kappa = (1. + magic_ssf) / (1. - magic_ssf) * (1. + 1e-9);
   const double bound = magic_ssf - 1.e-4, weight_tol = 1e-13, wf_thresh = 1.e-12;
+  auto X = [&](int a, int c) { return atoms[3 * a + c]; };
 
   for (;;) {
     if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1);
@@ -420,15 +426,15 @@ __global__ void ssf_weight_grad_kernel(PlanView pv, const DevTile* __restrict__ 
       __syncwarp();
       for (int a0 = 0; a0 < natoms; a0 += 32) {
         const int a = a0 + lane;
-        double x = 0., y = 0., z = 0., d = 1e300;
+        double d = 1e300;
         if (a < natoms) {
-          x = atoms[3 * a]; y = atoms[3 * a + 1]; z = atoms[3 * a + 2];
+          const double x = atoms[3 * a], y = atoms[3 * a + 1], z = atoms[3 * a + 2];
           d = a == par ? d_par : sqrt((px - x) * (px - x) + (py - y) * (py - y) + (pz - z) * (pz - z));
         }
         const bool keep = a < natoms && (d < r1 || a == par);
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const int pos = n1 + __popc(m & ((1u << lane) - 1u));
-        if (keep) { li[pos] = a; ld[pos] = d; lx[pos] = x; ly[pos] = y; lz[pos] = z; }
+        if (keep) { li[pos] = a; ld[pos] = d; }
         const unsigned mp = __ballot_sync(0xffffffffu, keep && a == par);
         if (mp) kpar = n1 + __popc(m & ((1u << (__ffs(mp) - 1)) - 1u));
         n1 += __popc(m);
@@ -441,11 +447,10 @@ __global__ void ssf_weight_grad_kernel(PlanView pv, const DevTile* __restrict__ 
         const double dk = ld[k];
         if (dk < r0) {
           P = 1.;
-          const double xk = lx[k], yk = ly[k], zk = lz[k];
+          const double* __restrict__ rinv_k = rab_inv + (size_t)li[k] * natoms;  // 1 / R_AB from the plan's table
           for (int j = 0; j < n1; ++j) {
             if (j == k) continue;
-            const double ex = xk - lx[j], ey = yk - ly[j], ez = zk - lz[j];
-            const double mu = (dk - ld[j]) / sqrt(ex * ex + ey * ey + ez * ez);
+            const double mu = (dk - ld[j]) * rinv_k[li[j]];
             if (mu >= magic_ssf) { P = 0.; break; }
             if (mu > -magic_ssf) P *= 0.5 * (1. - g_frisch_d(mu));
           }
@@ -457,68 +462,74 @@ __global__ void ssf_weight_grad_kernel(PlanView pv, const DevTile* __restrict__ 
       __syncwarp();
       const double P_par = lp[kpar];
       double pa[3] = {0., 0., 0.};  // lane-local share of what the parent receives (translational invariance)
-      // first term: - coef1 nabla_B mu_BA, B != parent
+      // first term: - coef1 nabla_B mu_BA, B != parent; lane = owner of its list entries
       for (int k = lane; k < n1; k += 32) {
         if (k == kpar) continue;
-        const double ux = lx[k] - ax, uy = ly[k] - ay, uz = lz[k] - az;
-        const double rAB = sqrt(ux * ux + uy * uy + uz * uz), rAB_inv = 1. / rAB;
+        const int ab = li[k];
+        const double bx = X(ab, 0), by = X(ab, 1), bz = X(ab, 2);
+        const double ux = bx - ax, uy = by - ay, uz = bz - az;
+        const double rAB_inv = rab_inv[(size_t)par * natoms + ab];
         const double dB = ld[k];
         const double mu_AB = (d_par - dB) * rAB_inv;
         if (fabs(mu_AB) < bound) {
-          const double coef1 = t_frisch_d(mu_AB) / rAB * (P_par - sum) / sum * wfi / dB;
-          const double gx = coef1 * ((lx[k] - px) + mu_AB * ux * rAB_inv * dB);
-          const double gy = coef1 * ((ly[k] - py) + mu_AB * uy * rAB_inv * dB);
-          const double gz = coef1 * ((lz[k] - pz) + mu_AB * uz * rAB_inv * dB);
-          atomicAdd(&g_s[3 * li[k]], gx); atomicAdd(&g_s[3 * li[k] + 1], gy); atomicAdd(&g_s[3 * li[k] + 2], gz);
+          const double coef1 = t_frisch_d(mu_AB) * rAB_inv * (P_par - sum) / sum * wfi / dB;
+          const double gx = coef1 * ((bx - px) + mu_AB * ux * rAB_inv * dB);
+          const double gy = coef1 * ((by - py) + mu_AB * uy * rAB_inv * dB);
+          const double gz = coef1 * ((bz - pz) + mu_AB * uz * rAB_inv * dB);
+          gw[3 * ab] += gx; gw[3 * ab + 1] += gy; gw[3 * ab + 2] += gz;
           pa[0] -= gx; pa[1] -= gy; pa[2] -= gz;
         }
       }
-      // second term: B with P_B > tol, C over list1
+      // second term: B with P_B > tol, C over list1 (lane = owner of entry kc)
       for (int kb = 0; kb < n1; ++kb) {
         const double PB = lp[kb];
         if (!(PB > weight_tol) || kb == kpar) continue;
-        const double xb = lx[kb], yb = ly[kb], zb = lz[kb], dB = ld[kb];
+        const int ab = li[kb];
+        const double xb = X(ab, 0), yb = X(ab, 1), zb = X(ab, 2), dB = ld[kb];
+        const double dB_inv = 1. / dB, ubx = (xb - px) * dB_inv, uby = (yb - py) * dB_inv, ubz = (zb - pz) * dB_inv;
+        const double* __restrict__ rinv_b = rab_inv + (size_t)ab * natoms;
+        const double pref = PB / sum * wfi;
         double gb[3] = {0., 0., 0.};
         for (int kc = lane; kc < n1; kc += 32) {
           if (kc == kb) continue;
-          const double ex = xb - lx[kc], ey = yb - ly[kc], ez = zb - lz[kc];
-          const double rBC = sqrt(ex * ex + ey * ey + ez * ez);
+          const int ac = li[kc];
           const double dC = ld[kc];
-          const double mu_BC = (dB - dC) / rBC;
+          const double Rinv = rinv_b[ac];
+          const double mu_BC = (dB - dC) * Rinv;
           if (fabs(mu_BC) < bound) {
-            const double coef = PB * t_frisch_d(mu_BC) / rBC / sum * wfi;
-            gb[0] -= coef * ((xb - px) / dB - mu_BC * ex / rBC);
-            gb[1] -= coef * ((yb - py) / dB - mu_BC * ey / rBC);
-            gb[2] -= coef * ((zb - pz) / dB - mu_BC * ez / rBC);
+            const double xc = X(ac, 0), yc = X(ac, 1), zc = X(ac, 2);
+            const double coef = pref * t_frisch_d(mu_BC) * Rinv;
+            const double mr = mu_BC * Rinv;
+            const double ex = (xb - xc) * mr, ey = (yb - yc) * mr, ez = (zb - zc) * mr;  // mu_BC (r_B - r_C) / R_BC
+            gb[0] -= coef * (ubx - ex);
+            gb[1] -= coef * (uby - ey);
+            gb[2] -= coef * (ubz - ez);
             if (kc != kpar) {
-              const double cx = coef * ((lx[kc] - px) / dC - mu_BC * ex / rBC);
-              const double cy = coef * ((ly[kc] - py) / dC - mu_BC * ey / rBC);
-              const double cz = coef * ((lz[kc] - pz) / dC - mu_BC * ez / rBC);
-              atomicAdd(&g_s[3 * li[kc]], cx); atomicAdd(&g_s[3 * li[kc] + 1], cy); atomicAdd(&g_s[3 * li[kc] + 2], cz);
+              const double dC_inv = 1. / dC;
+              const double cx = coef * ((xc - px) * dC_inv - ex);
+              const double cy = coef * ((yc - py) * dC_inv - ey);
+              const double cz = coef * ((zc - pz) * dC_inv - ez);
+              gw[3 * ac] += cx; gw[3 * ac + 1] += cy; gw[3 * ac + 2] += cz;
               pa[0] -= cx; pa[1] -= cy; pa[2] -= cz;
             }
           }
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const double v = warp_sum(gb[c]);
-          if (lane == 0) {
-            atomicAdd(&g_s[3 * li[kb] + c], v);
-            pa[c] -= v;
-          }
+        const double vx = warp_sum(gb[0]), vy = warp_sum(gb[1]), vz = warp_sum(gb[2]);
+        if (lane == (kb & 31)) {  // the owner lane of entry kb: per-lane program order keeps gw consistent
+          gw[3 * ab] += vx; gw[3 * ab + 1] += vy; gw[3 * ab + 2] += vz;
+          pa[0] -= vx; pa[1] -= vy; pa[2] -= vz;
         }
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double v = warp_sum(pa[c]);
-        if (lane == 0 && v != 0.) atomicAdd(&g_s[3 * par + c], v);
+      {
+        const double vx = warp_sum(pa[0]), vy = warp_sum(pa[1]), vz = warp_sum(pa[2]);
+        if (lane == (kpar & 31)) { gw[3 * par] += vx; gw[3 * par + 1] += vy; gw[3 * par + 2] += vz; }
       }
       __syncwarp();
     }
   }
-  __syncthreads();
-  for (int q = threadIdx.x; q < 3 * natoms; q += blockDim.x) {
-    const double v = g_s[q];
+  __syncwarp();
+  for (int q = lane; q < 3 * natoms; q += 32) {
+    const double v = gw[q];
     if (v != 0.) atomicAdd(&grad[q], v);
   }
 }
@@ -598,20 +609,21 @@ cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles
 }
 
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                                   const double* atoms, const double* dist_nearest, int natoms, const double* wf,
-                                   double* grad, cudaStream_t s) {
+                                   const double* atoms, const double* rab_inv, const double* dist_nearest, int natoms,
+                                   const double* wf, double* grad, cudaStream_t s) {
   if (ntiles <= 0) return cudaSuccess;
-  // shared memory: 3 natoms (CTA sums) + per warp 5 natoms doubles + natoms ints
-  auto bytes = [&](int nw) { return (size_t)natoms * (3 * 8 + (size_t)nw * (5 * 8 + 4)) + 16; };
+  // shared memory per warp: 5 natoms doubles (ld, lp, 3 natoms private sums) + natoms ints
+  auto bytes = [&](int nw) { return (size_t)natoms * (size_t)nw * (5 * 8 + 4) + 16; };
   int nw = 8;
-  while (nw > 1 && bytes(nw) > 200 * 1024) nw >>= 1;
+  while (nw > 1 && bytes(nw) > 100 * 1024) nw >>= 1;
   const size_t dyn = bytes(nw);
-  if (dyn > 227 * 1024) return cudaErrorInvalidConfiguration;  // > ~3400 atoms: the caller reports NYI
+  if (dyn > 227 * 1024) return cudaErrorInvalidConfiguration;  // > ~5 000 atoms: the caller reports NYI
   cudaError_t e = cudaFuncSetAttribute(ssf_weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / dyn));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / dyn));
   const int ncta = std::min(ntiles, std::max(1, nsm) * per_sm);
-  ssf_weight_grad_kernel<<<ncta, nw * 32, dyn, s>>>(pv, tiles, ntiles, counter, atoms, dist_nearest, natoms, wf, grad);
+  ssf_weight_grad_kernel<<<ncta, nw * 32, dyn, s>>>(pv, tiles, ntiles, counter, atoms, rab_inv, dist_nearest, natoms, wf,
+                                                    grad);
   return cudaGetLastError();
 }
 

@@ -50,8 +50,8 @@ cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles
 //   SSF weight derivatives contracted with wf, accumulated into grad (cudaErrorInvalidConfiguration: too many atoms
 //   for the shared-memory lists)
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                                   const double* atoms, const double* dist_nearest, int natoms, const double* wf,
-                                   double* grad, cudaStream_t s);
+                                   const double* atoms, const double* rab_inv, const double* dist_nearest, int natoms,
+                                   const double* wf, double* grad, cudaStream_t s);
 
 // finalisation
 void launch_reduce_partials(const double* exc_part, const double* nel_part, int n, double* out2,

@@ -1246,7 +1246,8 @@ void XCIntegrator::eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t
   if (include_weight_derivatives && !plan.tiles.empty()) {
     const cudaError_t e = gxb::launch_ssf_weight_grad(pv, plan.d_tiles.p, (int)plan.tiles.size(),
                                                       sc.d_counters.p + 9 * nbatch, sc.ncta, plan.d_atoms.p,
-                                                      plan.d_dist_nearest.p, natoms, I.d_wf.p, I.d_grad.p, s);
+                                                      plan.d_rab.p, plan.d_dist_nearest.p, natoms, I.d_wf.p,
+                                                      I.d_grad.p, s);
     if (e == cudaErrorInvalidConfiguration)
       GAUXC_GENERIC_EXCEPTION("SSF Weight Derivatives NYI in B200 path for this many atoms");
     CUDA_CHECK(e);

@@ -40,6 +40,10 @@ for ST in "$@"; do
     fast)  # bench:<workload>[:steps] without the CPU baseline and with a 2 s parity sample
       timeout 900 python bench.py --workload $A --steps ${B:-3} --warmup 3 --others "" --no-cpu-baseline --parity-seconds 2 > gpurun_out/${TAG}_fast_${A}.json 2> gpurun_out/${TAG}_fast_${A}.err
       echo "fast $A exit $?"; python tools/bench_brief.py gpurun_out/${TAG}_fast_${A}.json | head -4; tail -3 gpurun_out/${TAG}_fast_${A}.err ;;
+    gradlaunches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_grad_${A}.csv \
+        python tools/grad_once.py $A > gpurun_out/${TAG}_ncu_launch_grad_${A}.log 2>&1
+      echo "grad launch list $A exit $?" ;;
     grad)
       timeout 900 python tools/grad_report.py > gpurun_out/${TAG}_exc_grad.txt 2>&1; echo "grad exit $?"; cat gpurun_out/${TAG}_exc_grad.txt ;;
     *) echo "unknown stage $ST" ;;
