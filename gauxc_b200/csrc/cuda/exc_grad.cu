@@ -6,10 +6,15 @@
 // replacing the reference device kernels increment_exc_grad_{lda,gga} (kernels/increment_exc_grad.cu) and
 // eval_weight_1st_deriv_contracted_ssf_kernel_1d (kernels/cuda_ssf_1d.cu:146-350).
 //
-// Per batch of tiles the integrator runs: collocation (gradient for LDA, Hessian for GGA) -> the fused DMMA kernel
-// in XOUT mode once per needed X = 2 A P_sub (A = B; GGA also dB/dx, dB/dy, dB/dz) -> exc_grad_kernel.  Tile
-// matrices ([pad16(nbe)][TP], swizzled as everywhere, device_plan.hpp): LDA  B dx dy dz | X;  GGA  B dx dy dz xx xy
-// xz yy yz zz | X Xx Xy Xz.
+// Per batch of tiles the integrator runs: collocation (gradient for LDA, Hessian for GGA) -> the fused DMMA kernel in
+// XOUT mode for X = 2 B P_sub -> exc_grad_kernel.  LDA: one pass (PHASE 2).  GGA: the host needs X_a = 2 (dB/da) P_sub only
+// inside d11 = sum_a (d rho / da) X_a, which is LINEAR in the per-point vector grad rho: PHASE 0 evaluates the densities
+// and the functional and writes U = 2 w vgamma sum_a (d rho / da) dB/da (one matrix), the DMMA kernel forms Y = 2 U P_sub,
+// PHASE 1 assembles with Y in place of 2 w vgamma d11 -- TWO contractions instead of the reference's four
+// (eval_xmat over xmat_len = 4 blocks, reference_replicated_xc_host_integrator_exc_grad.hpp:370-373), same sums up to the
+// order of the additions.  UKS likewise: U_s, U_z carry the four vgamma combinations, four contractions instead of eight.
+// Tile matrices ([pad16(nbe)][TP], swizzled as everywhere, device_plan.hpp): LDA  B dx dy dz | X (UKS: XN XZ);
+// GGA  B dx dy dz xx xy xz yy yz zz | X | U | Y | F  (UKS: XN XZ | U_s U_z | Y_s Y_z | F), F = per-point factors.
 #include <algorithm>
 #include <initializer_list>
 
@@ -138,20 +143,22 @@ __global__ void __launch_bounds__(TP) collocation_hessian_kernel(PlanView pv, co
 // ------------------------------------------------------------------------------------------------
 constexpr int EG_THREADS = 256;
 
-// RKS: two CTAs per SM (128 registers; the GGA instantiation spills 104 bytes around the functional) -- the kernel streams
-// 5 / 14 matrices and wants the occupancy; the UKS GGA instantiation would spill 640 bytes and keeps one.
-template <bool GGA, bool UKS>
-__global__ void __launch_bounds__(EG_THREADS, UKS ? 1 : 2)
+// PHASE 2: everything (LDA).  PHASE 0 (GGA): densities, functional, per-point factors -> F, U rows.  PHASE 1 (GGA): assembly.
+// Two CTAs per SM where the registers allow (the kernel streams up to 13 matrices and wants the occupancy).
+template <bool GGA, bool UKS, int PHASE>
+__global__ void __launch_bounds__(EG_THREADS, (UKS && GGA && PHASE == 0) ? 1 : 2)
 exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int* __restrict__ counter,
-                const double* __restrict__ ws, FunctionalDesc func, const int* __restrict__ shell_atom, int natoms,
+                double* __restrict__ ws, FunctionalDesc func, const int* __restrict__ shell_atom, int natoms,
                 int include_wd, double* __restrict__ wf_out, double* __restrict__ grad, int smem_acc) {
   extern __shared__ double eg_dyn[];  // smem_acc: 3 natoms accumulators
   __shared__ double part[2][UKS ? 8 : 4][TP];
   __shared__ int s_tile;
   const int tid = threadIdx.x, p = tid & (TP - 1), h = tid >> 7, lane = tid & 31;
-  constexpr int NB = GGA ? 10 : 4;  // basis matrices ahead of X
-  constexpr int NX = GGA ? 4 : 1;   // X matrices per density (UKS: XN block, then XZ block)
-  if (smem_acc)
+  constexpr int NB = GGA ? 10 : 4;   // basis matrices ahead of X
+  constexpr int ND = UKS ? 2 : 1;    // densities: X, U, Y blocks of ND matrices each
+  constexpr int SU = NB + ND, SY = NB + 2 * ND, SF = NB + 3 * ND;  // GGA slots of U, Y and the factor rows
+  constexpr bool DO_A = PHASE != 1, DO_B = PHASE != 0;
+  if (DO_B && smem_acc)
     for (int q = tid; q < 3 * natoms; q += EG_THREADS) eg_dyn[q] = 0.;
   __syncthreads();
   auto add_atom = [&](int atom, int c, double v) {
@@ -168,173 +175,209 @@ exc_grad_kernel(PlanView pv, const DevTile* __restrict__ tiles, int ntiles, int*
     const DevTask task = pv.tasks[tile.task];
     const int nbe = tile.nbe;
     const size_t ms = (size_t)pad16(nbe) * TP;
-    const double* __restrict__ M = ws + tile.ws_off;
+    double* __restrict__ M = ws + tile.ws_off;
     const bool ok = p < tile.npts;
     // element (mu, p) of matrix q: M[q * ms + mu * TP + (p ^ ((mu & 3) << 2))]
     auto at = [&](int q, int mu) { return M[(size_t)q * ms + (size_t)mu * TP + swz(mu, p)]; };
+    double* __restrict__ F = M + (size_t)SF * ms;  // GGA: factor row q of point p at F[q * TP + p]
 
-    // ---- phase A
-    double r0 = 0., r1 = 0., r2 = 0., r3 = 0.;
-    double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;  // UKS: the same sums with X of Pz
-    if (ok) {
+    // RKS: wv = w vrho, wg = w vgamma, (dx, dy, dz) = grad rho.  UKS (:424-436, 482-513): wv = 1/2 w (v+ + v-),
+    // wvz = 1/2 w (v+ - v-), wg = c1 = 1/2 w (v++ + v+- + v--), c2 = 1/2 w (v++ - v--), c3 = 1/2 w (v++ - v+- + v--),
+    // (dx, dy, dz) = grad n, (mx, my, mz) = grad M_z
+    double wv = 0., wg = 0., wvz = 0., c2 = 0., c3 = 0.;
+    double dx = 0., dy = 0., dz = 0., mx = 0., my = 0., mz = 0.;
+    if (DO_A) {
+      // ---- phase A
+      double r0 = 0., r1 = 0., r2 = 0., r3 = 0.;
+      double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;  // UKS: the same sums with X of Pz
+      if (ok) {
 #pragma unroll 4
-      for (int mu = h; mu < nbe; mu += 2) {
-        const double x = at(NB, mu);
-        const double b0 = at(0, mu);
-        r0 = fma(b0, x, r0);
-        double b1 = 0., b2 = 0., b3 = 0.;
-        if (GGA) {
-          b1 = at(1, mu); b2 = at(2, mu); b3 = at(3, mu);
-          r1 = fma(b1, x, r1);
-          r2 = fma(b2, x, r2);
-          r3 = fma(b3, x, r3);
-        }
-        if (UKS) {
-          const double xz = at(NB + NX, mu);
-          q0 = fma(b0, xz, q0);
+        for (int mu = h; mu < nbe; mu += 2) {
+          const double x = at(NB, mu);
+          const double b0 = at(0, mu);
+          r0 = fma(b0, x, r0);
+          double b1 = 0., b2 = 0., b3 = 0.;
           if (GGA) {
-            q1 = fma(b1, xz, q1);
-            q2 = fma(b2, xz, q2);
-            q3 = fma(b3, xz, q3);
+            b1 = at(1, mu); b2 = at(2, mu); b3 = at(3, mu);
+            r1 = fma(b1, x, r1);
+            r2 = fma(b2, x, r2);
+            r3 = fma(b3, x, r3);
+          }
+          if (UKS) {
+            const double xz = at(NB + 1, mu);
+            q0 = fma(b0, xz, q0);
+            if (GGA) {
+              q1 = fma(b1, xz, q1);
+              q2 = fma(b2, xz, q2);
+              q3 = fma(b3, xz, q3);
+            }
           }
         }
       }
-    }
-    part[h][0][p] = r0;
-    if (GGA) { part[h][1][p] = r1; part[h][2][p] = r2; part[h][3][p] = r3; }
-    if (UKS) {
-      part[h][4][p] = q0;
-      if (GGA) { part[h][5][p] = q1; part[h][6][p] = q2; part[h][7][p] = q3; }
-    }
-    __syncthreads();
-    const double rho = part[0][0][p] + part[1][0][p];
-    double dx = 0., dy = 0., dz = 0.;
-    if (GGA) {
-      dx = 2. * (part[0][1][p] + part[1][1][p]);
-      dy = 2. * (part[0][2][p] + part[1][2][p]);
-      dz = 2. * (part[0][3][p] + part[1][3][p]);
-    }
-    double rho_z = 0., mx = 0., my = 0., mz = 0.;  // UKS: rho = rho_s, (dx, dy, dz) = grad n, (mx, my, mz) = grad M_z
-    if (UKS) {
-      rho_z = part[0][4][p] + part[1][4][p];
+      part[h][0][p] = r0;
+      if (GGA) { part[h][1][p] = r1; part[h][2][p] = r2; part[h][3][p] = r3; }
+      if (UKS) {
+        part[h][4][p] = q0;
+        if (GGA) { part[h][5][p] = q1; part[h][6][p] = q2; part[h][7][p] = q3; }
+      }
+      __syncthreads();
+      const double rho = part[0][0][p] + part[1][0][p];
       if (GGA) {
-        mx = 2. * (part[0][5][p] + part[1][5][p]);
-        my = 2. * (part[0][6][p] + part[1][6][p]);
-        mz = 2. * (part[0][7][p] + part[1][7][p]);
+        dx = 2. * (part[0][1][p] + part[1][1][p]);
+        dy = 2. * (part[0][2][p] + part[1][2][p]);
+        dz = 2. * (part[0][3][p] + part[1][3][p]);
       }
-    }
-    // RKS: wv = w vrho, wg = w vgamma.  UKS (:424-436, 482-513): wv = 1/2 w (v+ + v-), wvz = 1/2 w (v+ - v-),
-    // c1 = 1/2 w (v++ + v+- + v--), c2 = 1/2 w (v++ - v--), c3 = 1/2 w (v++ - v+- + v--)
-    double wv = 0., wg = 0., wvz = 0., c2 = 0., c3 = 0.;
-    if (ok) {
-      const double w = pv.w[tile.pt_off + p];
-      double eps;
-      if (!UKS) {
-        const XcOut xc = eval_functional(func, rho, GGA ? dx * dx + dy * dy + dz * dz : 0.);
-        wv = w * xc.vrho;
-        wg = w * xc.vsigma;
-        eps = xc.eps;
-      } else if (GGA) {
-        const double dn_sq = dx * dx + dy * dy + dz * dz, dm_sq = mx * mx + my * my + mz * mz,
-                     dn_dm = dx * mx + dy * my + dz * mz;
-        const double gpp = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm, gpm = 0.25 * (dn_sq - dm_sq),
-                     gmm = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
-        const XcOutPolGga xc = eval_functional_pol(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z), gpp, gpm, gmm);
-        const double vp = w * xc.va, vm = w * xc.vb;
-        wv = 0.5 * (vp + vm);
-        wvz = 0.5 * (vp - vm);
-        const double vpp = w * xc.vaa, vpm = w * xc.vab, vmm = w * xc.vbb;
-        wg = 0.5 * (vpp + vpm + vmm);
-        c2 = 0.5 * (vpp - vmm);
-        c3 = 0.5 * (vpp - vpm + vmm);
-        eps = xc.eps;
-      } else {
-        const XcOutPol xc = eval_functional_pol_lda(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z));
-        const double vp = w * xc.va, vm = w * xc.vb;
-        wv = 0.5 * (vp + vm);
-        wvz = 0.5 * (vp - vm);
-        eps = xc.eps;
+      double rho_z = 0.;
+      if (UKS) {
+        rho_z = part[0][4][p] + part[1][4][p];
+        if (GGA) {
+          mx = 2. * (part[0][5][p] + part[1][5][p]);
+          my = 2. * (part[0][6][p] + part[1][6][p]);
+          mz = 2. * (part[0][7][p] + part[1][7][p]);
+        }
       }
-      if (include_wd && h == 0) wf_out[tile.pt_off + p] = eps * (rho * w);  // eps *= den * w (:396-399)
+      if (ok) {
+        const double w = pv.w[tile.pt_off + p];
+        double eps;
+        if (!UKS) {
+          const XcOut xc = eval_functional(func, rho, GGA ? dx * dx + dy * dy + dz * dz : 0.);
+          wv = w * xc.vrho;
+          wg = w * xc.vsigma;
+          eps = xc.eps;
+        } else if (GGA) {
+          const double dn_sq = dx * dx + dy * dy + dz * dz, dm_sq = mx * mx + my * my + mz * mz,
+                       dn_dm = dx * mx + dy * my + dz * mz;
+          const double gpp = 0.25 * (dn_sq + dm_sq) + 0.5 * dn_dm, gpm = 0.25 * (dn_sq - dm_sq),
+                       gmm = 0.25 * (dn_sq + dm_sq) - 0.5 * dn_dm;
+          const XcOutPolGga xc = eval_functional_pol(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z), gpp, gpm, gmm);
+          const double vp = w * xc.va, vm = w * xc.vb;
+          wv = 0.5 * (vp + vm);
+          wvz = 0.5 * (vp - vm);
+          const double vpp = w * xc.vaa, vpm = w * xc.vab, vmm = w * xc.vbb;
+          wg = 0.5 * (vpp + vpm + vmm);
+          c2 = 0.5 * (vpp - vmm);
+          c3 = 0.5 * (vpp - vpm + vmm);
+          eps = xc.eps;
+        } else {
+          const XcOutPol xc = eval_functional_pol_lda(func, 0.5 * (rho + rho_z), 0.5 * (rho - rho_z));
+          const double vp = w * xc.va, vm = w * xc.vb;
+          wv = 0.5 * (vp + vm);
+          wvz = 0.5 * (vp - vm);
+          eps = xc.eps;
+        }
+        if (include_wd && h == 0) wf_out[tile.pt_off + p] = eps * (rho * w);  // eps *= den * w (:396-399)
+      }
+      if (PHASE == 0) {
+        // factor rows for the assembly pass, then U: the d11 terms of the host loop are linear in grad rho, so
+        //   RKS  2 wg d11           = (2 P_sub U)_mu,          U   = 2 wg sum_a (d rho / da) dB/da
+        //   UKS  wg d11nn + c2 (d11zn + d11nz) + c3 d11zz = (P_s U_s + P_z U_z)_mu,
+        //        U_s = sum_a (wg dn_a + c2 dm_a) dB/da,  U_z = sum_a (c2 dn_a + c3 dm_a) dB/da
+        if (h == 0 && p < tile_width(tile.npts)) {
+          F[0 * TP + p] = wv; F[1 * TP + p] = wg; F[2 * TP + p] = dx; F[3 * TP + p] = dy; F[4 * TP + p] = dz;
+          if (UKS) {
+            F[5 * TP + p] = wvz; F[6 * TP + p] = c2; F[7 * TP + p] = c3;
+            F[8 * TP + p] = mx; F[9 * TP + p] = my; F[10 * TP + p] = mz;
+          }
+        }
+        if (p < tile_width(tile.npts)) {
+          const double ux = UKS ? wg * dx + c2 * mx : 2. * wg * dx, uy = UKS ? wg * dy + c2 * my : 2. * wg * dy,
+                       uz = UKS ? wg * dz + c2 * mz : 2. * wg * dz;
+          const double vx = c2 * dx + c3 * mx, vy = c2 * dy + c3 * my, vz = c2 * dz + c3 * mz;
+          const int nbp = pad16(nbe);
+          for (int mu = h; mu < nbp; mu += 2) {
+            const size_t o = (size_t)mu * TP + swz(mu, p);
+            double us = 0., uzv = 0.;
+            if (ok && mu < nbe) {
+              const double b1 = M[ms + o], b2 = M[2 * ms + o], b3 = M[3 * ms + o];
+              us = ux * b1 + uy * b2 + uz * b3;
+              if (UKS) uzv = vx * b1 + vy * b2 + vz * b3;
+            }
+            M[(size_t)SU * ms + o] = us;
+            if (UKS) M[(size_t)(SU + 1) * ms + o] = uzv;
+          }
+        }
+      }
+    } else if (ok) {
+      wv = F[0 * TP + p]; wg = F[1 * TP + p]; dx = F[2 * TP + p]; dy = F[3 * TP + p]; dz = F[4 * TP + p];
+      if (UKS) {
+        wvz = F[5 * TP + p]; c2 = F[6 * TP + p]; c3 = F[7 * TP + p];
+        mx = F[8 * TP + p]; my = F[9 * TP + p]; mz = F[10 * TP + p];
+      }
     }
 
-    // ---- phase B
-    double acc[3] = {0., 0., 0.}, par[3] = {0., 0., 0.};
-    int cur_atom = -1;
-    auto flush = [&]() {
-      if (cur_atom < 0) return;
-      double v[3] = {acc[0], acc[1], acc[2]};
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
-      }
-      if (lane == 0) {
+    if (DO_B) {
+      // ---- phase B
+      double acc[3] = {0., 0., 0.}, par[3] = {0., 0., 0.};
+      int cur_atom = -1;
+      auto flush = [&]() {
+        if (cur_atom < 0) return;
+        double v[3] = {acc[0], acc[1], acc[2]};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          add_atom(cur_atom, c, -2. * v[c]);
-          par[c] += 2. * v[c];
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
         }
-      }
-      acc[0] = acc[1] = acc[2] = 0.;
-    };
-    for (int s = 0; s < task.nshells; ++s) {
-      const int atom = __ldg(shell_atom + __ldg(pv.task_shells + task.shell_off + s));
-      if (include_wd && atom == task.iParent) continue;
-      if (atom != cur_atom) {
-        flush();
-        cur_atom = atom;
-      }
-      if (!ok) continue;
-      const int bf0 = __ldg(pv.task_shell_bf + task.shell_off + s);
-      const int bf1 = s + 1 < task.nshells ? __ldg(pv.task_shell_bf + task.shell_off + s + 1) : nbe;
-      for (int mu = bf0 + ((bf0 ^ h) & 1); mu < bf1; mu += 2) {
-        const double xn = at(NB, mu);
-        const double xz = UKS ? at(NB + NX, mu) : 0.;
-        const double dbx = at(1, mu), dby = at(2, mu), dbz = at(3, mu);
-        const double a = UKS ? wv * xn + wvz * xz : wv * xn;
-        acc[0] = fma(a, dbx, acc[0]);
-        acc[1] = fma(a, dby, acc[1]);
-        acc[2] = fma(a, dbz, acc[2]);
-        if (GGA) {
-          const double xx = at(4, mu), xy = at(5, mu), xzz = at(6, mu), yy = at(7, mu), yz = at(8, mu), zz = at(9, mu);
-          const double d2x = xx * dx + xy * dy + xzz * dz;
-          const double d2y = xy * dx + yy * dy + yz * dz;
-          const double d2z = xzz * dx + yz * dy + zz * dz;
-          const double xnx = at(NB + 1, mu), xny = at(NB + 2, mu), xnz = at(NB + 3, mu);
-          const double d11 = dx * xnx + dy * xny + dz * xnz;
-          if (!UKS) {
-            const double g2 = 2. * wg;
-            acc[0] += g2 * (xn * d2x + dbx * d11);
-            acc[1] += g2 * (xn * d2y + dby * d11);
-            acc[2] += g2 * (xn * d2z + dbz * d11);
-          } else {
-            const double e2x = xx * mx + xy * my + xzz * mz;  // H grad M_z
-            const double e2y = xy * mx + yy * my + yz * mz;
-            const double e2z = xzz * mx + yz * my + zz * mz;
-            const double xzx = at(NB + NX + 1, mu), xzy = at(NB + NX + 2, mu), xzz_ = at(NB + NX + 3, mu);
-            const double d11nz = dx * xzx + dy * xzy + dz * xzz_;
-            const double d11zn = mx * xnx + my * xny + mz * xnz;
-            const double d11zz = mx * xzx + my * xzy + mz * xzz_;
-            // c1 (d2n xN + d11nn db) + c2 (d2z xN + d11zn db) + c2 (d2n xZ + d11nz db) + c3 (d2z xZ + d11zz db)
-            const double sx = wg * xn + c2 * xz, tx = c2 * xn + c3 * xz;  // multiply d2n resp. d2z
-            const double sd = wg * d11 + c2 * (d11zn + d11nz) + c3 * d11zz;
-            acc[0] += sx * d2x + tx * e2x + sd * dbx;
-            acc[1] += sx * d2y + tx * e2y + sd * dby;
-            acc[2] += sx * d2z + tx * e2z + sd * dbz;
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            add_atom(cur_atom, c, -2. * v[c]);
+            par[c] += 2. * v[c];
+          }
+        }
+        acc[0] = acc[1] = acc[2] = 0.;
+      };
+      for (int s = 0; s < task.nshells; ++s) {
+        const int atom = __ldg(shell_atom + __ldg(pv.task_shells + task.shell_off + s));
+        if (include_wd && atom == task.iParent) continue;
+        if (atom != cur_atom) {
+          flush();
+          cur_atom = atom;
+        }
+        if (!ok) continue;
+        const int bf0 = __ldg(pv.task_shell_bf + task.shell_off + s);
+        const int bf1 = s + 1 < task.nshells ? __ldg(pv.task_shell_bf + task.shell_off + s + 1) : nbe;
+        for (int mu = bf0 + ((bf0 ^ h) & 1); mu < bf1; mu += 2) {
+          const double xn = at(NB, mu);
+          const double xz = UKS ? at(NB + 1, mu) : 0.;
+          const double dbx = at(1, mu), dby = at(2, mu), dbz = at(3, mu);
+          double a = UKS ? wv * xn + wvz * xz : wv * xn;
+          if (GGA) a += UKS ? at(SY, mu) + at(SY + 1, mu) : at(SY, mu);  // the d11 terms, contracted by the DMMA pass
+          acc[0] = fma(a, dbx, acc[0]);
+          acc[1] = fma(a, dby, acc[1]);
+          acc[2] = fma(a, dbz, acc[2]);
+          if (GGA) {
+            const double xx = at(4, mu), xy = at(5, mu), xzz = at(6, mu), yy = at(7, mu), yz = at(8, mu), zz = at(9, mu);
+            const double d2x = xx * dx + xy * dy + xzz * dz;  // H grad rho (UKS: H grad n)
+            const double d2y = xy * dx + yy * dy + yz * dz;
+            const double d2z = xzz * dx + yz * dy + zz * dz;
+            if (!UKS) {
+              const double g2x = 2. * wg * xn;
+              acc[0] = fma(g2x, d2x, acc[0]);
+              acc[1] = fma(g2x, d2y, acc[1]);
+              acc[2] = fma(g2x, d2z, acc[2]);
+            } else {
+              const double e2x = xx * mx + xy * my + xzz * mz;  // H grad M_z
+              const double e2y = xy * mx + yy * my + yz * mz;
+              const double e2z = xzz * mx + yz * my + zz * mz;
+              // c1 d2n xN + c2 d2z xN + c2 d2n xZ + c3 d2z xZ
+              const double sx = wg * xn + c2 * xz, tx = c2 * xn + c3 * xz;  // multiply d2n resp. d2z
+              acc[0] += sx * d2x + tx * e2x;
+              acc[1] += sx * d2y + tx * e2y;
+              acc[2] += sx * d2z + tx * e2z;
+            }
           }
         }
       }
-    }
-    flush();
-    if (include_wd && lane == 0) {
+      flush();
+      if (include_wd && lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if (par[c] != 0.) add_atom(task.iParent, c, par[c]);
+        for (int c = 0; c < 3; ++c)
+          if (par[c] != 0.) add_atom(task.iParent, c, par[c]);
+      }
     }
     __syncthreads();  // part[] and s_tile are reused by the next tile
   }
-  if (smem_acc) {
+  if (DO_B && smem_acc) {
     __syncthreads();
     for (int q = tid; q < 3 * natoms; q += EG_THREADS) {
       const double v = eg_dyn[q];
@@ -588,13 +631,14 @@ void launch_collocation_hessian(const PlanView& pv, const DevTile* tiles, int nt
   collocation_hessian_kernel<<<ntiles, TP, 0, s>>>(pv, tiles, ws);
 }
 
-cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                            const double* ws, FunctionalDesc func, bool gga, bool uks, const int* shell_atom,
-                            int natoms, bool include_wd, double* wf_out, double* grad, cudaStream_t s) {
+cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm, double* ws,
+                            FunctionalDesc func, bool gga, bool uks, int phase, const int* shell_atom, int natoms,
+                            bool include_wd, double* wf_out, double* grad, cudaStream_t s) {
   if (ntiles <= 0) return cudaSuccess;
-  const size_t dyn = (size_t)3 * natoms * sizeof(double);
-  const bool smem_acc = dyn <= 160 * 1024;
-  const int ncta = std::min(ntiles, std::max(1, nsm) * (smem_acc && dyn > 64 * 1024 ? 1 : 3));
+  const bool accumulates = phase != 0;
+  const size_t dyn = accumulates ? (size_t)3 * natoms * sizeof(double) : 0;
+  const bool smem_acc = accumulates && dyn <= 96 * 1024;
+  const int ncta = std::min(ntiles, std::max(1, nsm) * 2);
   auto launch = [&](auto kern) {
     if (smem_acc && dyn > 32 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -604,8 +648,9 @@ cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles
                                                       include_wd ? 1 : 0, wf_out, grad, smem_acc ? 1 : 0);
     return cudaGetLastError();
   };
-  if (uks) return gga ? launch(exc_grad_kernel<true, true>) : launch(exc_grad_kernel<false, true>);
-  return gga ? launch(exc_grad_kernel<true, false>) : launch(exc_grad_kernel<false, false>);
+  if (!gga) return uks ? launch(exc_grad_kernel<false, true, 2>) : launch(exc_grad_kernel<false, false, 2>);
+  if (phase == 0) return uks ? launch(exc_grad_kernel<true, true, 0>) : launch(exc_grad_kernel<true, false, 0>);
+  return uks ? launch(exc_grad_kernel<true, true, 1>) : launch(exc_grad_kernel<true, false, 1>);
 }
 
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,

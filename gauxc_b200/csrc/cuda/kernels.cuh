@@ -40,13 +40,14 @@ cudaError_t launch_vxc(const CUtensorMap& tmapA, const CUtensorMap& tmapZ, const
 // EXC gradient (exc_grad.cu)
 //   Hessian collocation: ten matrices B, dx, dy, dz, xx, xy, xz, yy, yz, zz per tile
 void launch_collocation_hessian(const PlanView& pv, const DevTile* tiles, int ntiles, double* ws, cudaStream_t s);
-//   gradient assembly over tiles holding [B dx dy dz | X] (LDA) or [B dx dy dz xx xy xz yy yz zz | X Xx Xy Xz] (GGA);
+//   gradient kernel over tiles holding [B dx dy dz | X] (LDA; UKS: XN XZ; phase 2 = everything) or
+//   [B dx dy dz xx xy xz yy yz zz | X | U | Y | F] (GGA; UKS: two of each X, U, Y): phase 0 evaluates densities +
+//   functional and writes the factor rows F and U, phase 1 assembles with Y = fac U P_sub (exc_grad.cu);
 //   shell_atom: shell -> atom; include_wd: skip the parent atom's shells, give the parent the opposite sum and
 //   write wf_out[point] = w eps rho for the weight-derivative kernel; grad: 3 natoms, accumulated
-//   uks: tiles hold [.. | XN .. | XZ ..] (X of Ps and of Pz, factor 1) and func is a polarised functional
-cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,
-                            const double* ws, FunctionalDesc func, bool gga, bool uks, const int* shell_atom,
-                            int natoms, bool include_wd, double* wf_out, double* grad, cudaStream_t s);
+cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm, double* ws,
+                            FunctionalDesc func, bool gga, bool uks, int phase, const int* shell_atom, int natoms,
+                            bool include_wd, double* wf_out, double* grad, cudaStream_t s);
 //   SSF weight derivatives contracted with wf, accumulated into grad (cudaErrorInvalidConfiguration: too many atoms
 //   for the shared-memory lists)
 cudaError_t launch_ssf_weight_grad(const PlanView& pv, const DevTile* tiles, int ntiles, int* counter, int nsm,

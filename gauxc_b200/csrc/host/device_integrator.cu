@@ -1173,8 +1173,9 @@ void XCIntegrator::eval_exc_uks(int64_t m, int64_t n, const double* Ps, int64_t 
 
 // EXC gradient, RKS LDA / GGA (incore_replicated_xc_device_integrator_exc_grad.hpp:21-72, 134-270; host semantics
 // reference_replicated_xc_host_integrator_exc_grad.hpp:107-601).  Per batch: collocation gradient (LDA) / Hessian
-// (GGA) -> X = 2 P_sub A on the DMMA pipe for A = B (GGA: and the three dB) -> gradient assembly (densities,
-// functional, per-atom sums); with weight derivatives (the default, IntegratorSettingsEXC_GRAD) one more kernel
+// (GGA) -> X = 2 P_sub B on the DMMA pipe -> densities, functional [GGA: -> U = per-point combination of the dB ->
+// Y = 2 P_sub U on the DMMA pipe] -> per-atom sums (exc_grad.cu: two contractions where the reference runs four);
+// with weight derivatives (the default, IntegratorSettingsEXC_GRAD) one more kernel
 // contracts the SSF weight derivatives with w eps rho over all local points.  The 3 natoms sums are reduced over the
 // ranks on the device (the reference refuses a device reduction here: "Device Reduction + EXC Grad NYI").
 void XCIntegrator::eval_exc_grad(int64_t m, int64_t n, const double* P, int64_t ldp, double* EXC_GRAD,
@@ -1202,7 +1203,8 @@ void XCIntegrator::eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t
   cudaStream_t s = I.stream;
   const bool gga = func_->is_gga();
   const bool uks = Pz != nullptr;
-  const int nb = gga ? 10 : 4, nx = gga ? 4 : 1, nden = uks ? 2 : 1, nmat = nb + nden * nx;
+  // tile matrices: LDA [B dB | X(s)], GGA [B dB ddB | X(s) | U(s) | Y(s) | F] (exc_grad.cu)
+  const int nb = gga ? 10 : 4, nden = uks ? 2 : 1, nmat = gga ? nb + 3 * nden + 1 : nb + nden;
   I.ensure_matrices(nbf, red_->comm_size(), uks);
   CUDA_CHECK(cudaEventRecord(I.e_begin, s));
   CUDA_CHECK(cudaStreamWaitEvent(I.copy_stream, I.e_begin, 0));
@@ -1228,18 +1230,29 @@ void XCIntegrator::eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t
     if (gga) gxb::launch_collocation_hessian(pv, tl, nt, I.d_ws.p, s);
     else gxb::launch_collocation(pv, tl, nt, I.d_ws.p, true, s);
     if (ib == 0) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));  // the upload of P hides behind the collocation
-    for (int d = 0; d < nden; ++d)
-      for (int k = 0; k < nx; ++k) {
-        const int q = d * nx + k;  // X slot nb + q; queue head q of this batch
-        CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + q * nbatch + ib, sc.ncta, I.d_ws.p,
-                                     d == 0 ? I.dP.p : I.dPz.p, inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p,
-                                     b.tile_begin, s, 3, nullptr,
-                                     (size_t)k | ((size_t)(nb + q) << 16) | ((size_t)(uks ? 1 : 0) << 32)));
-      }
-    CUDA_CHECK(gxb::launch_exc_grad(pv, tl, nt, sc.d_counters.p + 8 * nbatch + ib, sc.ncta, I.d_ws.p, func_->desc, gga,
-                                    uks, plan.d_shell_center.p, natoms, include_weight_derivatives,
-                                    include_weight_derivatives ? I.d_wf.p : nullptr, I.d_grad.p, s));
-    launches += 2 + nden * nx;
+    // X = fac A P_sub on the DMMA pipe: matrix a_slot of the tile times the density d, written to x_slot; q: queue head
+    auto xpass = [&](int q, int d, int a_slot, int x_slot) {
+      CUDA_CHECK(gxb::launch_fused(I.tmapA, pv, tl, nt, sc.d_counters.p + q * nbatch + ib, sc.ncta, I.d_ws.p,
+                                   d == 0 ? I.dP.p : I.dPz.p, inbf, func_->desc, I.d_exc_part.p, I.d_nel_part.p,
+                                   b.tile_begin, s, 3, nullptr,
+                                   (size_t)a_slot | ((size_t)x_slot << 16) | ((size_t)(uks ? 1 : 0) << 32)));
+      ++launches;
+    };
+    auto gpass = [&](int q, int phase) {
+      CUDA_CHECK(gxb::launch_exc_grad(pv, tl, nt, sc.d_counters.p + q * nbatch + ib, sc.ncta, I.d_ws.p, func_->desc, gga,
+                                      uks, phase, plan.d_shell_center.p, natoms, include_weight_derivatives,
+                                      include_weight_derivatives ? I.d_wf.p : nullptr, I.d_grad.p, s));
+      ++launches;
+    };
+    for (int d = 0; d < nden; ++d) xpass(d, d, 0, nb + d);  // X(s) from B
+    if (!gga) {
+      gpass(8, 2);
+    } else {
+      gpass(8, 0);                                                               // densities, functional, U(s), F
+      for (int d = 0; d < nden; ++d) xpass(2 + d, d, nb + nden + d, nb + 2 * nden + d);  // Y(s) from U(s)
+      gpass(10, 1);                                                              // assembly
+    }
+    ++launches;  // collocation
     ++ib;
   }
   if (sc.batches.empty()) CUDA_CHECK(cudaStreamWaitEvent(s, I.e_p_ready, 0));
