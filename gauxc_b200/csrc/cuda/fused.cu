@@ -206,6 +206,10 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     const int a_ev_full = (wm * 64 + g) ^ (t << 2), a_ev_short = g ^ (t << 2);
 
     long long w_tq = 0, w_full = 0, w_full_first = 0, w_xempty = 0, w_store = 0, n_stage = 0, n_tile = 0;
+#if GXB_TIMING
+    long long b_clk[4] = {0, 0, 0, 0}, b_stage[4] = {0, 0, 0, 0};  // per tile-fill bucket (<= 32, 64, 96, 128 points)
+    long long b_wait[4] = {0, 0, 0, 0};                              // of which: waiting on any barrier
+#endif
     const long long t_begin = clock64();
     for (int it = 0;; ++it) {
       int tile_idx;
@@ -214,6 +218,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
       ++n_tile;
       const DevTile tile = tiles[tile_idx];
       const int nbe = tile.nbe;
+#if GXB_TIMING
+      const long long t_tile = clock64(), st_tile = n_stage;
+      const long long w_tile = w_full + w_full_first + w_xempty + w_store;
+      const int bucket = (tile.npts - 1) >> 5;
+#endif
       const int nk = pad16(nbe) / FK;
       const int nn = (nbe + FN - 1) / FN;
       // Short tiles (<= 64 points) would leave the wm = 1 warps idle and every sub-partition with a
@@ -335,6 +344,11 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         xph ^= 1;
         GXB_T1(w_store);
       }
+#if GXB_TIMING
+      b_clk[bucket] += clock64() - t_tile;
+      b_stage[bucket] += n_stage - st_tile;
+      b_wait[bucket] += w_full + w_full_first + w_xempty + w_store - w_tile;
+#endif
     }
 #if GXB_TIMING
     if (blockIdx.x == 0 && warp == 0 && lane == 0) {
@@ -343,6 +357,12 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
              "full(later) %.1f%% xempty %.1f%% X hand-over %.1f%%; per stage %.0f clk\n",
              n_tile, n_stage, tot, 100. * w_tq / tot, 100. * w_full_first / tot, 100. * w_full / tot, 100. * w_xempty / tot,
              100. * w_store / tot, tot / (double)(n_stage ? n_stage : 1));
+      printf("[fused fill] clk per stage by tile fill: <=32 pts %lld stages %.0f clk | <=64 %lld %.0f | <=96 %lld %.0f | <=128 %lld %.0f\n",
+             b_stage[0], b_stage[0] ? (double)b_clk[0] / b_stage[0] : 0., b_stage[1], b_stage[1] ? (double)b_clk[1] / b_stage[1] : 0.,
+             b_stage[2], b_stage[2] ? (double)b_clk[2] / b_stage[2] : 0., b_stage[3], b_stage[3] ? (double)b_clk[3] / b_stage[3] : 0.);
+      printf("[fused fillwait] barrier-wait clk per stage by tile fill: %.0f | %.0f | %.0f | %.0f\n",
+             b_stage[0] ? (double)b_wait[0] / b_stage[0] : 0., b_stage[1] ? (double)b_wait[1] / b_stage[1] : 0.,
+             b_stage[2] ? (double)b_wait[2] / b_stage[2] : 0., b_stage[3] ? (double)b_wait[3] / b_stage[3] : 0.);
     }
 #else
     (void)w_tq; (void)w_full; (void)w_full_first; (void)w_xempty; (void)w_store; (void)n_stage; (void)n_tile; (void)t_begin;
