@@ -121,16 +121,35 @@ __device__ __forceinline__ void sts4(double* p, const double (&v)[4]) {
 // rows / columns beyond the tile multiply stale-but-finite or zero-filled operands and are never read.
 // KB..KE: the 4-row K steps of the stage this warp takes (all four, or one half in the split-K mode
 // of short tiles).
-template <int MI, int KB = 0, int KE = 4>
+// PAIRED (GGA kernels): the 8 x 8 blocks of a warp tile are laid over the points / columns in PAIRS -- row g of blocks
+// 2q and 2q + 1 are the adjacent points 16 q + 2 g and 16 q + 2 g + 1, column g of the two column blocks the adjacent columns
+// 2 g and 2 g + 1 of the warp's strip -- so one LDS.128 fetches the fragments of two blocks (6 fragment loads per K step
+// instead of 10; the XOR swizzle of the tile rows only touches bits 2-3 of a column and keeps pairs together).  Ragged tiles
+// then skip whole pairs (16 points), which is what the even-count variants do anyway; the LDA kernel keeps the plain
+// mapping, whose exact odd counts in the split-K halves are worth more there.
+template <int MI, int KB = 0, int KE = 4, bool PAIRED = false>
 __device__ __forceinline__ void mma_stage(double (&acc)[8][2][2], const double* __restrict__ as,
                                           const double* __restrict__ ps, int a_ev, int a_od, int ap) {
 #pragma unroll
   for (int kk = KB; kk < KE; ++kk) {
     double a[MI], b[2];
+    if (PAIRED) {
+      static_assert(!PAIRED || (MI % 2 == 0), "paired blocks come in twos");
 #pragma unroll
-    for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * ap + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
+      for (int q = 0; q < MI / 2; ++q) {
+        const double2 v = *reinterpret_cast<const double2*>(as + kk * 4 * ap + a_ev + q * 16);
+        a[2 * q] = v.x;
+        a[2 * q + 1] = v.y;
+      }
+      const double2 w = *reinterpret_cast<const double2*>(ps + kk * 4 * P_LD);
+      b[0] = w.x;
+      b[1] = w.y;
+    } else {
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
+      for (int mi = 0; mi < MI; ++mi) a[mi] = as[kk * 4 * ap + ((mi & 1) ? a_od : a_ev) + (mi & ~1) * 8];
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) b[ni] = ps[kk * 4 * P_LD + ni * 8];
+    }
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
@@ -203,7 +222,8 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
     uint32_t ph = 0, xph = 0;
     // swizzled column of point (wm*64 + mi*8 + g) in a row with (row & 3) == t:
     // a0 ^ (mi << 3), i.e. a0 + 8*mi for even mi and (a0 ^ 8) + 8*(mi - 1) for odd mi
-    const int a_ev_full = (wm * 64 + g) ^ (t << 2), a_ev_short = g ^ (t << 2);
+    constexpr bool PAIRED = GGA;  // fragment layout of mma_stage
+    const int a_ev_full = (wm * 64 + (PAIRED ? 2 * g : g)) ^ (t << 2), a_ev_short = (PAIRED ? 2 * g : g) ^ (t << 2);
 
     long long w_tq = 0, w_full = 0, w_full_first = 0, w_xempty = 0, w_store = 0, n_stage = 0, n_tile = 0;
 #if GXB_TIMING
@@ -250,31 +270,31 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
           { GXB_T0(); mbar_wait(&S.full[s], ph); if (ks < FSTAGES) { GXB_T1(w_full_first); } else { GXB_T1(w_full); } }
           ++n_stage;
           const double* as = &S.A[s][0][0] + t * ap;
-          const double* ps = &S.P[s][t][wn * 16 + g];
+          const double* ps = &S.P[s][t][wn * 16 + (PAIRED ? 2 * g : g)];
           if (active) {
             if (!split) {
               switch (mi_var) {
-                case 4: mma_stage<8>(acc, as, ps, a_ev, a_od, ap); break;
-                case 3: mma_stage<6>(acc, as, ps, a_ev, a_od, ap); break;
-                case 2: mma_stage<4>(acc, as, ps, a_ev, a_od, ap); break;
-                default: mma_stage<2>(acc, as, ps, a_ev, a_od, ap); break;
+                case 4: mma_stage<8, 0, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                case 3: mma_stage<6, 0, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                case 2: mma_stage<4, 0, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                default: mma_stage<2, 0, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
               }
             } else if (GGA) {
               // split-K halves, row blocks rounded up to even (the GGA kernel measures faster with
               // the smaller set of variants: taxol fused 123 ms against 132 ms with exact counts)
               if (wm == 0) {
                 switch (mi_var) {
-                  case 4: mma_stage<8, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
-                  case 3: mma_stage<6, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
-                  case 2: mma_stage<4, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
-                  default: mma_stage<2, 0, 2>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 4: mma_stage<8, 0, 2, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 3: mma_stage<6, 0, 2, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 2: mma_stage<4, 0, 2, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  default: mma_stage<2, 0, 2, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
                 }
               } else {
                 switch (mi_var) {
-                  case 4: mma_stage<8, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
-                  case 3: mma_stage<6, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
-                  case 2: mma_stage<4, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
-                  default: mma_stage<2, 2, 4>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 4: mma_stage<8, 2, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 3: mma_stage<6, 2, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  case 2: mma_stage<4, 2, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
+                  default: mma_stage<2, 2, 4, PAIRED>(acc, as, ps, a_ev, a_od, ap); break;
                 }
               }
             } else if (wm == 0) {
@@ -312,7 +332,36 @@ fused_xmat_den_zmat_kernel(const __grid_constant__ TmapSet tmaps, PlanView pv,
         // hand the chunk of X to the density warps
         { GXB_T0(); mbar_wait(&S.xempty, xph ^ 1); GXB_T1(w_xempty); }
         GXB_T0();
-        if (!split) {
+        if (PAIRED) {
+          // element (mi, ni, j) of the warp tile is point 16 (mi >> 1) + 2 g + (mi & 1), column 2 (2 t + j) + ni
+          const int prow = (split ? 0 : wm * 64) + 2 * g;
+          if (!split || wm == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  *reinterpret_cast<double2*>(&S.X[wn * 16 + 2 * (2 * t + j) + ni][prow + 16 * q]) =
+                      make_double2(acc[2 * q][ni][j], acc[2 * q + 1][ni][j]);
+          }
+          if (split) {
+            // split-K: the wm = 1 partial went to shared memory first, wm = 0 adds its own on top
+            named_bar_sync(3, MMA_THREADS);
+            if (wm == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    double2* dst = reinterpret_cast<double2*>(&S.X[wn * 16 + 2 * (2 * t + j) + ni][prow + 16 * q]);
+                    const double2 o = *dst;
+                    *dst = make_double2(o.x + acc[2 * q][ni][j], o.y + acc[2 * q + 1][ni][j]);
+                  }
+            }
+          }
+        } else if (!split) {
 #pragma unroll
           for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
