@@ -1276,6 +1276,9 @@ void XCIntegrator::eval_exc_grad_(int64_t m, int64_t n, const double* P, int64_t
   stats_.last_local_work_ms = ms;
   timer_.add("XCIntegrator.LocalWork_EXC_GRAD", ms);
   stats_.kernel_launches = launches;
+  stats_.nbatches = (long long)sc.batches.size();
+  stats_.ntiles = (long long)sc.tiles.size();
+  stats_.npts = (long long)plan.npts;
 }
 
 }  // namespace GauXC

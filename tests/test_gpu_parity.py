@@ -643,3 +643,39 @@ def test_exc_grad_uks_golden_and_oracle(orc, name, func):
     assert np.abs(g0 - gr).max() < TOL
     with pytest.raises(gx.GauXCError, match="Requires A Polarized Functional"):
         rks.eval_exc_grad_uks(Ps, Pz, na)
+
+
+@pytest.mark.parametrize("name,func,uks", [("benzene_pbe0_cc-pvdz_ufg_ssf", "PBE0", False),
+                                            ("benzene_svwn5_cc-pvdz_ufg_ssf", "SVWN5", False),
+                                            ("cytosine_blyp_cc-pvdz_ufg_ssf_robust_uks", "BLYP", True)])
+def test_exc_grad_many_batches(monkeypatch, name, func, uks):
+    """The gradient with a workspace so small that the tile list is cut into many batches (one queue head per pass and
+    batch: X, U -> Y, the two gradient phases): same numbers as with one batch."""
+    if uks:
+        d = systems.golden(name)
+        atoms = [(int(Z), *xyz) for Z, xyz in zip(d["mol_Z"], d["mol_xyz"])]
+        shells = []
+        for i in range(len(d["sh_l"])):
+            n = int(d["sh_nprim"][i])
+            shells.append(dict(l=int(d["sh_l"][i]), pure=bool(d["sh_pure"][i]), exps=list(d["sh_alpha"][i, :n]),
+                               coefs=list(d["sh_coeff"][i, :n]), origin=tuple(d["sh_O"][i]), tol=1e-10))
+        P, Pz = d["DENSITY_SCALAR"], d["DENSITY_Z"]
+    else:
+        atoms, shells, P, _, _ = systems.golden_system(name)
+        Pz = None
+
+    def run():
+        _, basis, lb = make_lb(atoms, shells, "FineGrid", normalize=False, device=True)
+        gx.MolecularWeightsFactory("Device", "Default", "SSF").get_instance().modify_weights(lb)
+        integ = gx.XCIntegratorFactory("Device").get_instance(gx.Functional(func, polarized=uks), lb)
+        if uks:
+            g = integ.eval_exc_grad_uks(P, Pz, len(atoms), include_weight_derivatives=True)
+        else:
+            g = integ.eval_exc_grad(P, len(atoms), include_weight_derivatives=True)
+        return g, integ.stats()["nbatches"]
+
+    g1, b1 = run()
+    monkeypatch.setenv("GAUXC_B200_WORKSPACE_MB", "16")
+    g2, b2 = run()
+    assert b1 == 1 and b2 > 4
+    assert np.abs(g1 - g2).max() < 1e-11
