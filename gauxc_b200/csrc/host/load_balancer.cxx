@@ -100,6 +100,11 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
   auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_scr = 0, t_deal = 0; const double t_begin = tnow();
   std::vector<XCTask> local_work;
+  {
+    size_t nbatch_total = 0;
+    for (size_t a = 0; a < natoms; ++a) nbatch_total += mg_->get_grid(mol[a].Z).nbatches();
+    local_work.reserve(nbatch_total / (size_t)world_size + 64);  // grows if the deal is uneven
+  }
   std::vector<size_t> global_workload(world_size, 0);
 
   // Uniform cell list over the shell centres: a batch only tests the centres whose cell can reach its
@@ -214,6 +219,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
     const size_t nb = grid.nbatches();
     std::vector<XCTask> temp(nb);
     std::vector<char> keep(nb, 0);
+    std::vector<size_t> cost_of(nb, 0);
 
     const double t_a = tnow();
 #pragma omp parallel for schedule(dynamic, 4)
@@ -230,6 +236,7 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
         task.bfn_screening.nbe = dev_nbe[p];
         task.dist_nearest = molmeta_->dist_nearest[iAtom];
         keep[ib] = 1;
+        cost_of[ib] = task.cost(n_deriv, natoms);
         if (want[p]) {  // this rank's batch (the deal was replayed on the counts): materialise it
           task.points.resize(gb.points.size());
           for (size_t i = 0; i < gb.points.size(); ++i)
@@ -294,21 +301,32 @@ std::vector<XCTask> LoadBalancer::create_local_tasks_() const {
       task.bfn_screening.nbe = (int32_t)nbe;
       task.dist_nearest = molmeta_->dist_nearest[iAtom];
       keep[ib] = 1;
+      cost_of[ib] = task.cost(n_deriv, natoms);
     }
 
     const double t_b = tnow(); t_scr += t_b - t_a;
-    // deterministic greedy deal in batch order
+    // deterministic greedy deal in batch order.  The serial part only reads two flat arrays (cost, keep): the tasks
+    // themselves were just written by the worker threads, and pulling 1.5e6 of them through the master's cache one by
+    // one cost ~1 us each on a multi-chiplet host ((H2O)833: 1.5-2.3 s).  The owned tasks are then moved to their slots
+    // by all threads.
+    std::vector<size_t> slot(nb, (size_t)-1);
+    size_t n_mine = 0;
     for (size_t ib = 0; ib < nb; ++ib) {
       if (!keep[ib]) continue;
       auto min_it = std::min_element(global_workload.begin(), global_workload.end());
       const int64_t min_rank = std::distance(global_workload.begin(), min_it);
-      global_workload[min_rank] += temp[ib].cost(n_deriv, natoms);
+      global_workload[min_rank] += cost_of[ib];
       if (world_rank == min_rank) {
         if (device_screen_ && !want[(size_t)dev_atom_first[iAtom] + ib])
           GAUXC_GENERIC_EXCEPTION("Device LoadBalancer: replayed deal disagrees with the deal");
-        local_work.push_back(std::move(temp[ib]));
+        slot[ib] = n_mine++;
       }
     }
+    const size_t base = local_work.size();
+    local_work.resize(base + n_mine);
+#pragma omp parallel for schedule(static)
+    for (size_t ib = 0; ib < nb; ++ib)
+      if (slot[ib] != (size_t)-1) local_work[base + slot[ib]] = std::move(temp[ib]);
     t_deal += tnow() - t_b;
   }
   const double t_loop = tnow();
