@@ -156,17 +156,19 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
       const size_t nt = tasks.size();
       std::vector<std::array<double, 3>> cen(nt);
       double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+#pragma omp parallel for schedule(dynamic, 256)
       for (size_t i = 0; i < nt; ++i) {
         double c[3] = {0., 0., 0.};
         for (auto& p : tasks[i].points)
           for (int d = 0; d < 3; ++d) c[d] += p[d];
         const double inv = tasks[i].points.empty() ? 0. : 1. / double(tasks[i].points.size());
+        for (int d = 0; d < 3; ++d) cen[i][d] = c[d] * inv;
+      }
+      for (size_t i = 0; i < nt; ++i)
         for (int d = 0; d < 3; ++d) {
-          cen[i][d] = c[d] * inv;
           lo[d] = std::min(lo[d], cen[i][d]);
           hi[d] = std::max(hi[d], cen[i][d]);
         }
-      }
       auto spread = [](uint64_t x) {  // 21 bits -> every third bit
         x &= 0x1fffff;
         x = (x | x << 32) & 0x1f00000000ffffull;
@@ -187,9 +189,9 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
         key[i] = {code, i};
       }
       std::sort(key.begin(), key.end());
-      std::vector<XCTask> sorted;
-      sorted.reserve(nt);
-      for (auto& k : key) sorted.push_back(std::move(tasks[k.second]));
+      std::vector<XCTask> sorted(nt);
+#pragma omp parallel for schedule(static)
+      for (size_t i = 0; i < nt; ++i) sorted[i] = std::move(tasks[key[i].second]);
       tasks.swap(sorted);
     }
   }
@@ -215,52 +217,75 @@ static std::shared_ptr<DevicePlan> build_plan(LoadBalancer& lb) {
     shells[s] = d;
   }
 
-  size_t npts = 0;
-  for (auto& t : tasks) npts += t.points.size();
+  // flat device arrays: offsets by a serial prefix sum over the tasks, contents by all threads (146 M points and 1e6 tasks
+  // for the 2499-atom cluster: the serial version of this loop was seconds of every first call)
+  const size_t ntask = tasks.size();
+  std::vector<size_t> pt_off(ntask + 1, 0), sh_off(ntask + 1, 0), ao_off(ntask + 1, 0), tl_off(ntask + 1, 0);
+  for (size_t it = 0; it < ntask; ++it) {
+    const auto& t = tasks[it];
+    pt_off[it + 1] = pt_off[it] + t.points.size();
+    sh_off[it + 1] = sh_off[it] + t.bfn_screening.shell_list.size();
+    ao_off[it + 1] = ao_off[it] + (size_t)t.bfn_screening.nbe;
+    tl_off[it + 1] = tl_off[it] + (t.points.size() + gxb::TP - 1) / gxb::TP;
+  }
+  const size_t npts = pt_off[ntask];
   if (npts > (size_t)std::numeric_limits<int>::max()) GAUXC_GENERIC_EXCEPTION("Too Many Local Points");
+  if (ao_off[ntask] > (size_t)std::numeric_limits<int>::max() || sh_off[ntask] > (size_t)std::numeric_limits<int>::max())
+    GAUXC_GENERIC_EXCEPTION("Too Many Local Tasks");
   plan->npts = npts;
   std::vector<double> px(npts), py(npts), pz(npts), w(npts);
-  std::vector<int> task_shells, task_shell_bf, task_ao;
-  size_t off = 0;
-  for (size_t it = 0; it < tasks.size(); ++it) {
-    auto& t = tasks[it];
+  std::vector<int> task_shells(sh_off[ntask]), task_shell_bf(sh_off[ntask]), task_ao(ao_off[ntask]);
+  plan->tasks.resize(ntask);
+  plan->tiles.resize(tl_off[ntask]);
+  double f_dense = 0., sum_nbe_npts = 0.;
+  int bad_nbe = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : f_dense, sum_nbe_npts, bad_nbe)
+  for (size_t it = 0; it < ntask; ++it) {
+    const auto& t = tasks[it];
     gxb::DevTask d{};
-    d.shell_off = (int)task_shells.size();
+    d.shell_off = (int)sh_off[it];
     d.nshells = (int)t.bfn_screening.shell_list.size();
-    d.ao_off = (int)task_ao.size();
+    d.ao_off = (int)ao_off[it];
     d.nbe = t.bfn_screening.nbe;
-    d.pt_off = (int)off;
+    d.pt_off = (int)pt_off[it];
     d.npts = (int)t.points.size();
     d.iParent = t.iParent;
     int bf = 0;
-    for (int s : t.bfn_screening.shell_list) {
-      task_shells.push_back(s);
-      task_shell_bf.push_back(bf);
-      const auto r = bmap.shell_to_ao_range[s];
-      for (int a = r.first; a < r.second; ++a) task_ao.push_back(a);
+    size_t q = sh_off[it], a_out = ao_off[it];
+    for (int sidx : t.bfn_screening.shell_list) {
+      task_shells[q] = sidx;
+      task_shell_bf[q] = bf;
+      ++q;
+      const auto r = bmap.shell_to_ao_range[sidx];
+      if (bf + (r.second - r.first) <= d.nbe)
+        for (int a = r.first; a < r.second; ++a) task_ao[a_out++] = a;
       bf += r.second - r.first;
     }
-    if (bf != d.nbe) GAUXC_GENERIC_EXCEPTION("Inconsistent NBE in Task");
+    if (bf != d.nbe) ++bad_nbe;
+    const size_t off = pt_off[it];
     for (size_t i = 0; i < t.points.size(); ++i) {
       px[off + i] = t.points[i][0];
       py[off + i] = t.points[i][1];
       pz[off + i] = t.points[i][2];
       w[off + i] = t.weights[i];
     }
+    size_t tl = tl_off[it];
     for (int p0 = 0; p0 < d.npts; p0 += gxb::TP) {
-      gxb::DevTile tl{};
-      tl.task = (int)it;
-      tl.pt_off = d.pt_off + p0;
-      tl.npts = std::min(gxb::TP, d.npts - p0);
-      tl.nbe = d.nbe;
-      tl.ao_off = d.ao_off;
-      plan->tiles.push_back(tl);
+      gxb::DevTile tile{};
+      tile.task = (int)it;
+      tile.pt_off = d.pt_off + p0;
+      tile.npts = std::min(gxb::TP, d.npts - p0);
+      tile.nbe = d.nbe;
+      tile.ao_off = d.ao_off;
+      plan->tiles[tl++] = tile;
     }
-    plan->f_dense += 4. * double(d.nbe) * double(d.nbe) * double(d.npts);
-    plan->sum_nbe_npts += double(d.nbe) * double(d.npts);
-    off += t.points.size();
-    plan->tasks.push_back(d);
+    f_dense += 4. * double(d.nbe) * double(d.nbe) * double(d.npts);
+    sum_nbe_npts += double(d.nbe) * double(d.npts);
+    plan->tasks[it] = d;
   }
+  if (bad_nbe) GAUXC_GENERIC_EXCEPTION("Inconsistent NBE in Task");
+  plan->f_dense = f_dense;
+  plan->sum_nbe_npts = sum_nbe_npts;
 
   std::vector<double> atoms(3 * mol.size());
   for (size_t a = 0; a < mol.size(); ++a) {
