@@ -18,8 +18,6 @@ namespace gxb {
 
 namespace {
 
-constexpr int MAX_STAGED_PRIMS = 512;
-
 // element (row, i) of a tile matrix lives at column i ^ ((row & 3) << 2) (device_plan.hpp)
 template <bool GRAD>
 __device__ __forceinline__ void store(double* __restrict__ B, size_t ms, int row, int i, bool ok,
