@@ -640,7 +640,7 @@ cudaError_t launch_exc_grad(const PlanView& pv, const DevTile* tiles, int ntiles
   const bool smem_acc = accumulates && dyn <= 96 * 1024;
   const int ncta = std::min(ntiles, std::max(1, nsm) * 2);
   auto launch = [&](auto kern) {
-    if (smem_acc && dyn > 32 * 1024) {
+    if (smem_acc) {  // static (up to 16 KB) + dynamic may pass the 48 KB default well before dyn does: always opt in
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e != cudaSuccess) return e;
     }
