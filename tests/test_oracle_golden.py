@@ -401,3 +401,41 @@ def test_exc_grad_uks_golden(orc, name, func):
         # 1e-8): like the 1.3e-9 EXC offset of these two fixtures it is independent of the functional, while the full
         # gradient -- which shares every kernel with it -- agrees to 1e-13; the benzene RKS fixtures give 2e-12 / 1e-14
         assert rms < (1e-10 if wd else 1e-8)
+
+
+@pytest.mark.parametrize("func", ["SVWN5", "PBE"])
+def test_exc_grad_full_is_the_derivative_of_exc(orc, func):
+    """Size-independent property: with the weight derivatives included, the EXC gradient is the derivative of the
+    quadrature sum EXC(R) at fixed density matrix -- grid points move with their parent atom, SSF weights and basis
+    centres follow the geometry.  Central differences of the oracle's EXC over displaced water geometries against the
+    oracle's analytic full gradient."""
+    from gauxc_b200 import systems
+    atoms0 = systems.geometry("water")
+    shells0 = systems.make_basis_shells(atoms0, "cc-pvdz", spherical=True, tol=1e-12)
+    P = systems.synthetic_density(atoms0, shells0)
+
+    def setup(atoms):
+        shells = systems.make_basis_shells(atoms, "cc-pvdz", spherical=True, tol=1e-12)
+        mol, basis, lb = make_lb(atoms, shells, "FineGrid", "Unpruned", normalize=True)
+        tasks = lb.export_tasks()
+        coords = np.array([a[1:] for a in atoms])
+        tasks["weights"] = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"],
+                                           tasks["points"], tasks["weights"])
+        return basis, tasks, coords
+
+    basis, tasks, coords = setup(atoms0)
+    g = orc.exc_grad(basis.flat(), shell_centers(atoms0, basis), coords, basis.nbf(), P, tasks, func,
+                     include_weight_derivatives=True)
+    h = 1e-4
+    for ia, c in ((0, 1), (1, 0), (2, 2)):
+        e = []
+        for sgn in (+1, -1):
+            atoms = [list(a) for a in atoms0]
+            atoms[ia][1 + c] += sgn * h
+            atoms = [tuple(a) for a in atoms]
+            b, t, _ = setup(atoms)
+            e.append(orc.exc_vxc(b.flat(), b.nbf(), P, t, func)["exc"])
+        fd = (e[0] - e[1]) / (2 * h)
+        print(func, "atom", ia, "xyz"[c], "analytic", g[ia, c], "finite difference", fd)
+        # measured agreement 1e-9 (h^2 truncation + the displaced geometries' slightly different screened task lists)
+        assert abs(fd - g[ia, c]) < 1e-7
