@@ -121,10 +121,17 @@ static double default_atomic_radius(int64_t Z) {
 }
 
 double default_radial_scaling_factor(RadialQuad rq, int64_t Z) {
-  // src/molgrid_defaults.cxx:52-71 (MuraKnowles), :118-122 (MurrayHandyLaming)
-  if (rq == RadialQuad::MurrayHandyLaming) return default_atomic_radius(Z) * (Z != 1 ? 0.5 : 1.0);
-  if (rq != RadialQuad::MuraKnowles)
-    GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path (MuraKnowles, MurrayHandyLaming)");
+  // src/molgrid_defaults.cxx:52-71 (MuraKnowles), :73-116 (TreutlerAhlrichs), :118-128 (MurrayHandyLaming, Becke)
+  if (rq == RadialQuad::MurrayHandyLaming || rq == RadialQuad::Becke)
+    return default_atomic_radius(Z) * (Z != 1 ? 0.5 : 1.0);
+  if (rq == RadialQuad::TreutlerAhlrichs) {
+    static const double xi[37] = {0,   0.8, 0.9, 1.8, 1.4, 1.3, 1.1, 0.9, 0.9, 0.9, 0.9, 1.4, 1.3,
+                                  1.3, 1.2, 1.1, 1.0, 1.0, 1.0, 1.5, 1.4, 1.3, 1.2, 1.2, 1.2, 1.2,
+                                  1.2, 1.2, 1.1, 1.1, 1.1, 1.1, 1.0, 0.9, 0.9, 0.9, 0.9};
+    if (Z < 1 || Z > 36) GAUXC_GENERIC_EXCEPTION("Z > 36 Not Supported for TA Quadrature");
+    return xi[Z];
+  }
+  if (rq != RadialQuad::MuraKnowles) GAUXC_GENERIC_EXCEPTION("Radial Quadrature Not Recognized");
   switch (Z) {
     case 3: case 4: case 11: case 12: case 19: case 20:
     case 37: case 38: case 55: case 56: case 87: case 88:
@@ -198,10 +205,34 @@ PrunedAtomicGridSpecification create_pruned_spec(PruningScheme scheme,
 // against the raw points of tests/ref_data/benzene_weights_ssf.hdf5):
 //   x_i = i/(n+1), r_i = -R ln(1-x_i^3), w_i = 3 R x_i^2/(1-x_i^3)/(n+1) * r_i^2
 // ---------------------------------------------------------------------------
+// Becke (J. Chem. Phys. 88, 2547) and Treutler-Ahlrichs M4 (J. Chem. Phys. 102, 346) map the Gauss-Chebyshev nodes of
+// the second kind x_i = cos(i pi / (n + 1)), weights pi / (n + 1) sin^2 / sqrt(1 - x^2) for a plain integral over
+// [-1, 1], onto r = R (1 + x) / (1 - x) resp. r = R / ln 2 (1 + x)^0.6 ln(2 / (1 - x)).  These two follow the published
+// rules; IntegratorXX (un-vendored) is the reference's implementation and no fixture of the reference holds a grid built
+// with them, so their parity is UNPINNED -- points are returned in ascending r like the other rules.
 void radial_quadrature(RadialQuad rq, int n, double R, std::vector<double>& r,
                        std::vector<double>& w) {
   r.resize(n);
   w.resize(n);
+  if (rq == RadialQuad::Becke || rq == RadialQuad::TreutlerAhlrichs) {
+    const double pi = 3.14159265358979323846, ln2 = 0.69314718055994530942;
+    for (int i = 1; i <= n; ++i) {
+      const double th = pi * double(i) / double(n + 1);
+      const double x = std::cos(th), wx = pi / double(n + 1) * std::sin(th);  // sin^2 / sqrt(1 - x^2) = sin
+      double ri, dr;
+      if (rq == RadialQuad::Becke) {
+        ri = R * (1. + x) / (1. - x);
+        dr = 2. * R / ((1. - x) * (1. - x));
+      } else {
+        const double a = 0.6, p = std::pow(1. + x, a), lg = std::log(2. / (1. - x));
+        ri = R / ln2 * p * lg;
+        dr = R / ln2 * p * (a * lg / (1. + x) + 1. / (1. - x));
+      }
+      r[n - i] = ri;  // x descends with i: store in ascending r
+      w[n - i] = wx * dr * ri * ri;
+    }
+    return;
+  }
   for (int i = 1; i <= n; ++i) {
     const double x = double(i) / double(n + 1);
     double ri, dr;
@@ -214,7 +245,7 @@ void radial_quadrature(RadialQuad rq, int n, double R, std::vector<double>& r,
       ri = R * x * x / (omx * omx);
       dr = 2. * R * x / (omx * omx * omx);
     } else {
-      GAUXC_GENERIC_EXCEPTION("Radial Quadrature NYI in B200 path");
+      GAUXC_GENERIC_EXCEPTION("Radial Quadrature Not Recognized");
     }
     r[i - 1] = ri;
     w[i - 1] = dr / double(n + 1) * ri * ri;

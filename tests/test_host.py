@@ -253,3 +253,33 @@ def test_synthetic_density_is_deterministic_and_symmetric():
     assert np.linalg.eigvalsh(P1).min() > 0
     assert abs(np.trace(P1) - (5.0 + 0.02 * 24)) < 1e-12  # 10 electrons / 2 + floor
     assert len(systems.water_cluster(833)) == 2499
+
+
+@pytest.mark.parametrize("rq,R", [("Becke", 0.66), ("TreutlerAhlrichs", 1.1), ("MurrayHandyLaming", 0.66),
+                                  ("MuraKnowles", 5.0)])
+def test_radial_rules_integrate_known_functions(rq, R):
+    """Every radial rule of src/grid_factory.cxx:35-141 (weights include r^2): int_0^inf r^2 e^{-a r^2} dr =
+    sqrt(pi) / (4 a^1.5) and int r^2 e^{-2 r} dr = 1/4 (a hydrogen 1s density) -- Becke and Treutler-Ahlrichs follow the
+    published rules (IntegratorXX is un-vendored and no fixture of the reference pins them: parity unpinned)."""
+    r, w = capi.radial(rq, 99, R)
+    assert np.all(np.diff(r) > 0) and np.all(w > 0)
+    for a in (0.3, 1.0, 4.0):
+        assert abs((w * np.exp(-a * r * r)).sum() / (np.sqrt(np.pi) / (4 * a ** 1.5)) - 1) < 1e-9
+    assert abs((w * np.exp(-2 * r)).sum() / 0.25 - 1) < 1e-8
+
+
+def test_molgrid_with_every_radial_rule_integrates_a_gaussian_density():
+    """gauxc_molgrid_new_default accepts all four radial quadratures of the reference's enum: the unpartitioned grid of
+    a single oxygen atom (Lebedev-590 x 99 radial points) integrates a normalised Gaussian centred on it."""
+    atoms = [(8, 0.1, -0.2, 0.3)]
+    shells = systems.make_basis_shells(atoms, "cc-pvdz", tol=1e-14)
+    for rq in ("Becke", "TreutlerAhlrichs", "MurrayHandyLaming", "MuraKnowles"):
+        mol = gx.Molecule(atoms)
+        basis = gx.BasisSet(shells, normalize=True)
+        mg = gx.MolGrid(mol, "Unpruned", 512, rq, "UltraFineGrid")
+        rt = gx.RuntimeEnvironment(device=False)
+        lb = gx.LoadBalancerFactory("Host", "Replicated").get_instance(rt, mol, mg, basis)
+        t = lb.export_tasks()
+        d2 = ((t["points"] - np.array(atoms[0][1:])) ** 2).sum(1)
+        rho = (1.3 / np.pi) ** 1.5 * np.exp(-1.3 * d2)
+        assert abs((t["weights"] * rho).sum() - 1.0) < 1e-8, rq
