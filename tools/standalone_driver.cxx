@@ -6,7 +6,7 @@
 //   [GAUXC]
 //   ref_file = benzene_svwn5_cc-pvdz_ufg_ssf.hdf5     required: /MOLECULE, /BASIS, /DENSITY (RKS) or
 //                                                     /DENSITY_SCALAR + /DENSITY_Z (UKS), optional /EXC, /VXC...
-//   grid = UltraFine | Fine | SuperFine | GM3 | GM5     rad_quad = MuraKnowles | MurrayHandyLaming
+//   grid = UltraFine | Fine | SuperFine | GM3 | GM5     rad_quad = MuraKnowles | MurrayHandyLaming | Becke | TreutlerAhlrichs (MK, MHL, TA)
 //   pruning_scheme = Unpruned | Robust | Treutler        batch_size = 512       basis_tol = 1e-10
 //   func = PBE0 | SVWN5 | PBE | BLYP | B3LYP | ...       integrate_vxc / integrate_den / integrate_exc_grad = TRUE|FALSE
 //   lb_exec_space / int_exec_space / integrator_kernel / lwd_kernel / reduction_kernel as in the reference
@@ -179,7 +179,10 @@ int main(int argc, char** argv) {
     const std::map<std::string, RadialQuad> rq_map = {{"BECKE", RadialQuad::Becke},
                                                       {"MURAKNOWLES", RadialQuad::MuraKnowles},
                                                       {"TREUTLERAHLRICHS", RadialQuad::TreutlerAhlrichs},
-                                                      {"MURRAYHANDYLAMING", RadialQuad::MurrayHandyLaming}};
+                                                      {"MURRAYHANDYLAMING", RadialQuad::MurrayHandyLaming},
+                                                      {"MK", RadialQuad::MuraKnowles},
+                                                      {"TA", RadialQuad::TreutlerAhlrichs},
+                                                      {"MHL", RadialQuad::MurrayHandyLaming}};
     const std::map<std::string, ExecutionSpace> ex_map = {{"HOST", ExecutionSpace::Host}, {"DEVICE", ExecutionSpace::Device}};
 
     // ---- molecule, basis (hdf5_read.cxx records), densities ----
