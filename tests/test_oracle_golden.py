@@ -439,3 +439,39 @@ def test_exc_grad_full_is_the_derivative_of_exc(orc, func):
         print(func, "atom", ia, "xyz"[c], "analytic", g[ia, c], "finite difference", fd)
         # measured agreement 1e-9 (h^2 truncation + the displaced geometries' slightly different screened task lists)
         assert abs(fd - g[ia, c]) < 1e-7
+
+
+def test_exc_grad_uks_full_is_the_derivative_of_exc(orc):
+    """The same property for UKS (BLYP, Pz != 0): central differences of the oracle's UKS EXC against its analytic
+    full gradient."""
+    from gauxc_b200 import systems
+    atoms0 = systems.geometry("water")
+    shells0 = systems.make_basis_shells(atoms0, "cc-pvdz", spherical=True, tol=1e-12)
+    Ps = 2.0 * systems.synthetic_density(atoms0, shells0)
+    rng = np.random.default_rng(11)
+    D = rng.standard_normal(Ps.shape) * 0.02
+    Pz = 0.1 * Ps + 0.5 * (D + D.T)
+
+    def setup(atoms):
+        shells = systems.make_basis_shells(atoms, "cc-pvdz", spherical=True, tol=1e-12)
+        mol, basis, lb = make_lb(atoms, shells, "FineGrid", "Unpruned", normalize=True)
+        tasks = lb.export_tasks()
+        coords = np.array([a[1:] for a in atoms])
+        tasks["weights"] = orc.ssf_weights(coords, tasks["npts"], tasks["iParent"], tasks["dist_nearest"],
+                                           tasks["points"], tasks["weights"])
+        return basis, tasks, coords
+
+    basis, tasks, coords = setup(atoms0)
+    g = orc.exc_grad_uks(basis.flat(), shell_centers(atoms0, basis), coords, basis.nbf(), Ps, Pz, tasks, "BLYP",
+                         include_weight_derivatives=True)
+    h = 1e-4
+    for ia, c in ((0, 1), (2, 0)):
+        e = []
+        for sgn in (+1, -1):
+            atoms = [list(a) for a in atoms0]
+            atoms[ia][1 + c] += sgn * h
+            b, t, _ = setup([tuple(a) for a in atoms])
+            e.append(orc.exc_vxc_uks(b.flat(), b.nbf(), Ps, Pz, t, "BLYP")["exc"])
+        fd = (e[0] - e[1]) / (2 * h)
+        print("UKS BLYP atom", ia, "xyz"[c], "analytic", g[ia, c], "finite difference", fd)
+        assert abs(fd - g[ia, c]) < 1e-7
