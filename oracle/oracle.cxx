@@ -583,8 +583,50 @@ void shell_at_point(const Basis& B, int s, const double* p, bool grad, double* v
   }
 }
 
+// The reference's own collocation backend: gau2grid, compiled from the reference tree into oracle/_ref/libgau2grid.so
+// (oracle/Makefile).  When loaded (oracle_init_gau2grid -- the CPU-baseline / --impl reference legs of bench.py do),
+// collocation() makes exactly the calls of gau2grid_collocation[_gradient]
+// (local_work_driver/host/reference/gau2grid_collocation.cxx:25-116): one gg_collocation[_deriv1] per shell into a
+// [component][point] scratch, then gg_fast_transpose into [point][component].  Otherwise the restatement above is used
+// (tests/test_oracle_golden.py checks the two against each other to 1e-14).
+typedef void (*gg_colloc_t)(int, unsigned long, const double*, unsigned long, int, const double*, const double*,
+                            const double*, int, double*);
+typedef void (*gg_deriv1_t)(int, unsigned long, const double*, unsigned long, int, const double*, const double*,
+                            const double*, int, double*, double*, double*, double*);
+typedef void (*gg_transpose_t)(unsigned long, unsigned long, const double*, double*);
+gg_colloc_t f_gg_colloc = nullptr;
+gg_deriv1_t f_gg_deriv1 = nullptr;
+gg_transpose_t f_gg_transpose = nullptr;
+bool use_gau2grid = false;
+
 void collocation(const Basis& B, int nsh, const int32_t* shell_list, int npts, const double* pts, int nbe,
                  bool grad, double* ev, double* dx, double* dy, double* dz) {
+  if (use_gau2grid && f_gg_colloc && npts > 0 && nbe > 0) {
+    const size_t nn = (size_t)npts * nbe;
+    static thread_local std::vector<double> rv;
+    rv.resize((grad ? 4 : 1) * nn);
+    double *r0 = rv.data(), *rx = r0 + nn, *ry = rx + nn, *rz = ry + nn;
+    size_t ncomp = 0;
+    for (int q = 0; q < nsh; ++q) {
+      const int s = shell_list[q];
+      const int order = B.pure[s] ? 300 : 400;  // GG_SPHERICAL_CCA / GG_CARTESIAN_CCA
+      const size_t ioff = ncomp * npts;
+      if (grad)
+        f_gg_deriv1(B.l[s], (unsigned long)npts, pts, 3, B.nprim[s], B.coeff + 32 * s, B.alpha + 32 * s, B.origin + 3 * s,
+                    order, r0 + ioff, rx + ioff, ry + ioff, rz + ioff);
+      else
+        f_gg_colloc(B.l[s], (unsigned long)npts, pts, 3, B.nprim[s], B.coeff + 32 * s, B.alpha + 32 * s, B.origin + 3 * s,
+                    order, r0 + ioff);
+      ncomp += B.size(s);
+    }
+    f_gg_transpose(ncomp, (unsigned long)npts, r0, ev);
+    if (grad) {
+      f_gg_transpose(ncomp, (unsigned long)npts, rx, dx);
+      f_gg_transpose(ncomp, (unsigned long)npts, ry, dy);
+      f_gg_transpose(ncomp, (unsigned long)npts, rz, dz);
+    }
+    return;
+  }
   for (int i = 0; i < npts; ++i) {
     int off = 0;
     for (int q = 0; q < nsh; ++q) {
@@ -596,7 +638,6 @@ void collocation(const Basis& B, int nsh, const int32_t* shell_list, int npts, c
     }
   }
 }
-
 
 // values, gradient and Hessian (xx,xy,xz,yy,yz,zz) of one shell at one point: the semantics of gau2grid
 // gg_collocation_deriv2 as called by gau2grid_collocation_hessian
@@ -721,6 +762,20 @@ const char* oracle_init_blas(const char* path_hint) {
     }
   }
   return blas_name;
+}
+
+// loads oracle/_ref/libgau2grid.so (the reference's own collocation code); returns 1 when collocation() will use it
+int oracle_init_gau2grid(const char* path, int enable) {
+  if (!f_gg_colloc && path && *path) {
+    if (void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL)) {
+      f_gg_colloc = (gg_colloc_t)dlsym(h, "gg_collocation");
+      f_gg_deriv1 = (gg_deriv1_t)dlsym(h, "gg_collocation_deriv1");
+      f_gg_transpose = (gg_transpose_t)dlsym(h, "gg_fast_transpose");
+      if (!f_gg_colloc || !f_gg_deriv1 || !f_gg_transpose) f_gg_colloc = nullptr;
+    }
+  }
+  use_gau2grid = enable && f_gg_colloc;
+  return use_gau2grid ? 1 : 0;
 }
 
 int oracle_num_threads() {

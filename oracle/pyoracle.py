@@ -66,6 +66,17 @@ def init_blas():
     return lib().oracle_init_blas(find_blas().encode()).decode()
 
 
+def init_gau2grid(enable=True):
+    """Collocation through the reference's own gau2grid (oracle/_ref/libgau2grid.so) when it was built: the calls of
+    gau2grid_collocation[_gradient].  Returns True if it is in use.  bench.py's CPU legs switch it on; the parity tests
+    keep the restatement and check the two against each other."""
+    p = os.path.join(_HERE, "_ref", "libgau2grid.so")
+    L = lib()
+    L.oracle_init_gau2grid.restype = C.c_int
+    L.oracle_init_gau2grid.argtypes = [C.c_char_p, C.c_int]
+    return bool(L.oracle_init_gau2grid(p.encode() if os.path.exists(p) else b"", int(bool(enable))))
+
+
 def num_threads():
     return lib().oracle_num_threads()
 

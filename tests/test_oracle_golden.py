@@ -475,3 +475,22 @@ def test_exc_grad_uks_full_is_the_derivative_of_exc(orc):
         fd = (e[0] - e[1]) / (2 * h)
         print("UKS BLYP atom", ia, "xyz"[c], "analytic", g[ia, c], "finite difference", fd)
         assert abs(fd - g[ia, c]) < 1e-7
+
+
+def test_oracle_with_the_references_gau2grid_collocation(orc, benzene_golden):
+    """oracle_init_gau2grid: the oracle's EXC/VXC driver with collocation done by the reference's own gau2grid (the exact
+    calls of gau2grid_collocation_gradient) instead of the restatement -- same EXC / VXC to rounding.  (Timed on the
+    build host, gau2grid at -O3 -march=x86-64-v3: taxol PBE sample 2.6 s against 1.8 s for the restatement, ubiquitin
+    SVWN5 6.1 s against 6.7 s: the CPU baseline of bench.py keeps the restatement, which does not understate it.)"""
+    if orc.gau2grid() is None:
+        pytest.skip("oracle/_ref/libgau2grid.so not built (reference tree absent)")
+    atoms, shells, P, VXC, EXC = benzene_golden("benzene_pbe0_cc-pvdz_ufg_ssf", "Unpruned")
+    mol, basis, lb = make_lb(atoms, shells, "FineGrid", "Unpruned", normalize=False)
+    tasks = lb.export_tasks()
+    a = orc.exc_vxc(basis.flat(), basis.nbf(), P, tasks, "PBE0")
+    try:
+        assert orc.init_gau2grid(True)
+        b = orc.exc_vxc(basis.flat(), basis.nbf(), P, tasks, "PBE0")
+    finally:
+        orc.init_gau2grid(False)
+    assert abs(a["exc"] - b["exc"]) < 1e-11 and np.abs(a["vxc"] - b["vxc"]).max() < 1e-12
